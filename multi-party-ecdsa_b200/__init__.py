@@ -1,0 +1,158 @@
+"""multi-party-ecdsa_b200 — host-side mirror of the reference's arithmetic surface over the
+B200 C-ABI library (include/tecdsa_b200.h).
+
+The reference (ZenGo-X/multi-party-ecdsa) is Rust and its seam is the curv-kzen
+`BigInt` / kzen-paillier trait surface; there is no Rust toolchain in this image, so this
+module is the thin host layer the tests and the bench drive: same operation names and
+argument meaning (`mod_pow(base, exponent, modulus)` = `BigInt::mod_pow`,
+/root/reference/src/utilities/mta/range_proofs.rs:52), batched over the leading axis.
+It only packs limbs and calls the shared library through ctypes — there is NO CPU
+arithmetic fallback here: if the CUDA library is missing or no GPU is present every call
+raises.  (The directory name has a hyphen; import it with `load_package()` from
+__graft_entry__.py or tests/conftest.py, which registers it as `mpecdsa_b200`.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtecdsa_b200.so")
+
+HOST, DEVICE = 0, 1
+ST_OK, ST_EVEN_MODULUS, ST_INVALID_KEY, ST_RANGE, ST_NOT_INVERTIBLE, ST_HASH_MISMATCH = 0, 1, 2, 3, 4, 5
+ST_PDL_VERIFY, ST_PHASE5_BAD_SUM, ST_PHASE6, ST_INVALID_SIG, ST_PROOF, ST_COMMITMENT = 6, 7, 8, 9, 10, 11
+
+# every symbol include/tecdsa_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "tecdsa_ctx_create", "tecdsa_ctx_destroy", "tecdsa_ctx_sync", "tecdsa_last_error", "tecdsa_ctx_set_tpi",
+    "tecdsa_ctx_last_kernel_ms", "tecdsa_ctx_launch_count", "tecdsa_modexp_batch", "tecdsa_imad_peak",
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the in-tree CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} not built — run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.tecdsa_last_error.restype = ctypes.c_char_p
+        lib.tecdsa_ctx_launch_count.restype = ctypes.c_uint64
+        lib.tecdsa_ctx_launch_count.argtypes = [ctypes.c_void_p]
+        lib.tecdsa_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]
+        lib.tecdsa_ctx_destroy.argtypes = [ctypes.c_void_p]
+        lib.tecdsa_ctx_sync.argtypes = [ctypes.c_void_p]
+        lib.tecdsa_ctx_set_tpi.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        lib.tecdsa_ctx_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
+        lib.tecdsa_modexp_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        lib.tecdsa_imad_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
+        _lib = lib
+    return _lib
+
+
+# ----------------------------------------------------------------------------- limb packing
+def ints_to_limbs(vals: Sequence[int], k: int) -> np.ndarray:
+    """Python ints -> (len, k) uint32 little-endian limb rows (the ABI's operand-major layout)."""
+    buf = b"".join(int(v).to_bytes(4 * k, "little") for v in vals)
+    return np.frombuffer(buf, dtype="<u4").reshape(len(vals), k).copy()
+
+
+def limbs_to_ints(a: np.ndarray) -> List[int]:
+    a = np.ascontiguousarray(a, dtype="<u4")
+    return [int.from_bytes(a[i].tobytes(), "little") for i in range(a.shape[0])]
+
+
+def _ptr(a) -> Optional[int]:
+    """Address of a numpy array (host) or torch tensor (host or device)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return a.data_ptr()            # torch.Tensor
+
+
+class Engine:
+    """One engine context = one GPU + one stream (tecdsa_ctx)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        self._ctx = ctypes.c_void_p()
+        rc = self.lib.tecdsa_ctx_create(ctypes.byref(self._ctx), device, stream)
+        if rc != 0:
+            raise EngineError(f"tecdsa_ctx_create: {self.lib.tecdsa_last_error().decode()} (rc={rc})")
+        self.device = device
+
+    def close(self):
+        if self._ctx:
+            self.lib.tecdsa_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what}: {self.lib.tecdsa_last_error().decode()} (rc={rc})")
+
+    def sync(self):
+        self._ck(self.lib.tecdsa_ctx_sync(self._ctx), "sync")
+
+    def set_tpi(self, mod_bits: int, tpi: int):
+        self._ck(self.lib.tecdsa_ctx_set_tpi(self._ctx, mod_bits, tpi), "set_tpi")
+
+    def last_kernel_ms(self):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        self._ck(self.lib.tecdsa_ctx_last_kernel_ms(self._ctx, ctypes.byref(ms), ctypes.byref(n)), "last_kernel_ms")
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.tecdsa_ctx_launch_count(self._ctx))
+
+    def imad_peak(self):
+        """(MAC32/s, ms) of the integer multiply-add saturation micro-benchmark."""
+        v, ms = ctypes.c_double(), ctypes.c_float()
+        self._ck(self.lib.tecdsa_imad_peak(self._ctx, ctypes.byref(v), ctypes.byref(ms)), "imad_peak")
+        return v.value, ms.value
+
+    # ---- BigInt::mod_pow, batched -------------------------------------------------------
+    def modexp_raw(self, mod_bits: int, exp_limbs: int, base, exp, modulus, out, status=None, mod_idx=None,
+                   n_mod: int = 0, count: Optional[int] = None, mem: int = HOST):
+        """Direct ABI call on caller buffers (numpy for HOST, torch CUDA tensors for DEVICE)."""
+        if count is None:
+            count = base.shape[0]
+        self._ck(self.lib.tecdsa_modexp_batch(self._ctx, mod_bits, exp_limbs, _ptr(base), _ptr(exp), _ptr(modulus),
+                                              _ptr(mod_idx), n_mod, _ptr(out), _ptr(status), count, mem), "modexp_batch")
+
+    def mod_pow(self, base: Iterable[int], exponent: Iterable[int], modulus: Iterable[int], mod_bits: int = 2048,
+                exp_bits: Optional[int] = None):
+        """Batched `BigInt::mod_pow(base, exponent, modulus)`; returns (results, status)."""
+        base, exponent, modulus = list(base), list(exponent), list(modulus)
+        n = len(base)
+        if n == 0:
+            return [], np.zeros(0, dtype=np.uint8)
+        k = mod_bits // 32
+        if exp_bits is None:
+            exp_bits = max(1, max(int(e).bit_length() for e in exponent))
+        el = (exp_bits + 31) // 32
+        b, e, m = ints_to_limbs(base, k), ints_to_limbs(exponent, el), ints_to_limbs(modulus, k)
+        out = np.zeros_like(b)
+        st = np.full(n, 255, dtype=np.uint8)
+        self.modexp_raw(mod_bits, el, b, e, m, out, st)
+        return limbs_to_ints(out), st

@@ -1,0 +1,270 @@
+// C ABI of the engine (see include/tecdsa_b200.h).  Host side: context, workspace,
+// staging of host buffers, launch geometry.  No torch types, no CPU arithmetic fallback:
+// if CUDA is unavailable every entry point fails with TECDSA_E_CUDA.
+#include "../../include/tecdsa_b200.h"
+#include "modexp.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+using namespace tecdsa;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+    return code;
+}
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return fail(TECDSA_E_CUDA, #call, _e);   \
+    } while (0)
+
+struct tecdsa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    uint64_t launches = 0;
+    int tpi[3] = {0, 0, 0};   // 1024, 2048, 4096
+};
+
+static int ws_reserve(tecdsa_ctx* c, size_t bytes) {
+    if (bytes <= c->ws_bytes) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->ws) CK(cudaFree(c->ws));
+    c->ws = nullptr; c->ws_bytes = 0;
+    size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc(&c->ws, want);
+    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&c->ws, want); }
+    if (e != cudaSuccess) return fail(TECDSA_E_NOMEM, "cudaMalloc(workspace)", e);
+    c->ws_bytes = want;
+    return 0;
+}
+struct Bump {
+    char* p; size_t off = 0;
+    explicit Bump(char* base) : p(base) {}
+    template <typename T> T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* r = reinterpret_cast<T*>(p + off);
+        off += n * sizeof(T);
+        return r;
+    }
+};
+static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+
+extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
+    if (!out) return fail(TECDSA_E_ARG, "ctx_create: null out");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(TECDSA_E_ARG, "ctx_create: bad device");
+    CK(cudaSetDevice(device));
+    tecdsa_ctx* c = new tecdsa_ctx();
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; }
+    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+extern "C" int tecdsa_ctx_destroy(tecdsa_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->ws) { cudaMemsetAsync(c->ws, 0, c->ws_bytes, c->stream); cudaStreamSynchronize(c->stream); cudaFree(c->ws); }
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+extern "C" int tecdsa_ctx_sync(tecdsa_ctx* c) {
+    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" const char* tecdsa_last_error(void) { return g_err.c_str(); }
+extern "C" int tecdsa_ctx_set_tpi(tecdsa_ctx* c, int mod_bits, int tpi) {
+    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+    int slot = mod_bits == 1024 ? 0 : mod_bits == 2048 ? 1 : mod_bits == 4096 ? 2 : -1;
+    if (slot < 0) return fail(TECDSA_E_ARG, "set_tpi: mod_bits must be 1024/2048/4096");
+    if (tpi != 0 && tpi != 4 && tpi != 8 && tpi != 16 && tpi != 32) return fail(TECDSA_E_ARG, "set_tpi: tpi must be 0/4/8/16/32");
+    c->tpi[slot] = tpi;
+    return 0;
+}
+extern "C" int tecdsa_ctx_last_kernel_ms(tecdsa_ctx* c, float* ms, int* launches) {
+    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+    CK(cudaEventSynchronize(c->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    c->last_ms = t;
+    if (ms) *ms = t;
+    if (launches) *launches = c->last_launches;
+    return 0;
+}
+extern "C" uint64_t tecdsa_ctx_launch_count(tecdsa_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------ modexp
+template <int K, int TPI>
+static cudaError_t launch_modexp(cudaStream_t s, const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
+                                 const uint32_t* mod_idx, uint32_t* out, uint8_t* status, uint32_t* table,
+                                 int count, int exp_limbs) {
+    constexpr int BLOCK = 128;
+    constexpr int PER_BLOCK = BLOCK / TPI;
+    int grid = (count + PER_BLOCK - 1) / PER_BLOCK;
+    modexp_kernel<K, TPI><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs);
+    return cudaGetLastError();
+}
+
+static int default_tpi(int mod_bits) { return mod_bits == 1024 ? 4 : mod_bits == 2048 ? 8 : 16; }
+
+static cudaError_t dispatch_modexp(int mod_bits, int tpi, cudaStream_t s, const uint32_t* base, const uint32_t* exp,
+                                   const uint32_t* mod, const uint32_t* mod_idx, uint32_t* out, uint8_t* status,
+                                   uint32_t* table, int count, int exp_limbs) {
+#define GO(K, T) return launch_modexp<K, T>(s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs)
+    switch (mod_bits) {
+    case 1024: switch (tpi) { case 4: GO(32, 4); case 8: GO(32, 8); case 16: GO(32, 16); default: return cudaErrorInvalidValue; }
+    case 2048: switch (tpi) { case 4: GO(64, 4); case 8: GO(64, 8); case 16: GO(64, 16); case 32: GO(64, 32); default: return cudaErrorInvalidValue; }
+    case 4096: switch (tpi) { case 8: GO(128, 8); case 16: GO(128, 16); case 32: GO(128, 32); default: return cudaErrorInvalidValue; }
+    }
+#undef GO
+    return cudaErrorInvalidValue;
+}
+
+extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, const uint32_t* base, const uint32_t* exp,
+                                   const uint32_t* modulus, const uint32_t* mod_idx, size_t n_mod, uint32_t* out,
+                                   uint8_t* status, size_t count, int mem) {
+    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+    if (mod_bits != 1024 && mod_bits != 2048 && mod_bits != 4096) return fail(TECDSA_E_UNSUPPORTED, "modexp: mod_bits must be 1024/2048/4096");
+    if (exp_limbs <= 0 || exp_limbs > 4096) return fail(TECDSA_E_ARG, "modexp: exp_limbs out of range");
+    if (count == 0) { c->last_launches = 0; return 0; }
+    if (!base || !exp || !modulus || !out) return fail(TECDSA_E_ARG, "modexp: null buffer");
+    if (mem != TECDSA_HOST && mem != TECDSA_DEVICE) return fail(TECDSA_E_ARG, "modexp: bad mem");
+    if (count > (size_t)1 << 30) return fail(TECDSA_E_ARG, "modexp: count too large");
+    CK(cudaSetDevice(c->device));
+    const int K = mod_bits / 32;
+    const int slot = mod_bits == 1024 ? 0 : mod_bits == 2048 ? 1 : 2;
+    const int tpi = c->tpi[slot] ? c->tpi[slot] : default_tpi(mod_bits);
+    if (!mod_idx) n_mod = count;
+    if (n_mod == 0) return fail(TECDSA_E_ARG, "modexp: n_mod == 0");
+
+    const size_t CHUNK = 1 << 17;                                // operands per launch (bounds the table)
+    const size_t chunk = count < CHUNK ? count : CHUNK;
+    const size_t per_block = 128 / tpi;
+    const size_t slots = ((chunk + per_block - 1) / per_block) * per_block;
+    const size_t table_words = slots * ((size_t)K << WINDOW_BITS);
+    size_t need = al(table_words * 4);
+    if (mem == TECDSA_HOST)
+        need += al(chunk * K * 4) * 2 + al(chunk * exp_limbs * 4) + al(n_mod * K * 4) + al(chunk * 4) + al(chunk) + 4096;
+    int rc = ws_reserve(c, need);
+    if (rc) return rc;
+    Bump bump(c->ws);
+    uint32_t* d_table = bump.take<uint32_t>(table_words);
+    uint32_t *d_base = nullptr, *d_exp = nullptr, *d_mod = nullptr, *d_idx = nullptr, *d_out = nullptr;
+    uint8_t* d_status = nullptr;
+    if (mem == TECDSA_HOST) {
+        d_base = bump.take<uint32_t>(chunk * K);
+        d_out = bump.take<uint32_t>(chunk * K);
+        d_exp = bump.take<uint32_t>(chunk * exp_limbs);
+        d_mod = bump.take<uint32_t>(n_mod * K);
+        d_idx = bump.take<uint32_t>(chunk);
+        d_status = bump.take<uint8_t>(chunk);
+        if (mod_idx) CK(cudaMemcpyAsync(d_mod, modulus, n_mod * K * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    int launches = 0;
+    bool first = true;
+    for (size_t off = 0; off < count; off += chunk) {
+        const size_t m = (count - off < chunk) ? count - off : chunk;
+        const uint32_t *kb, *ke, *km, *ki; uint32_t* ko; uint8_t* ks;
+        if (mem == TECDSA_HOST) {
+            CK(cudaMemcpyAsync(d_base, base + off * K, m * K * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(d_exp, exp + off * exp_limbs, m * exp_limbs * 4, cudaMemcpyHostToDevice, c->stream));
+            if (mod_idx) CK(cudaMemcpyAsync(d_idx, mod_idx + off, m * 4, cudaMemcpyHostToDevice, c->stream));
+            else CK(cudaMemcpyAsync(d_mod, modulus + off * K, m * K * 4, cudaMemcpyHostToDevice, c->stream));
+            kb = d_base; ke = d_exp; km = d_mod; ki = mod_idx ? d_idx : nullptr; ko = d_out; ks = status ? d_status : nullptr;
+        } else {
+            kb = base + off * K; ke = exp + off * exp_limbs; km = mod_idx ? modulus : modulus + off * K;
+            ki = mod_idx ? mod_idx + off : nullptr; ko = out + off * K; ks = status ? status + off : nullptr;
+        }
+        if (first) { CK(cudaEventRecord(c->ev0, c->stream)); first = false; }
+        cudaError_t e = dispatch_modexp(mod_bits, tpi, c->stream, kb, ke, km, ki, ko, ks, d_table, (int)m, exp_limbs);
+        if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? TECDSA_E_UNSUPPORTED : TECDSA_E_CUDA, "modexp launch", e);
+        launches++;
+        CK(cudaEventRecord(c->ev1, c->stream));
+        if (mem == TECDSA_HOST) {
+            CK(cudaMemcpyAsync(out + off * K, d_out, m * K * 4, cudaMemcpyDeviceToHost, c->stream));
+            if (status) CK(cudaMemcpyAsync(status + off, d_status, m, cudaMemcpyDeviceToHost, c->stream));
+            if (off + chunk < count) CK(cudaStreamSynchronize(c->stream));   // staging buffers are reused
+        }
+    }
+    c->last_launches = launches;
+    c->launches += launches;
+    if (mem == TECDSA_HOST) CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ IMAD peak
+// Eight independent 4-pair carry chains per thread per iteration = 32 IMAD.WIDE.U32(.X),
+// register pairs aligned exactly as in the Montgomery rows (bigint.cuh mad_even / mad_odd).
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
+    uint32_t a[4], acc[8][10];
+#pragma unroll
+    for (int j = 0; j < 4; j++) a[j] = seed * (threadIdx.x + 1) + j * 0x9e3779b9u;
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int j = 0; j < 10; j++) acc[r][j] = seed + r * 17 + j;
+    uint32_t b = seed ^ 0x85ebca6bu;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint32_t bb = b + r;
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[r][0]), "+r"(acc[r][1]) : "r"(a[0]), "r"(bb));
+#pragma unroll
+            for (int j = 2; j < 8; j += 2)
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[r][j]), "+r"(acc[r][j + 1]) : "r"(a[j / 2]), "r"(bb));
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(acc[r][8]));
+        }
+        b = b * 3 + 1;
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int j = 0; j < 10; j++) x ^= acc[r][j];
+    if (x == 0x12345678u) sink[0] = x;
+}
+
+extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_out) {
+    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    int rc = ws_reserve(c, 4096);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    const int iters = 1 << 14, block = 256, grid = prop.multiProcessorCount * 6;
+    imad_peak_kernel<<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u, 64);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(c->ev0, c->stream));
+        imad_peak_kernel<<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, iters);
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaEventSynchronize(c->ev1));
+        float t;
+        CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+        if (t < best) best = t;
+    }
+    CK(cudaGetLastError());
+    c->launches += 4;
+    double macs = (double)grid * block * (double)iters * 32.0;
+    if (mac32_per_s) *mac32_per_s = macs / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return 0;
+}
