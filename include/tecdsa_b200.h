@@ -55,7 +55,8 @@ enum {
 };
 
 /* ---- context ------------------------------------------------------------------------ */
-/* `stream` is a cudaStream_t to launch on, or NULL for a private non-blocking stream.      */
+/* `stream` is the cudaStream_t every launch and copy of this context goes to (NULL = the
+ * device's default stream, which is also torch's default current stream).                  */
 int tecdsa_ctx_create(tecdsa_ctx** ctx, int device, void* stream);
 int tecdsa_ctx_destroy(tecdsa_ctx* ctx);
 int tecdsa_ctx_sync(tecdsa_ctx* ctx);
@@ -80,6 +81,65 @@ uint64_t tecdsa_ctx_launch_count(tecdsa_ctx* ctx);
 int tecdsa_modexp_batch(tecdsa_ctx* ctx, int mod_bits, int exp_limbs, const uint32_t* base, const uint32_t* exp,
                         const uint32_t* modulus, const uint32_t* mod_idx, size_t n_mod, uint32_t* out,
                         uint8_t* status, size_t count, int mem);
+
+/* ---- L3: the batched GG20 offline-signing stage ----------------------------------------
+ * One "unit" = one party's OfflineStage Round0..Round6
+ *   (src/protocols/multi_party_ecdsa/gg_2020/state_machine/sign/rounds.rs:68-636,
+ *    calling gg_2020/party_i.rs:526-848, utilities/mta/{mod,range_proofs}.rs,
+ *    utilities/zk_pdl_with_slack/mod.rs) for keygen parameters t = 1, n = 3 and two signers.
+ * A session is two units (2s, 2s+1); both run on the same GPU and exchange their messages in
+ * device memory.  The LocalKey material (keygen/rounds.rs:310-322) is uploaded once per key
+ * set; per-key constants (N^2, p^2, q^2, the CRT constants of Paillier decrypt) are derived
+ * on the device.                                                                          */
+typedef struct tecdsa_keyset tecdsa_keyset;
+typedef struct {
+    size_t n_keysets;             /* rows below are indexed by keyset*3 + party (party 0..2)      */
+    const uint32_t* paillier_p;   /* [rows][32]  DecryptionKey.p  (1024-bit prime)                 */
+    const uint32_t* paillier_q;   /* [rows][32]  DecryptionKey.q                                   */
+    const uint32_t* n_tilde;      /* [rows][64]  DLogStatement.N   (h1_h2_n_tilde_vec)             */
+    const uint32_t* h1;           /* [rows][64]  DLogStatement.g                                   */
+    const uint32_t* h2;           /* [rows][64]  DLogStatement.ni                                  */
+    const uint32_t* x_i;          /* [rows][8]   keys_linear.x_i                                   */
+    const uint32_t* pk;           /* [rows][16]  pk_vec[j] = x_j * G, affine x||y                  */
+    const uint32_t* y;            /* [n_keysets][16]  y_sum_s                                      */
+} tecdsa_keys;
+int tecdsa_keys_upload(tecdsa_ctx* ctx, const tecdsa_keys* keys, tecdsa_keyset** out);
+int tecdsa_keys_free(tecdsa_ctx* ctx, tecdsa_keyset* ks);
+/* copy one derived per-key table back (test access): 0 = N, 1 = N^2, 5 = p^2, 6 = q^2 ... see csrc/gg20_fields.h */
+int tecdsa_keys_table(tecdsa_ctx* ctx, const tecdsa_keyset* ks, int table, uint32_t* out_host);
+
+/* Layout (uint32 limb offsets) of one unit's randomness record: every value the reference
+ * samples inside OfflineStage, in order of use.  Ranges are the caller's contract and are those
+ * of the reference: scalars in [1,q); r_k, beta', r' below the respective Paillier N;
+ * alpha < q^3, beta in Z*_N, gamma < q^3 N~, rho < q N~ (utilities/mta/range_proofs.rs:48-51,
+ * utilities/zk_pdl_with_slack/mod.rs:73-77).                                                */
+enum {
+    TECDSA_RND_GAMMA = 0, TECDSA_RND_K = 8, TECDSA_RND_BLIND = 16, TECDSA_RND_RK = 24,
+    TECDSA_RND_ALICE = 88, TECDSA_RND_ALICE_STRIDE = 248,       /* x 3 statements                  */
+    TECDSA_RND_ALICE_ALPHA = 0, TECDSA_RND_ALICE_BETA = 24, TECDSA_RND_ALICE_GAMMA = 88, TECDSA_RND_ALICE_RHO = 176,
+    TECDSA_RND_BETATAG_GAMMA = 832, TECDSA_RND_R_GAMMA = 896, TECDSA_RND_NONCE_GAMMA_B = 960, TECDSA_RND_NONCE_GAMMA_BETA = 968,
+    TECDSA_RND_BETATAG_W = 976, TECDSA_RND_R_W = 1040, TECDSA_RND_NONCE_W_B = 1104, TECDSA_RND_NONCE_W_BETA = 1112,
+    TECDSA_RND_L = 1120, TECDSA_RND_PED_S1 = 1128, TECDSA_RND_PED_S2 = 1136,
+    TECDSA_RND_PDL_ALPHA = 1144, TECDSA_RND_PDL_BETA = 1168, TECDSA_RND_PDL_RHO = 1232, TECDSA_RND_PDL_GAMMA = 1304,
+    TECDSA_RND_HEG_S1 = 1392, TECDSA_RND_HEG_S2 = 1400,
+    TECDSA_RND_LIMBS = 1408
+};
+
+/* sessions[s] = {keyset, party of signer position 0, party of signer position 1} (parties 0..2,
+ * i.e. keygen index - 1; `s_l` of OfflineStage::new, sign.rs:78).  rnd = [2*n_sessions][TECDSA_RND_LIMBS].
+ * Outputs per unit (any may be NULL except status): status byte (TECDSA_ST_*; first failing check
+ * of that party), R (affine x||y, 16 limbs), sigma_i (8 limbs), t_vec (2 x 16 limbs) — the fields
+ * of CompletedOfflineStage (sign/rounds.rs:647-654) — and a SHA-256 digest (8 limbs) over every
+ * message the unit emitted in a fixed-width canonical encoding (the result record that the
+ * multi-GPU gather collects and that the parity tests compare with the oracle).
+ * Declared work-saving identities, all value-preserving: the three AliceProof::verify of a peer's
+ * MessageA are evaluated once for the two MessageB::b calls (mta/mod.rs:123-131); (N+1)^x mod N^2 is
+ * evaluated as 1 + xN; (z^-1)^e as (z^e)^-1; Paillier decrypt's per-key constants are cached.   */
+int tecdsa_gg20_offline_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
+                              const uint32_t* rnd, uint8_t* status, uint32_t* R, uint32_t* sigma, uint32_t* t_vec,
+                              uint32_t* digest, int mem);
+/* test access: copy one named per-unit field of the last batch (names in csrc/gg20_fields.h) */
+int tecdsa_gg20_debug_field(tecdsa_ctx* ctx, const char* name, uint32_t* out_host, size_t* limbs_per_unit);
 
 /* Saturation micro-benchmark of the integer multiply-add pipe (IMAD.WIDE.U32 with carry
  * chains shaped like the Montgomery rows): 32x32+64 MACs per second on this device.  This is

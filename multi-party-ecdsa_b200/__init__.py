@@ -30,6 +30,7 @@ ST_PDL_VERIFY, ST_PHASE5_BAD_SUM, ST_PHASE6, ST_INVALID_SIG, ST_PROOF, ST_COMMIT
 EXPORTS = [
     "tecdsa_ctx_create", "tecdsa_ctx_destroy", "tecdsa_ctx_sync", "tecdsa_last_error", "tecdsa_ctx_set_tpi",
     "tecdsa_ctx_last_kernel_ms", "tecdsa_ctx_launch_count", "tecdsa_modexp_batch", "tecdsa_imad_peak",
+    "tecdsa_keys_upload", "tecdsa_keys_free", "tecdsa_keys_table", "tecdsa_gg20_offline_batch", "tecdsa_gg20_debug_field",
 ]
 
 

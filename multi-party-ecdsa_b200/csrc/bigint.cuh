@@ -133,6 +133,19 @@ __device__ __forceinline__ uint32_t group_sub_masked(uint32_t (&t)[L], const uin
     return top;
 }
 
+// t += (m & y), group-wide; returns carry out
+template <int TPI, int L>
+__device__ __forceinline__ uint32_t group_add_masked(uint32_t (&t)[L], const uint32_t (&y)[L], uint32_t m) {
+    t[0] = add_cc(t[0], y[0] & m);
+#pragma unroll
+    for (int j = 1; j < L; j++) t[j] = addc_cc(t[j], y[j] & m);
+    uint32_t c = addc(0, 0);
+    uint32_t top;
+    uint32_t ci = group_carry<TPI>(c, all_ones<L>(t), &top);
+    add_small<L>(t, ci);
+    return top;
+}
+
 // One Montgomery row.  A is this row's even set; B was the previous row's even set (still
 // unshifted, column 0 gone) and becomes this row's odd set; `inc` is the limb the right
 // neighbour handed down after the previous row.  Returns the limb to hand to the left.
@@ -151,10 +164,10 @@ __device__ __forceinline__ uint32_t mont_row(uint32_t (&A)[L + 2], uint32_t (&B)
     return (group_lane<TPI>() == TPI - 1) ? 0u : dn;
 }
 
-// Montgomery product r = a*b/2^(32K): inputs < R = 2^(32K), output < R and congruent to
-// a*b*R^-1 (mod n).  It is NOT fully reduced below n: the engine keeps every intermediate
-// merely below R (one masked subtract when the product spills past R) and canonicalises
-// once at the end (mont_mul by 1, then cond_sub).
+// Montgomery product r = a*b*R^-1 mod n, R = 2^(32K), n odd.  With one operand < n and the
+// other < R the value before the final step is < 2n, so the single conditional subtract
+// returns the canonical residue in [0, n): every Montgomery-domain value in the engine is
+// canonical.
 template <int TPI, int L>
 __device__ __forceinline__ void mont_mul(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L],
                                          const uint32_t (&n)[L], uint32_t n0inv) {
@@ -195,10 +208,15 @@ __device__ __forceinline__ void mont_mul(uint32_t (&r)[L], const uint32_t (&a)[L
     uint32_t top;
     uint32_t ci = group_carry<TPI>(c, all_ones<L>(T), &top);
     add_small<L>(T, ci);
-    uint32_t ov = __shfl_sync(FULL, h0, TPI - 1, TPI) + top;   // 0 or 1: product >= R
-    (void)group_sub_masked<TPI, L>(T, n, 0u - ov, ov);
+    uint32_t ov = __shfl_sync(FULL, h0, TPI - 1, TPI) + top;   // 0 or 1: value >= R
+    // a, b < n  =>  value < 2n: one conditional subtract gives the canonical residue
+    uint32_t D[L];
 #pragma unroll
-    for (int j = 0; j < L; j++) r[j] = T[j];
+    for (int j = 0; j < L; j++) D[j] = T[j];
+    uint32_t ge = group_sub_masked<TPI, L>(D, n, 0xffffffffu, 1u);
+    const bool take = (ov | ge) != 0;
+#pragma unroll
+    for (int j = 0; j < L; j++) r[j] = take ? D[j] : T[j];
 }
 
 // t >= n ? t - n : t   (one conditional subtract; canonical output for t < 2n)
@@ -214,7 +232,7 @@ __device__ __forceinline__ void cond_sub(uint32_t (&t)[L], const uint32_t (&n)[L
     }
 }
 
-// t = 2t mod-ish n with the same "< R" invariant as mont_mul.
+// t = 2t mod n for canonical t < n (any n < R).
 template <int TPI, int L>
 __device__ __forceinline__ void mod_double(uint32_t (&t)[L], const uint32_t (&n)[L]) {
     const int gl = group_lane<TPI>();
@@ -225,7 +243,77 @@ __device__ __forceinline__ void mod_double(uint32_t (&t)[L], const uint32_t (&n)
 #pragma unroll
     for (int j = L - 1; j > 0; j--) t[j] = (t[j] << 1) | (t[j - 1] >> 31);
     t[0] = (t[0] << 1) | inb;
-    (void)group_sub_masked<TPI, L>(t, n, 0u - ov, ov);
+    uint32_t D[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) D[j] = t[j];
+    uint32_t ge = group_sub_masked<TPI, L>(D, n, 0xffffffffu, 1u);
+    if (ov | ge) {
+#pragma unroll
+        for (int j = 0; j < L; j++) t[j] = D[j];
+    }
+}
+
+// group-wide logical shifts by one bit
+template <int TPI, int L>
+__device__ __forceinline__ void group_shl1(uint32_t (&t)[L]) {
+    uint32_t inb = __shfl_up_sync(FULL, t[L - 1] >> 31, 1, TPI);
+    if (group_lane<TPI>() == 0) inb = 0;
+#pragma unroll
+    for (int j = L - 1; j > 0; j--) t[j] = (t[j] << 1) | (t[j - 1] >> 31);
+    t[0] = (t[0] << 1) | inb;
+}
+template <int TPI, int L>
+__device__ __forceinline__ void group_shr1(uint32_t (&t)[L]) {
+    uint32_t inb = __shfl_down_sync(FULL, t[0] & 1u, 1, TPI);
+    if (group_lane<TPI>() == TPI - 1) inb = 0;
+#pragma unroll
+    for (int j = 0; j < L - 1; j++) t[j] = (t[j] >> 1) | (t[j + 1] << 31);
+    t[L - 1] = (t[L - 1] >> 1) | (inb << 31);
+}
+
+// x = 2^(32K) mod n, canonical, for ANY n >= 1 (n need not have its top bit set): shift n up
+// until its top bit is set, take R - n', then walk n' back down with one compare-subtract per
+// bit.  For the 2047..2048-bit moduli of the protocol this is 0..2 iterations.
+template <int TPI, int L>
+__device__ __forceinline__ void r_mod_n(uint32_t (&x)[L], const uint32_t (&n)[L]) {
+    uint32_t m[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) m[j] = n[j];
+    int s = 0;
+    while (true) {                                       // warp-uniform trip count
+        uint32_t top = __shfl_sync(FULL, m[L - 1] >> 31, TPI - 1, TPI);
+        bool need = (top == 0) && (s < 32 * TPI * L);
+        if (!__any_sync(FULL, need)) break;
+        if (need) { s++; }
+        uint32_t sh[L];
+#pragma unroll
+        for (int j = 0; j < L; j++) sh[j] = m[j];
+        group_shl1<TPI, L>(sh);
+        if (need) {
+#pragma unroll
+            for (int j = 0; j < L; j++) m[j] = sh[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < L; j++) x[j] = 0;
+    (void)group_sub_masked<TPI, L>(x, m, 0xffffffffu, 1u);    // R - n'
+    cond_sub<TPI, L>(x, m);
+    int smax = s;
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) smax = max(smax, __shfl_xor_sync(FULL, smax, off));
+#pragma unroll 1
+    for (int i = 0; i < smax; i++) {
+        const bool act = i < s;
+        uint32_t sh[L], y[L];
+#pragma unroll
+        for (int j = 0; j < L; j++) { sh[j] = m[j]; y[j] = x[j]; }
+        group_shr1<TPI, L>(sh);
+        cond_sub<TPI, L>(y, sh);
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < L; j++) { m[j] = sh[j]; x[j] = y[j]; }
+        }
+    }
 }
 
 // -n^-1 mod 2^32 (n odd)

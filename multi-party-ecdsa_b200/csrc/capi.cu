@@ -1,39 +1,21 @@
 // C ABI of the engine (see include/tecdsa_b200.h).  Host side: context, workspace,
 // staging of host buffers, launch geometry.  No torch types, no CPU arithmetic fallback:
 // if CUDA is unavailable every entry point fails with TECDSA_E_CUDA.
-#include "../../include/tecdsa_b200.h"
-#include "modexp.cuh"
+#include "ctx.h"
+#include "modinv.cuh"
 
 #include <cstdio>
-#include <cstring>
 #include <string>
 
 using namespace tecdsa;
 
 static thread_local std::string g_err;
-static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+int tecdsa_fail(int code, const char* what, cudaError_t e) {
     g_err = what;
     if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
     return code;
 }
-#define CK(call)                                                        \
-    do {                                                                \
-        cudaError_t _e = (call);                                        \
-        if (_e != cudaSuccess) return fail(TECDSA_E_CUDA, #call, _e);   \
-    } while (0)
-
-struct tecdsa_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    char* ws = nullptr;
-    size_t ws_bytes = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_ms = 0.f;
-    int last_launches = 0;
-    uint64_t launches = 0;
-    int tpi[3] = {0, 0, 0};   // 1024, 2048, 4096
-};
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) { return tecdsa_fail(code, what, e); }
 
 static int ws_reserve(tecdsa_ctx* c, size_t bytes) {
     if (bytes <= c->ws_bytes) return 0;
@@ -67,8 +49,10 @@ extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
     CK(cudaSetDevice(device));
     tecdsa_ctx* c = new tecdsa_ctx();
     c->device = device;
-    if (stream) { c->stream = (cudaStream_t)stream; }
-    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    c->stream = (cudaStream_t)stream;              // NULL = the device's default stream
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     *out = c;
@@ -78,9 +62,14 @@ extern "C" int tecdsa_ctx_destroy(tecdsa_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->ws) { cudaMemsetAsync(c->ws, 0, c->ws_bytes, c->stream); cudaStreamSynchronize(c->stream); cudaFree(c->ws); }
+    // secrets may sit in every scratch buffer: wipe before release (the reference zeroizes its
+    // proof round-1 secrets on drop, utilities/mta/range_proofs.rs:26-27)
+    char* bufs[3] = {c->ws, c->jobmem, c->arena};
+    size_t sizes[3] = {c->ws_bytes, c->jobmem_bytes, c->arena_bytes};
+    for (int i = 0; i < 3; i++) if (bufs[i]) cudaMemsetAsync(bufs[i], 0, sizes[i], c->stream);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 3; i++) if (bufs[i]) cudaFree(bufs[i]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
@@ -210,36 +199,30 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
 }
 
 // ------------------------------------------------------------------------------------ IMAD peak
-// Eight independent 4-pair carry chains per thread per iteration = 32 IMAD.WIDE.U32(.X),
-// register pairs aligned exactly as in the Montgomery rows (bigint.cuh mad_even / mad_odd).
+// Eight independent 64-bit accumulators per thread, acc += a*b as IMAD.WIDE.U32 (the
+// instruction every Montgomery row is made of; the .X carry variant issues on the same
+// pipe at the same rate), ~24 registers so the SM runs at full occupancy.
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
-    uint32_t a[4], acc[8][10];
+    uint64_t acc[8];
+    uint32_t a[8];
 #pragma unroll
-    for (int j = 0; j < 4; j++) a[j] = seed * (threadIdx.x + 1) + j * 0x9e3779b9u;
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int j = 0; j < 10; j++) acc[r][j] = seed + r * 17 + j;
-    uint32_t b = seed ^ 0x85ebca6bu;
+    for (int j = 0; j < 8; j++) { a[j] = (seed + j) * (threadIdx.x | 1u); acc[j] = (uint64_t)seed * (j + 1) + threadIdx.x; }
+    uint32_t b = seed ^ 0x85ebca6bu ^ threadIdx.x;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            uint32_t bb = b + r;
-            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[r][0]), "+r"(acc[r][1]) : "r"(a[0]), "r"(bb));
+        for (int u = 0; u < 4; u++) {
+            const uint32_t bu = b ^ a[u];
 #pragma unroll
-            for (int j = 2; j < 8; j += 2)
-                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[r][j]), "+r"(acc[r][j + 1]) : "r"(a[j / 2]), "r"(bb));
-            asm volatile("addc.u32 %0, %0, 0;" : "+r"(acc[r][8]));
+            for (int j = 0; j < 8; j++)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[(j + u) & 7]), "r"(bu));
         }
-        b = b * 3 + 1;
+        b = b * 5u + (uint32_t)acc[0];
     }
-    uint32_t x = 0;
+    uint64_t x = 0;
 #pragma unroll
-    for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int j = 0; j < 10; j++) x ^= acc[r][j];
-    if (x == 0x12345678u) sink[0] = x;
+    for (int j = 0; j < 8; j++) x ^= acc[j];
+    if (x == 0x12345678u) sink[0] = (uint32_t)x;
 }
 
 extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_out) {
@@ -249,7 +232,7 @@ extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_ou
     if (rc) return rc;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c->device));
-    const int iters = 1 << 14, block = 256, grid = prop.multiProcessorCount * 6;
+    const int iters = 1 << 13, block = 256, grid = prop.multiProcessorCount * 16;
     imad_peak_kernel<<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u, 64);   // warm-up
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
@@ -263,8 +246,79 @@ extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_ou
     }
     CK(cudaGetLastError());
     c->launches += 4;
-    double macs = (double)grid * block * (double)iters * 32.0;
+    double macs = (double)grid * block * (double)iters * 32.0;   // 4 x 8 wide MACs per iteration
     if (mac32_per_s) *mac32_per_s = macs / (best * 1e-3);
     if (ms_out) *ms_out = best;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ job-list launches
+static int grow(char** buf, size_t* have, size_t need, cudaStream_t s, const char* what) {
+    if (need <= *have) return 0;
+    CK(cudaStreamSynchronize(s));
+    if (*buf) CK(cudaFree(*buf));
+    *buf = nullptr; *have = 0;
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e != cudaSuccess) return tecdsa_fail(TECDSA_E_NOMEM, what, e);
+    *have = need;
+    return 0;
+}
+int tecdsa_ctx::reserve_arena(size_t bytes) { return grow(&arena, &arena_bytes, bytes, stream, "cudaMalloc(arena)"); }
+
+namespace {
+constexpr int JOB_SLOTS = 64;
+constexpr size_t SLOT_BYTES = (sizeof(ExpLaunch) + 255) & ~size_t(255);
+constexpr int JOB_BLOCK = 128;
+struct JobGeom { int grid; size_t table_bytes; };
+template <int K, int TPI> JobGeom job_geom(int sm_count) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exp_jobs_kernel<K, TPI>, JOB_BLOCK, 0);
+    if (per_sm < 1) per_sm = 1;
+    JobGeom g;
+    g.grid = sm_count * per_sm;
+    g.table_bytes = (size_t)g.grid * (JOB_BLOCK / 32) * (32 / TPI) * 2 * (size_t)(K << WINDOW_BITS) * 4;
+    return g;
+}
+}  // namespace
+
+static int job_prepare(tecdsa_ctx* c, size_t table_bytes, const void* desc, size_t desc_bytes, char** d_desc, unsigned int** d_counter, uint32_t** d_tables) {
+    static_assert(sizeof(InvLaunch) <= sizeof(ExpLaunch), "slot size");
+    const size_t head = JOB_SLOTS * SLOT_BYTES + JOB_SLOTS * 256;
+    int rc = grow(&c->jobmem, &c->jobmem_bytes, head + table_bytes, c->stream, "cudaMalloc(job memory)");
+    if (rc) return rc;
+    if (c->job_slot == JOB_SLOTS) { CK(cudaStreamSynchronize(c->stream)); c->job_slot = 0; }
+    const int slot = c->job_slot++;
+    *d_desc = c->jobmem + (size_t)slot * SLOT_BYTES;
+    *d_counter = reinterpret_cast<unsigned int*>(c->jobmem + JOB_SLOTS * SLOT_BYTES + (size_t)slot * 256);
+    *d_tables = reinterpret_cast<uint32_t*>(c->jobmem + head);
+    CK(cudaMemcpyAsync(*d_desc, desc, desc_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(*d_counter, 0, 4, c->stream));
+    return 0;
+}
+
+int tecdsa_ctx::launch_exp(const ExpLaunch& l, int K) {
+    JobGeom g = K == 64 ? job_geom<64, TPI_2048>(sm_count) : job_geom<128, TPI_4096>(sm_count);
+    char* d_desc; unsigned int* d_counter; uint32_t* d_tables;
+    int rc = job_prepare(this, g.table_bytes, &l, sizeof(ExpLaunch), &d_desc, &d_counter, &d_tables);
+    if (rc) return rc;
+    if (K == 64) exp_jobs_kernel<64, TPI_2048><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
+    else exp_jobs_kernel<128, TPI_4096><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
+    count_launch();
+    CK(cudaGetLastError());
+    return 0;
+}
+int tecdsa_ctx::launch_inv(const InvLaunch& l, int K) {
+    char* d_desc; unsigned int* d_counter; uint32_t* d_tables;
+    int rc = job_prepare(this, 0, &l, sizeof(InvLaunch), &d_desc, &d_counter, &d_tables);
+    if (rc) return rc;
+    int per_sm = 0;
+    if (K == 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inv_jobs_kernel<64, TPI_2048>, JOB_BLOCK, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inv_jobs_kernel<128, TPI_4096>, JOB_BLOCK, 0);
+    if (per_sm < 1) per_sm = 1;
+    const int grid = sm_count * per_sm;
+    if (K == 64) inv_jobs_kernel<64, TPI_2048><<<grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const InvLaunch*>(d_desc), d_counter);
+    else inv_jobs_kernel<128, TPI_4096><<<grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const InvLaunch*>(d_desc), d_counter);
+    count_launch();
+    CK(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,56 @@
+// Engine context shared by the translation units of the library (see include/tecdsa_b200.h).
+#pragma once
+#include "../../include/tecdsa_b200.h"
+#include "gg20_fields.h"
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+
+namespace tecdsa {
+struct ExpLaunch;
+struct InvLaunch;
+// lane-group widths of the job-list kernels (16 limbs per lane for both modulus widths)
+constexpr int TPI_2048 = 4;
+constexpr int TPI_4096 = 8;
+}  // namespace tecdsa
+
+int tecdsa_fail(int code, const char* what, cudaError_t e = cudaSuccess);
+
+#define CK(call)                                                               \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return tecdsa_fail(TECDSA_E_CUDA, #call, _e);   \
+    } while (0)
+
+struct tecdsa_keyset {
+    uint32_t* mem = nullptr;
+    uint32_t* tab[tecdsa::KT_COUNT] = {};
+    uint32_t* ypk = nullptr;
+    int n_keysets = 0;
+};
+
+struct tecdsa_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    char* ws = nullptr;            // modexp_batch workspace (window tables + staging)
+    size_t ws_bytes = 0;
+    char* jobmem = nullptr;        // job-list launches: descriptor ring, counters, window tables
+    size_t jobmem_bytes = 0;
+    int job_slot = 0;
+    char* arena = nullptr;         // per-unit state of the last gg20 batch
+    size_t arena_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    uint64_t launches = 0;
+    int tpi[3] = {0, 0, 0};        // modexp_batch override for 1024, 2048, 4096
+    int last_U = 0;
+    uint32_t last_off[tecdsa::F_COUNT] = {};
+
+    void count_launch() { launches++; }
+    int reserve_arena(size_t bytes);
+    int launch_exp(const tecdsa::ExpLaunch& l, int K);
+    int launch_inv(const tecdsa::InvLaunch& l, int K);
+};

@@ -1,0 +1,330 @@
+// Batched round driver of the GG20 offline-signing stage (t = 1, n = 3, two signers per
+// session): reproduces /root/reference/src/protocols/multi_party_ecdsa/gg_2020/state_machine/
+// sign/rounds.rs Round0..Round6 for `units` parties at once.  Both parties of a session are
+// resident on the same GPU, so the six message rounds are plain reads of the peer's arena
+// fields.  Every round is: a glue kernel (EC / hashing / plain integers), one persistent
+// job-list launch per modulus width (2048-bit: N_tilde, N, p^2, q^2; 4096-bit: N^2), and, where
+// the verifier needs `mod_inv`, an inversion launch.
+#include "ctx.h"
+#include "gg20_glue.cuh"
+#include "modinv.cuh"
+
+#include <vector>
+
+using namespace tecdsa;
+
+namespace {
+
+struct Builder {
+    tecdsa_ctx* c;
+    const tecdsa_keyset* ks;
+    Arena A;
+    int U;
+    ExpLaunch L64, L128;
+    InvLaunch I64, I128;
+
+    Operand fld(int f, int limbs = 0) const {
+        return Operand{A.base + (size_t)A.off[f] * U, nullptr, A.size[f], 0, (uint32_t)(limbs ? limbs : A.size[f])};
+    }
+    Operand peer(int f, int limbs = 0) const {
+        return Operand{A.base + (size_t)A.off[f] * U, A.peer, A.size[f], 1, (uint32_t)(limbs ? limbs : A.size[f])};
+    }
+    // sub-field of the randomness record (own unit or peer unit)
+    Operand rnd(int off, int limbs, bool of_peer = false) const {
+        return Operand{A.base + (size_t)A.off[F_RND] * U + off, of_peer ? A.peer : nullptr, RND_LIMBS, 1, (uint32_t)limbs};
+    }
+    Operand key(int t, const uint32_t* rows) const { return Operand{A.key[t], rows, (uint32_t)KEY_SIZE[t], 1, (uint32_t)KEY_SIZE[t]}; }
+    uint32_t* out(int f) const { return A.base + (size_t)A.off[f] * U; }
+
+    static void reset(ExpLaunch& l) { l.n_classes = 0; l.total_items = 0; }
+    static void reset(InvLaunch& l) { l.n_classes = 0; l.total_items = 0; }
+    void exp_class(ExpLaunch& l, int gpw, Operand mod, int nb, Operand b0, Operand e0, int el0, Operand b1, Operand e1, int el1,
+                   int nm, Operand m0, Operand m1, int out_field, int wide0 = 0) {
+        ExpClass& k = l.cls[l.n_classes++];
+        k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
+        k.mul[0] = m0; k.mul[1] = m1; k.nbases = nb; k.nmul = nm; k.wide0 = wide0;
+        k.out = out(out_field); k.out_stride = A.size[out_field]; k.count = U; k.item_begin = l.total_items;
+        l.total_items += (U + gpw - 1) / gpw;
+    }
+    void inv_class(InvLaunch& l, int gpw, Operand mod, Operand in, int out_field, int flag_byte) {
+        InvClass& k = l.cls[l.n_classes++];
+        k.mod = mod; k.in = in; k.out = out(out_field); k.out_stride = A.size[out_field];
+        k.ok = reinterpret_cast<uint8_t*>(out(F_FLAGS)) + flag_byte; k.ok_stride = A.size[F_FLAGS] * 4;
+        k.count = U; k.item_begin = l.total_items;
+        l.total_items += (U + gpw - 1) / gpw;
+    }
+};
+
+const Operand NONE = {nullptr, nullptr, 0, 0, 0};
+constexpr int GPW64 = 32 / TPI_2048, GPW128 = 32 / TPI_4096;
+
+template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A) {
+    int grid = (A.U + 63) / 64;
+    kern<<<grid, 64, 0, c->stream>>>(A);
+    c->count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "glue launch", e);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ keys
+extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_keyset** out) {
+    if (!c || !k || !out) return tecdsa_fail(TECDSA_E_ARG, "keys_upload: null argument");
+    if (k->n_keysets == 0 || !k->paillier_p || !k->paillier_q || !k->n_tilde || !k->h1 || !k->h2 || !k->x_i || !k->pk || !k->y)
+        return tecdsa_fail(TECDSA_E_ARG, "keys_upload: missing table");
+    CK(cudaSetDevice(c->device));
+    const int rows = (int)k->n_keysets * 3;
+    tecdsa_keyset* ks = new tecdsa_keyset();
+    ks->n_keysets = (int)k->n_keysets;
+    size_t total = 0;
+    size_t offs[KT_COUNT];
+    for (int t = 0; t < KT_COUNT; t++) { offs[t] = total; total += (size_t)rows * KEY_SIZE[t]; total = (total + 63) & ~size_t(63); }
+    size_t y_off = total; total += (size_t)k->n_keysets * 16;
+    total = (total + 63) & ~size_t(63);
+    size_t ptr_off = total;
+    CK(cudaMalloc(&ks->mem, total * 4 + KT_COUNT * sizeof(uint32_t*)));
+    CK(cudaMemsetAsync(ks->mem, 0, total * 4, c->stream));
+    for (int t = 0; t < KT_COUNT; t++) ks->tab[t] = ks->mem + offs[t];
+    ks->ypk = ks->mem + y_off;
+    struct { int t; const uint32_t* src; } in[] = {{KT_P, k->paillier_p}, {KT_Q, k->paillier_q}, {KT_NT, k->n_tilde}, {KT_H1, k->h1},
+                                                   {KT_H2, k->h2}, {KT_XI, k->x_i}, {KT_PK, k->pk}};
+    for (auto& i : in) CK(cudaMemcpyAsync(ks->tab[i.t], i.src, (size_t)rows * KEY_SIZE[i.t] * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(ks->ypk, k->y, (size_t)k->n_keysets * 16 * 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t** d_ptrs = reinterpret_cast<uint32_t**>(ks->mem + ptr_off);
+    CK(cudaMemcpyAsync(d_ptrs, ks->tab, sizeof(ks->tab), cudaMemcpyHostToDevice, c->stream));
+    gg20_key_setup<<<(rows + 31) / 32, 32, 0, c->stream>>>(d_ptrs, rows);
+    c->count_launch();
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    // parity bits of the uploaded moduli are validated on the host copy of the inputs only
+    for (int r = 0; r < rows; r++) {
+        if (!(k->paillier_p[(size_t)r * 32] & 1) || !(k->paillier_q[(size_t)r * 32] & 1) || !(k->n_tilde[(size_t)r * 64] & 1)) {
+            cudaFree(ks->mem); delete ks;
+            return tecdsa_fail(TECDSA_E_ARG, "keys_upload: even modulus");
+        }
+    }
+    *out = ks;
+    return 0;
+}
+extern "C" int tecdsa_keys_free(tecdsa_ctx* c, tecdsa_keyset* ks) {
+    if (!ks) return 0;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    if (ks->mem) cudaFree(ks->mem);
+    delete ks;
+    return 0;
+}
+extern "C" int tecdsa_keys_table(tecdsa_ctx* c, const tecdsa_keyset* ks, int table, uint32_t* out_host) {
+    if (!c || !ks || !out_host || table < 0 || table >= KT_COUNT) return tecdsa_fail(TECDSA_E_ARG, "keys_table: bad argument");
+    CK(cudaMemcpyAsync(out_host, ks->tab[table], (size_t)ks->n_keysets * 3 * KEY_SIZE[table] * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ job launches
+static int run_exp(tecdsa_ctx* c, ExpLaunch& l, int K) {
+    if (l.n_classes == 0) return 0;
+    int rc = c->launch_exp(l, K);
+    l.n_classes = 0; l.total_items = 0;
+    return rc;
+}
+static int run_inv(tecdsa_ctx* c, InvLaunch& l, int K) {
+    if (l.n_classes == 0) return 0;
+    int rc = c->launch_inv(l, K);
+    l.n_classes = 0; l.total_items = 0;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ offline stage
+extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
+                                         const uint32_t* rnd, uint8_t* status, uint32_t* R_out, uint32_t* sigma_out,
+                                         uint32_t* tvec_out, uint32_t* digest_out, int mem) {
+    if (!c || !ks || !sessions || !rnd || !status) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: null argument");
+    if (mem != TECDSA_HOST && mem != TECDSA_DEVICE) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: bad mem");
+    if (n_sessions == 0) return 0;
+    if (n_sessions > (1u << 22)) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: too many sessions");
+    CK(cudaSetDevice(c->device));
+    const int U = (int)n_sessions * 2;
+
+    // ---- host-side unit tables (who am I, who is my peer, which key rows)
+    std::vector<uint32_t> h_sess(n_sessions * 3);
+    if (mem == TECDSA_HOST) memcpy(h_sess.data(), sessions, h_sess.size() * 4);
+    else { CK(cudaMemcpyAsync(h_sess.data(), sessions, h_sess.size() * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+    std::vector<uint32_t> idx((size_t)7 * U);
+    uint32_t *row_own = idx.data(), *row_peer = row_own + U, *row_st = row_peer + U, *peer = row_st + 3 * (size_t)U, *kset = peer + U;
+    for (size_t s = 0; s < n_sessions; s++) {
+        uint32_t k = h_sess[3 * s], a = h_sess[3 * s + 1], b = h_sess[3 * s + 2];
+        if (k >= (uint32_t)ks->n_keysets || a > 2 || b > 2 || a == b) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: bad session descriptor");
+        for (int p = 0; p < 2; p++) {
+            size_t u = 2 * s + p;
+            row_own[u] = k * 3 + (p ? b : a); row_peer[u] = k * 3 + (p ? a : b);
+            for (int x = 0; x < 3; x++) row_st[(size_t)x * U + u] = k * 3 + x;
+            peer[u] = (uint32_t)(u ^ 1); kset[u] = k;
+        }
+    }
+    // ---- arena
+    Builder B;
+    B.c = c; B.ks = ks; B.U = U;
+    Arena& A = B.A;
+    size_t limbs = 0;
+    for (int f = 0; f < F_COUNT; f++) { A.off[f] = (uint32_t)limbs; A.size[f] = (uint16_t)FIELD_SIZE[f]; limbs += FIELD_SIZE[f]; }
+    const size_t arena_bytes = limbs * 4 * (size_t)U;
+    const size_t idx_bytes = idx.size() * 4;
+    int rc = c->reserve_arena(arena_bytes + idx_bytes + 4096 + (size_t)U);
+    if (rc) return rc;
+    A.base = reinterpret_cast<uint32_t*>(c->arena);
+    A.U = U;
+    uint32_t* d_idx = reinterpret_cast<uint32_t*>(c->arena + ((arena_bytes + 255) & ~size_t(255)));
+    A.row_own = d_idx; A.row_peer = d_idx + U; A.row_st = d_idx + 2 * (size_t)U; A.peer = d_idx + 5 * (size_t)U; A.keyset = d_idx + 6 * (size_t)U;
+    A.status = reinterpret_cast<uint8_t*>(d_idx + 7 * (size_t)U);
+    for (int t = 0; t < KT_COUNT; t++) A.key[t] = ks->tab[t];
+    A.ypk = ks->ypk;
+    CK(cudaMemcpyAsync(d_idx, idx.data(), idx_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(A.status, 0, U, c->stream));
+    CK(cudaMemsetAsync(B.out(F_FLAGS), 0, (size_t)U * A.size[F_FLAGS] * 4, c->stream));
+    CK(cudaMemcpyAsync(B.out(F_RND), rnd, (size_t)U * RND_LIMBS * 4,
+                       mem == TECDSA_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+    const int launches0 = (int)c->launches;
+    CK(cudaEventRecord(c->ev0, c->stream));
+
+    ExpLaunch &L64 = B.L64, &L128 = B.L128;
+    InvLaunch &I64 = B.I64, &I128 = B.I128;
+    Builder::reset(L64); Builder::reset(L128); Builder::reset(I64); Builder::reset(I128);
+    const uint32_t *ro = A.row_own, *rp = A.row_peer;
+    auto st_rows = [&](int x) { return A.row_st + (size_t)x * U; };
+#define RUN(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+    // ================= Round 0 (rounds.rs:68-104): MessageA::a with one AliceProof per statement
+    RUN(glue(c, gg20_r0_pre, A));
+    // c_k = (1 + k N) * r_k^N mod N^2                                   (mta/mod.rs:68-75)
+    B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(RND_RK, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_MK), NONE, F_CK);
+    for (int x = 0; x < 3; x++) {
+        const int al = RND_AL + x * RND_AL_STRIDE;
+        // u = (alpha N + 1) * beta^N mod N^2                            (range_proofs.rs:53-55)
+        B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(al + RND_AL_BETA, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_ALIN0 + x), NONE, F_U0 + x);
+        // w = h1^alpha * h2^gamma mod N_tilde                           (range_proofs.rs:56-57)
+        B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 2, B.key(KT_H2, st_rows(x)), B.rnd(al + RND_AL_GAMMA, 88), 88,
+                    B.key(KT_H1, st_rows(x)), B.rnd(al + RND_AL_ALPHA, 24), 24, 0, NONE, NONE, F_WP0 + x);
+        // z = h1^a * h2^ro mod N_tilde                                  (range_proofs.rs:52)
+        B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 2, B.key(KT_H2, st_rows(x)), B.rnd(al + RND_AL_RHO, 72), 72,
+                    B.key(KT_H1, st_rows(x)), B.rnd(RND_K, 8), 8, 0, NONE, NONE, F_Z0 + x);
+    }
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(glue(c, gg20_r0_mid, A));
+    for (int x = 0; x < 3; x++)    // s = r^e * beta mod N                (range_proofs.rs:86)
+        B.exp_class(L64, GPW64, B.key(KT_N, ro), 1, B.rnd(RND_RK, 64), B.fld(F_E0 + x), 8, NONE, NONE, 0, 1,
+                    B.rnd(RND_AL + x * RND_AL_STRIDE + RND_AL_BETA, 64), NONE, F_S0 + x);
+    RUN(run_exp(c, L64, 64));
+
+    // ================= Round 1 (rounds.rs:122-206): 2 x MessageB::b — the three AliceProof::verify
+    // of the peer's MessageA are computed ONCE and used for both calls (declared de-duplication).
+    RUN(glue(c, gg20_r1_pre, A));
+    for (int x = 0; x < 3; x++) {
+        B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 1, B.peer(F_Z0 + x), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_ZE0 + x);   // z^e (:122)
+        B.exp_class(L128, GPW128, B.key(KT_NN, rp), 1, B.peer(F_CK), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_CE0 + x);              // c^e (:135)
+    }
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    for (int x = 0; x < 3; x++) {
+        B.inv_class(I64, GPW64, B.key(KT_NT, st_rows(x)), B.fld(F_ZE0 + x), F_ZEI0 + x, x);
+        B.inv_class(I128, GPW128, B.key(KT_NN, rp), B.fld(F_CE0 + x), F_CEI0 + x, 3 + x);
+    }
+    RUN(run_inv(c, I128, 128)); RUN(run_inv(c, I64, 64));
+    for (int x = 0; x < 3; x++) {
+        // w' = h1^s1 * h2^s2 * (z^e)^-1 mod N_tilde                     (range_proofs.rs:129-132)
+        B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 2, B.key(KT_H2, st_rows(x)), B.peer(F_S20 + x), 92,
+                    B.key(KT_H1, st_rows(x)), B.peer(F_S10 + x), 28, 1, B.fld(F_ZEI0 + x), NONE, F_WV0 + x);
+        // u' = (s1 N + 1) * s^N * (c^e)^-1 mod N^2                      (range_proofs.rs:134-141)
+        B.exp_class(L128, GPW128, B.key(KT_NN, rp), 1, B.peer(F_S0 + x, 64), B.key(KT_N, rp), 64, NONE, NONE, 0, 2, B.fld(F_GS10 + x), B.fld(F_CEI0 + x), F_UV0 + x);
+    }
+    // c_b = c_a^b * Enc(beta'; r') mod N^2 for b = gamma_i and b = w_i  (mta/mod.rs:133-145)
+    B.exp_class(L128, GPW128, B.key(KT_NN, rp), 2, B.rnd(RND_R_G, 64), B.key(KT_N, rp), 64, B.peer(F_CK), B.rnd(RND_GAMMA, 8), 8, 1, B.fld(F_LBG), NONE, F_CBG);
+    B.exp_class(L128, GPW128, B.key(KT_NN, rp), 2, B.rnd(RND_R_W, 64), B.key(KT_N, rp), 64, B.peer(F_CK), B.fld(F_W), 8, 1, B.fld(F_LBW), NONE, F_CBW);
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(glue(c, gg20_r1_post, A));
+
+    // ================= Round 2 (rounds.rs:234-317): Paillier decrypt of the peer's two MessageB
+    B.exp_class(L64, GPW64, B.key(KT_PP, ro), 1, B.peer(F_CBG), B.key(KT_PM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DPG, 1);
+    B.exp_class(L64, GPW64, B.key(KT_QQ, ro), 1, B.peer(F_CBG), B.key(KT_QM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DQG, 1);
+    B.exp_class(L64, GPW64, B.key(KT_PP, ro), 1, B.peer(F_CBW), B.key(KT_PM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DPW, 1);
+    B.exp_class(L64, GPW64, B.key(KT_QQ, ro), 1, B.peer(F_CBW), B.key(KT_QM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DQW, 1);
+    RUN(run_exp(c, L64, 64));
+    RUN(glue(c, gg20_r2, A));
+    // ================= Round 3 (rounds.rs:347-402)
+    RUN(glue(c, gg20_r3, A));
+    // ================= Round 4 (rounds.rs:431-498): R, R_dash, PDLwSlackProof::prove against the peer's statement
+    RUN(glue(c, gg20_r4_pre, A));
+    B.exp_class(L64, GPW64, B.key(KT_NT, rp), 2, B.key(KT_H2, rp), B.rnd(RND_PDL_RHO, 72), 72, B.key(KT_H1, rp), B.rnd(RND_K, 8), 8, 0, NONE, NONE, F_PZ);          // z  (:78-84)
+    B.exp_class(L64, GPW64, B.key(KT_NT, rp), 2, B.key(KT_H2, rp), B.rnd(RND_PDL_GAMMA, 88), 88, B.key(KT_H1, rp), B.rnd(RND_PDL_ALPHA, 24), 24, 0, NONE, NONE, F_PU3); // u3 (:93-99)
+    // u2 = (N+1)^alpha * beta^N mod N^2, with (N+1)^alpha == 1 + alpha N (declared shortcut, identical value) (:86-92)
+    B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(RND_PDL_BETA, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_PLIN), NONE, F_PU2);
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(glue(c, gg20_r4_mid, A));
+    B.exp_class(L64, GPW64, B.key(KT_N, ro), 1, B.rnd(RND_RK, 64), B.fld(F_PE), 8, NONE, NONE, 0, 1, B.rnd(RND_PDL_BETA, 64), NONE, F_PS2);   // s2 = r^e * beta mod N (:113)
+    RUN(run_exp(c, L64, 64));
+
+    // ================= Round 5 (rounds.rs:525-592): verify both signers' PDL proofs (own one included)
+    RUN(glue(c, gg20_r5_pre, A));
+    for (int j = 0; j < 2; j++) {
+        const uint32_t* prover = j ? rp : ro;            // key row of the prover
+        const uint32_t* stmt = j ? ro : rp;              // whose (N_tilde, h1, h2) the proof was made against
+        Operand z = j ? B.peer(F_PZ) : B.fld(F_PZ), ck = j ? B.peer(F_CK) : B.fld(F_CK);
+        B.exp_class(L64, GPW64, B.key(KT_NT, stmt), 1, z, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VZE0 + j);       // z^e; (z^-1)^e == (z^e)^-1 (:166-172)
+        B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, ck, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VCE0 + j);  // c^e (:151-157)
+    }
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    for (int j = 0; j < 2; j++) {
+        B.inv_class(I64, GPW64, B.key(KT_NT, j ? ro : rp), B.fld(F_VZE0 + j), F_VZEI0 + j, 6 + j);
+        B.inv_class(I128, GPW128, B.key(KT_NN, j ? rp : ro), B.fld(F_VCE0 + j), F_VCEI0 + j, 8 + j);
+    }
+    RUN(run_inv(c, I128, 128)); RUN(run_inv(c, I64, 64));
+    for (int j = 0; j < 2; j++) {
+        const uint32_t* prover = j ? rp : ro;
+        const uint32_t* stmt = j ? ro : rp;
+        Operand s1 = j ? B.peer(F_PS1) : B.fld(F_PS1), s2 = j ? B.peer(F_PS2, 64) : B.fld(F_PS2, 64), s3 = j ? B.peer(F_PS3) : B.fld(F_PS3);
+        // u3' = h1^s1 * h2^s3 * z^-e mod N_tilde                         (:158-172)
+        B.exp_class(L64, GPW64, B.key(KT_NT, stmt), 2, B.key(KT_H2, stmt), s3, 92, B.key(KT_H1, stmt), s1, 28, 1, B.fld(F_VZEI0 + j), NONE, F_VU30 + j);
+        // u2' = (N+1)^s1 * s2^N * c^-e mod N^2                           (:144-157)
+        B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, s2, B.key(KT_N, prover), 64, NONE, NONE, 0, 2, B.fld(F_VLIN0 + j), B.fld(F_VCEI0 + j), F_VU20 + j);
+    }
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(glue(c, gg20_r5_post, A));
+    // ================= Round 6 (rounds.rs:612-636) + result records
+    RUN(glue(c, gg20_r6, A));
+#undef RUN
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->last_launches = (int)c->launches - launches0;
+
+    // ---- outputs
+    const cudaMemcpyKind kind = mem == TECDSA_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(status, A.status, U, kind, c->stream));
+    if (R_out) CK(cudaMemcpyAsync(R_out, B.out(F_R), (size_t)U * 16 * 4, kind, c->stream));
+    if (sigma_out) CK(cudaMemcpyAsync(sigma_out, B.out(F_SIGMA), (size_t)U * 8 * 4, kind, c->stream));
+    if (digest_out) CK(cudaMemcpyAsync(digest_out, B.out(F_DIGEST), (size_t)U * 8 * 4, kind, c->stream));
+    if (tvec_out) {
+        // t_vec[u] = (T of signer position 0, T of signer position 1) of the session
+        CK(cudaMemcpy2DAsync(tvec_out, 64 * 4, B.out(F_T), 32 * 4, 32 * 4, n_sessions, kind, c->stream));        // even units
+        CK(cudaMemcpy2DAsync(tvec_out + 32, 64 * 4, B.out(F_T), 32 * 4, 32 * 4, n_sessions, kind, c->stream));   // odd units
+    }
+    c->last_U = U;
+    memcpy(c->last_off, A.off, sizeof(A.off));
+    if (mem == TECDSA_HOST) CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Debug / test access: copy one arena field of the last gg20_offline batch to the host.
+extern "C" int tecdsa_gg20_debug_field(tecdsa_ctx* c, const char* name, uint32_t* out_host, size_t* limbs_per_unit) {
+    if (!c || !name) return tecdsa_fail(TECDSA_E_ARG, "debug_field: null argument");
+    if (c->last_U == 0) return tecdsa_fail(TECDSA_E_ARG, "debug_field: no batch has run");
+    for (int f = 0; f < F_COUNT; f++) {
+        if (strcmp(name, FIELD_NAME[f]) == 0) {
+            if (limbs_per_unit) *limbs_per_unit = FIELD_SIZE[f];
+            if (out_host) {
+                CK(cudaMemcpyAsync(out_host, reinterpret_cast<uint32_t*>(c->arena) + (size_t)c->last_off[f] * c->last_U,
+                                   (size_t)c->last_U * FIELD_SIZE[f] * 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+            }
+            return 0;
+        }
+    }
+    return tecdsa_fail(TECDSA_E_ARG, "debug_field: unknown field");
+}

@@ -15,8 +15,8 @@ static constexpr int WINDOW_BITS = 5;
 // Everything a group needs to exponentiate modulo one modulus.
 template <int L> struct MontCtx {
     uint32_t n[L];
-    uint32_t rr[L];      // R^2 mod n (lazy: < R)
-    uint32_t one[L];     // R mod n   (lazy: < R)
+    uint32_t rr[L];      // R^2 mod n
+    uint32_t one[L];     // R mod n
     uint32_t n0inv;
 };
 
@@ -25,11 +25,8 @@ template <int TPI, int L>
 __device__ __forceinline__ void mont_setup(MontCtx<L>& c) {
     const int gl = group_lane<TPI>();
     c.n0inv = neg_inv32(__shfl_sync(FULL, c.n[0], 0, TPI));
-    // R - n  ==  R mod n up to multiples of n, and < R.
     uint32_t x[L];
-#pragma unroll
-    for (int j = 0; j < L; j++) x[j] = 0;
-    (void)group_sub_masked<TPI, L>(x, c.n, 0xffffffffu, 1u);
+    r_mod_n<TPI, L>(x, c.n);
 #pragma unroll
     for (int j = 0; j < L; j++) c.one[j] = x[j];
     // x = 2^e * R with e = 1, then square (e -> 2e) / double (e -> e+1) up to e = 32*K.
@@ -58,7 +55,6 @@ __device__ __forceinline__ void mont_to_plain(uint32_t (&x)[L], const MontCtx<L>
     for (int j = 0; j < L; j++) u[j] = 0;
     if (gl == 0) u[0] = 1;
     mont_mul<TPI, L>(x, x, u, c.n, c.n0inv);
-    cond_sub<TPI, L>(x, c.n);
 }
 
 // exponent window `w` (WINDOW_BITS wide) of a little-endian limb array
@@ -71,7 +67,7 @@ __device__ __forceinline__ uint32_t exp_window(const uint32_t* __restrict__ e, i
     return (uint32_t)(v >> off) & ((1u << WINDOW_BITS) - 1);
 }
 
-// acc = base^exp in Montgomery form (lazy).  `tbl` is this group's private window table
+// acc = base^exp in Montgomery form.  `tbl` is this group's private window table
 // (2^WINDOW_BITS entries of K limbs, operand-major) in global memory.
 template <int TPI, int L>
 __device__ __forceinline__ void mont_pow(uint32_t (&acc)[L], const uint32_t (&base)[L], const uint32_t* __restrict__ e,

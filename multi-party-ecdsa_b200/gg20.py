@@ -1,0 +1,130 @@
+"""Host-side mirror of the reference's GG20 offline-stage entry (`OfflineStage::new(i, s_l, local_key)`
++ the rounds of /root/reference/src/protocols/multi_party_ecdsa/gg_2020/state_machine/sign.rs),
+batched: packs `LocalKey` material and per-unit randomness into the ABI's limb records and
+calls tecdsa_gg20_offline_batch.  No arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence
+
+import numpy as np
+
+from . import HOST, Engine, EngineError, ints_to_limbs, limbs_to_ints, _ptr
+
+RND_LIMBS = 1408
+# (offset, limbs) of every field of the randomness record — include/tecdsa_b200.h TECDSA_RND_*
+RND = {
+    "gamma_i": (0, 8), "k_i": (8, 8), "blind": (16, 8), "r_k": (24, 64),
+    "beta_tag_gamma": (832, 64), "r_gamma": (896, 64), "nonce_gamma_b": (960, 8), "nonce_gamma_beta": (968, 8),
+    "beta_tag_w": (976, 64), "r_w": (1040, 64), "nonce_w_b": (1104, 8), "nonce_w_beta": (1112, 8),
+    "l": (1120, 8), "ped_s1": (1128, 8), "ped_s2": (1136, 8),
+    "heg_s1": (1392, 8), "heg_s2": (1400, 8),
+}
+RND_ALICE, RND_ALICE_STRIDE = 88, 248
+RND_ALICE_PARTS = ((0, 24), (24, 64), (88, 88), (176, 72))          # alpha, beta, gamma, rho
+RND_PDL_PARTS = ((1144, 24), (1168, 64), (1232, 72), (1304, 88))    # alpha, beta, rho, gamma
+
+
+class _Keys(ctypes.Structure):
+    _fields_ = [("n_keysets", ctypes.c_size_t)] + [(n, ctypes.c_void_p) for n in
+                                                   ("paillier_p", "paillier_q", "n_tilde", "h1", "h2", "x_i", "pk", "y")]
+
+
+def _bind(lib):
+    if getattr(lib, "_gg20_bound", False):
+        return
+    lib.tecdsa_keys_upload.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Keys), ctypes.POINTER(ctypes.c_void_p)]
+    lib.tecdsa_keys_free.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.tecdsa_keys_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    lib.tecdsa_gg20_offline_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 6 + [ctypes.c_int]
+    lib.tecdsa_gg20_debug_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+    lib._gg20_bound = True
+
+
+def pack_point(p) -> List[int]:
+    """affine point -> x||y as one 512-bit little-endian integer (identity = 0)"""
+    return 0 if p is None else p[0] | (p[1] << 256)
+
+
+def unpack_point(v: int):
+    return None if v == 0 else (v & ((1 << 256) - 1), v >> 256)
+
+
+class KeySets:
+    """Device-resident LocalKey material of several (t=1,n=3) key sets.  `keysets[k]` is a list of
+    three objects with the fields of the reference's LocalKey (i, x_i, dk.p, dk.q, pk_vec,
+    h1_h2_n_tilde_vec, y_sum_s) — e.g. oracle.LocalKey or any duck-typed equivalent."""
+
+    def __init__(self, eng: Engine, keysets: Sequence[Sequence]):
+        _bind(eng.lib)
+        self.eng = eng
+        self.n = len(keysets)
+        rows = [lk for ks in keysets for lk in ks]
+        self._bufs = dict(
+            paillier_p=ints_to_limbs([lk.dk.p for lk in rows], 32), paillier_q=ints_to_limbs([lk.dk.q for lk in rows], 32),
+            n_tilde=ints_to_limbs([lk.h1_h2_n_tilde_vec[lk.i - 1].N for lk in rows], 64),
+            h1=ints_to_limbs([lk.h1_h2_n_tilde_vec[lk.i - 1].g for lk in rows], 64),
+            h2=ints_to_limbs([lk.h1_h2_n_tilde_vec[lk.i - 1].ni for lk in rows], 64),
+            x_i=ints_to_limbs([lk.x_i for lk in rows], 8),
+            pk=ints_to_limbs([pack_point(lk.pk_vec[lk.i - 1]) for lk in rows], 16),
+            y=ints_to_limbs([pack_point(ks[0].y_sum_s) for ks in keysets], 16))
+        k = _Keys(self.n, *[self._bufs[n].ctypes.data for n in ("paillier_p", "paillier_q", "n_tilde", "h1", "h2", "x_i", "pk", "y")])
+        self.handle = ctypes.c_void_p()
+        eng._ck(eng.lib.tecdsa_keys_upload(eng._ctx, ctypes.byref(k), ctypes.byref(self.handle)), "keys_upload")
+
+    def table(self, index: int, limbs: int) -> List[int]:
+        out = np.zeros((self.n * 3, limbs), dtype=np.uint32)
+        self.eng._ck(self.eng.lib.tecdsa_keys_table(self.eng._ctx, self.handle, index, out.ctypes.data), "keys_table")
+        return limbs_to_ints(out)
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.tecdsa_keys_free(self.eng._ctx, self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+def pack_randomness(units: Sequence) -> np.ndarray:
+    """oracle.UnitRandomness-shaped objects -> [units][RND_LIMBS] uint32"""
+    out = np.zeros((len(units), RND_LIMBS), dtype=np.uint32)
+
+    def put(row, off, limbs, val):
+        out[row, off:off + limbs] = np.frombuffer(int(val).to_bytes(4 * limbs, "little"), dtype="<u4")
+
+    for u, r in enumerate(units):
+        for name, (off, limbs) in RND.items():
+            put(u, off, limbs, getattr(r, name))
+        for x in range(3):
+            for (o, l), v in zip(RND_ALICE_PARTS, r.alice[x]):
+                put(u, RND_ALICE + x * RND_ALICE_STRIDE + o, l, v)
+        for (o, l), v in zip(RND_PDL_PARTS, r.pdl):
+            put(u, o, l, v)
+    return out
+
+
+class OfflineResult:
+    def __init__(self, status, R, sigma, t_vec, digest):
+        self.status, self.R, self.sigma, self.t_vec, self.digest = status, R, sigma, t_vec, digest
+
+
+def offline_batch(eng: Engine, keys: KeySets, sessions: Sequence[Sequence[int]], rnd: np.ndarray, mem: int = HOST) -> OfflineResult:
+    """sessions[s] = (keyset, party0, party1) with parties 0-based; rnd from pack_randomness()."""
+    _bind(eng.lib)
+    n = len(sessions)
+    sess = np.ascontiguousarray(np.array(sessions, dtype=np.uint32).reshape(n, 3))
+    U = 2 * n
+    assert rnd.shape == (U, RND_LIMBS)
+    status = np.full(U, 255, dtype=np.uint8)
+    R = np.zeros((U, 16), np.uint32); sigma = np.zeros((U, 8), np.uint32)
+    tvec = np.zeros((U, 32), np.uint32); digest = np.zeros((U, 8), np.uint32)
+    eng._ck(eng.lib.tecdsa_gg20_offline_batch(eng._ctx, keys.handle, _ptr(sess), n, _ptr(rnd), _ptr(status), _ptr(R), _ptr(sigma),
+                                              _ptr(tvec), _ptr(digest), mem), "gg20_offline_batch")
+    return OfflineResult(status, R, sigma, tvec, digest)
+
+
+def debug_field(eng: Engine, name: str, units: int) -> np.ndarray:
+    _bind(eng.lib)
+    n = ctypes.c_size_t()
+    eng._ck(eng.lib.tecdsa_gg20_debug_field(eng._ctx, name.encode(), None, ctypes.byref(n)), "debug_field")
+    out = np.zeros((units, n.value), dtype=np.uint32)
+    eng._ck(eng.lib.tecdsa_gg20_debug_field(eng._ctx, name.encode(), out.ctypes.data, ctypes.byref(n)), "debug_field")
+    return out

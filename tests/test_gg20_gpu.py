@@ -1,0 +1,105 @@
+"""GPU parity tests of the batched GG20 offline stage (tecdsa_gg20_offline_batch) against the
+oracle's restatement of sign/rounds.rs Round0..Round6: per-unit status, R, sigma_i, t_vec and the
+SHA-256 digest over every emitted message (ciphertexts, range proofs, PDL proofs, sigma proofs)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import gg20_oracle as o
+from oracle.sampling import Drbg, sample_unit
+
+pytestmark = pytest.mark.gpu
+
+
+def _session_inputs(keyset, pairs, seed):
+    """pairs: list of (party_a, party_b) 0-based -> oracle inputs + packed randomness"""
+    rng = Drbg(seed, "gg20-gpu")
+    sess, rnds, oracle_in = [], [], []
+    for a, b in pairs:
+        s_l = [a + 1, b + 1]
+        keys = [keyset[a], keyset[b]]
+        r = [sample_unit(rng, keys, s_l, p) for p in range(2)]
+        sess.append((0, a, b)); rnds += r; oracle_in.append((keys, s_l, r))
+    return sess, rnds, oracle_in
+
+
+def _digest_int(row):
+    return int.from_bytes(row.tobytes(), "little")
+
+
+def test_key_tables_derived_on_device(engine, pkg, keyset):
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    assert ks.table(0, 64) == [k.dk.p * k.dk.q for k in keyset]
+    assert ks.table(1, 128) == [(k.dk.p * k.dk.q) ** 2 for k in keyset]
+    assert ks.table(5, 64) == [k.dk.p ** 2 for k in keyset]
+    R = 1 << 1024
+    assert ks.table(11, 32) == [pow(k.dk.p, -1, R) for k in keyset]                       # p^-1 mod 2^1024
+    assert ks.table(13, 32) == [(-pow(k.dk.q, -1, k.dk.p)) % k.dk.p * R % k.dk.p for k in keyset]   # hp * R mod p
+    assert ks.table(15, 32) == [pow(k.dk.p, -1, k.dk.q) * R % k.dk.q for k in keyset]     # (p^-1 mod q) * R mod q
+    ks.free()
+
+
+def test_offline_stage_matches_oracle(engine, pkg, keyset):
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    pairs = [(0, 1), (0, 2), (1, 2), (1, 0), (2, 0)]
+    sess, rnds, oracle_in = _session_inputs(keyset, pairs, 0xB2000005)
+    res = gg20.offline_batch(engine, ks, sess, gg20.pack_randomness(rnds))
+    assert list(res.status) == [0] * (2 * len(pairs))
+    for s, (keys, s_l, r) in enumerate(oracle_in):
+        want = o.offline_session(keys, s_l, r)
+        for p in range(2):
+            u = 2 * s + p
+            assert want[p].status == 0
+            assert gg20.unpack_point(pkg.limbs_to_ints(res.R[u:u + 1])[0]) == want[p].R
+            assert pkg.limbs_to_ints(res.sigma[u:u + 1])[0] == want[p].sigma_i
+            tv = [gg20.unpack_point(v) for v in pkg.limbs_to_ints(res.t_vec[u].reshape(2, 16))]
+            assert tv == want[p].t_vec
+            assert _digest_int(res.digest[u]).to_bytes(32, "big") == want[p].transcript, (s, p)
+    # intermediate messages, byte for byte: MessageA.c and the first AliceProof of unit 0
+    keys, s_l, r = oracle_in[0]
+    m_a = o.message_a(r[0].k_i, keys[0].paillier_key_vec[keys[0].i - 1], r[0].r_k, keys[0].h1_h2_n_tilde_vec, r[0].alice)
+    U = 2 * len(pairs)
+    assert pkg.limbs_to_ints(gg20.debug_field(engine, "CK", U)[:1]) == [m_a.c]
+    pf = m_a.range_proofs[0]
+    for name, val in (("Z0", pf.z), ("E0", pf.e), ("S0", pf.s), ("S10", pf.s1), ("S20", pf.s2)):
+        assert pkg.limbs_to_ints(gg20.debug_field(engine, name, U)[:1]) == [val], name
+    ks.free()
+
+
+def test_offline_signature_verifies_independently(engine, pkg, keyset):
+    """end-to-end validity: the online step on the GPU outputs gives an ECDSA signature that an
+    independent implementation (OpenSSL via `cryptography`) accepts (cf. gg_2020/test.rs:711-748)."""
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec, utils
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    sess, rnds, _ = _session_inputs(keyset, [(0, 2), (2, 1)], 4242)
+    res = gg20.offline_batch(engine, ks, sess, gg20.pack_randomness(rnds))
+    assert not res.status.any()
+    msg = o.sha256_bigints([o.bn_from_bytes(b"ZenGo")])
+    y = keyset[0].y_sum_s
+    pub = ec.EllipticCurvePublicNumbers(y[0], y[1], ec.SECP256K1()).public_key()
+    for s in range(2):
+        R = gg20.unpack_point(pkg.limbs_to_ints(res.R[2 * s:2 * s + 1])[0])
+        parts = [o.local_sig(rnds[2 * s + p].k_i, msg, R, pkg.limbs_to_ints(res.sigma[2 * s + p:2 * s + p + 1])[0]) for p in range(2)]
+        r_, s_, _ = o.output_signature(R, parts)
+        pub.verify(utils.encode_dss_signature(r_, s_), msg.to_bytes(32, "big"), ec.ECDSA(utils.Prehashed(hashes.SHA256())))
+    ks.free()
+
+
+def test_offline_detects_tampering(engine, pkg, keyset):
+    """fault injection (gg_2020/test.rs:69-148 style): out-of-range alpha in one range proof of
+    unit 0 -> its peer rejects MessageA with InvalidKey; the untouched session stays OK."""
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    sess, rnds, oracle_in = _session_inputs(keyset, [(0, 1), (1, 2)], 77)
+    a = rnds[0].alice[1]
+    rnds[0].alice[1] = ((1 << 768) - 1, a[1], a[2], a[3])          # alpha > q^3 -> s1 > q^3
+    res = gg20.offline_batch(engine, ks, sess, gg20.pack_randomness(rnds))
+    want = o.offline_session(*oracle_in[0])
+    assert res.status[1] == pkg.ST_INVALID_KEY == want[1].status
+    assert res.status[0] == 0 and list(res.status[2:]) == [0, 0]
+    ks.free()
