@@ -53,6 +53,8 @@ extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    // the glue kernels call non-inlined EC / hash routines with multi-KB frames
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     *out = c;

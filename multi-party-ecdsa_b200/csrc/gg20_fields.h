@@ -39,7 +39,7 @@ enum : int {
     X(BETA_G, 8) X(NU, 8) X(BTG_FE, 8) X(BTW_FE, 8)                                               \
     X(DL0, 40) X(DL1, 40) X(DL2, 40) X(DL3, 40)     /* pk 16 | T 16 | response 8 */              \
     /* round 2 */                                                                                 \
-    X(DPG, 64) X(DQG, 64) X(DPW, 64) X(DQW, 64)                                                   \
+    X(DPG, 64) X(DQG, 64) X(DPW, 64) X(DQW, 64) X(APLG, 64) X(APLW, 64)   /* alpha' plaintexts */      \
     X(ALPHA, 8) X(MU, 8) X(DELTA, 8) X(SIGMA, 8) X(T, 16)                                         \
     X(PED, 64)                                      /* e 8 | a1 16 | a2 16 | z1 8 | z2 8 | pad */ \
     X(DINV, 8)                                                                                    \
@@ -51,7 +51,8 @@ enum : int {
     X(VZEI0, 64) X(VZEI1, 64) X(VCEI0, 128) X(VCEI1, 128) X(VU20, 128) X(VU21, 128) X(VU30, 64) X(VU31, 64) \
     X(SI, 16) X(HEG, 48)                            /* T 16 | A3 16 | z1 8 | z2 8 */             \
     X(DIGEST, 8)                                                                                  \
-    X(FLAGS, 4)                                     /* ok bytes of the inversions, packed */
+    X(FLAGS, 4)                                     /* ok bytes of the inversions, packed */         \
+    X(DBG, 256)                                     /* scratch for tools/debug_gg20.py */
 
 enum Field : int {
 #define X(name, size) F_##name,

@@ -184,7 +184,7 @@ __global__ void gg20_r1_post(Arena A) {
     bool ok = fl[10] == 0;
     for (int x = 0; x < 3; x++) {
         ok = ok && fl[x] && fl[3 + x];
-        uint32_t e[8];
+        uint32_t* e = A.p(F_DBG, u) + 8 * x;          // recomputed challenge (kept in the arena)
         alice_hash(e, Np, A.p(F_CK, pu), A.p(F_Z0 + x, pu), A.p(F_UV0 + x, u), A.p(F_WV0 + x, u));
         ok = ok && st::cmp(e, A.p(F_E0 + x, pu), 8) == 0;
     }
@@ -237,7 +237,8 @@ __global__ void gg20_r2(Arena A) {
     U256 shares[2];
     bool ok = true;
     for (int m = 0; m < 2; m++) {
-        uint32_t plain[64];
+        // the plaintext goes to the arena (it is also part of the reference's return value, mta/mod.rs:175)
+        uint32_t* plain = A.p(m ? F_APLW : F_APLG, u);
         decrypt_finish(plain, A, row, A.p(m ? F_DPW : F_DPG, u), A.p(m ? F_DQW : F_DQG, u));
         U256 alpha = sc_from_limbs(plain, 64);
         shares[m] = alpha;

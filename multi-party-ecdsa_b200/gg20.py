@@ -128,3 +128,69 @@ def debug_field(eng: Engine, name: str, units: int) -> np.ndarray:
     out = np.zeros((units, n.value), dtype=np.uint32)
     eng._ck(eng.lib.tecdsa_gg20_debug_field(eng._ctx, name.encode(), out.ctypes.data, ctypes.byref(n)), "debug_field")
     return out
+
+
+# ----------------------------------------------------------------------------- synthetic batches (bench / scale tests)
+_Q = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+
+
+def synthetic_batch(keysets: Sequence[Sequence], n_sessions: int, seed: int):
+    """Random valid inputs for `n_sessions` two-signer sessions over the given key sets: returns
+    (sessions [n,3] uint32, rnd [2n, RND_LIMBS] uint32).  Every value is drawn uniformly with one
+    bit less than its reference bound (so it is always in range; the bounds are those of
+    `sample_unit` in oracle/sampling.py), vectorised with numpy so that 10^5 units take seconds."""
+    rng = np.random.default_rng(seed)
+    pairs = [(0, 1), (0, 2), (1, 2), (1, 0), (2, 0), (2, 1)]
+    n_ks = len(keysets)
+    ks_idx = rng.integers(0, n_ks, size=n_sessions)
+    pr_idx = rng.integers(0, len(pairs), size=n_sessions)
+    sessions = np.zeros((n_sessions, 3), dtype=np.uint32)
+    sessions[:, 0] = ks_idx
+    sessions[:, 1] = [pairs[i][0] for i in pr_idx]
+    sessions[:, 2] = [pairs[i][1] for i in pr_idx]
+    U = 2 * n_sessions
+    rnd = np.zeros((U, RND_LIMBS), dtype=np.uint32)
+
+    def fill(rows, off, limbs, bits):
+        """uniform `bits`-bit values (lowest limb forced odd/non-zero where it matters is not needed)"""
+        full, rem = divmod(bits, 32)
+        block = rng.integers(0, 2 ** 32, size=(len(rows), limbs), dtype=np.uint32)
+        block[:, full + (1 if rem else 0):] = 0
+        if rem:
+            block[:, full] &= np.uint32((1 << rem) - 1)
+        block[:, 0] |= 1                      # never zero
+        rnd[np.asarray(rows)[:, None], off + np.arange(limbs)[None, :]] = block
+
+    all_rows = np.arange(U)
+    for name in ("gamma_i", "k_i", "nonce_gamma_b", "nonce_gamma_beta", "nonce_w_b", "nonce_w_beta", "l", "ped_s1", "ped_s2", "heg_s1", "heg_s2"):
+        fill(all_rows, RND[name][0], 8, 255)
+    fill(all_rows, RND["blind"][0], 8, 256)
+    q3_bits = (_Q ** 3).bit_length() - 1
+    # the remaining fields depend on the moduli of the unit's own / peer's key rows
+    unit_ks = np.repeat(ks_idx, 2)
+    own = np.stack([sessions[:, 1], sessions[:, 2]], axis=1).reshape(-1)
+    peer = np.stack([sessions[:, 2], sessions[:, 1]], axis=1).reshape(-1)
+    for k in range(n_ks):
+        for party in range(3):
+            lk = keysets[k][party]
+            n_bits = (lk.dk.p * lk.dk.q).bit_length() - 1
+            rows = all_rows[(unit_ks == k) & (own == party)]
+            if len(rows):
+                fill(rows, RND["r_k"][0], 64, n_bits)
+                fill(rows, RND_PDL_PARTS[1][0], 64, n_bits)                       # pdl beta
+                for x in range(3):
+                    nt = keysets[k][x].h1_h2_n_tilde_vec[x].N
+                    base = RND_ALICE + x * RND_ALICE_STRIDE
+                    fill(rows, base + RND_ALICE_PARTS[0][0], 24, q3_bits)
+                    fill(rows, base + RND_ALICE_PARTS[1][0], 64, n_bits)
+                    fill(rows, base + RND_ALICE_PARTS[2][0], 88, (_Q ** 3 * nt).bit_length() - 1)
+                    fill(rows, base + RND_ALICE_PARTS[3][0], 72, (_Q * nt).bit_length() - 1)
+            rows = all_rows[(unit_ks == k) & (peer == party)]
+            if len(rows):
+                for name in ("beta_tag_gamma", "r_gamma", "beta_tag_w", "r_w"):
+                    fill(rows, RND[name][0], 64, n_bits)
+                nt = lk.h1_h2_n_tilde_vec[party].N                                # PDL is proved against the peer's statement
+                fill(rows, RND_PDL_PARTS[0][0], 24, q3_bits)
+                fill(rows, RND_PDL_PARTS[2][0], 72, (_Q * nt).bit_length() - 1)
+                fill(rows, RND_PDL_PARTS[3][0], 88, (_Q ** 3 * nt).bit_length() - 1)
+    return sessions, rnd
