@@ -138,6 +138,110 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+# ---------------------------------------------------------------------------------------------
+# Secondary workload: the full GG20 offline-signing stage (BASELINE.json metric part 1,
+# configs[4] sharded per GPU).  SURVEY.md section 8(d): W_unit = 2.003e9 MAC32 (reference
+# operation list), ~18 KB moved per unit.
+OFFLINE_SESSIONS = 8192
+W_UNIT = 2.003e9
+W_UNIT_EXECUTED = 1.49e9      # after the declared de-duplication / shortcuts
+BYTES_PER_UNIT = 18 * 1024
+
+
+def bench_offline(args, eng, pkg, torch, dist, rank, world, n_sessions):
+    from mpecdsa_b200 import gg20
+    from tests.golden import fixtures
+    keysets = [fixtures.load_keyset(0), fixtures.load_keyset(1)]
+    ks = gg20.KeySets(eng, keysets)
+    sess, rnd = gg20.synthetic_batch(keysets, n_sessions, SEED + 17 * rank)
+    U = 2 * n_sessions
+    h_rnd = torch.from_numpy(rnd.view(np.int32)).pin_memory()
+    h_sess = torch.from_numpy(sess.view(np.int32)).pin_memory()
+    d_rnd, d_sess = h_rnd.cuda(), h_sess.cuda()
+    d_status = torch.empty(U, dtype=torch.uint8, device="cuda")
+    d_digest = torch.empty((U, 8), dtype=torch.int32, device="cuda")
+    d_R = torch.empty((U, 16), dtype=torch.int32, device="cuda")
+    d_sigma = torch.empty((U, 8), dtype=torch.int32, device="cuda")
+    h_status = torch.empty(U, dtype=torch.uint8).pin_memory()
+    h_digest = torch.empty((U, 8), dtype=torch.int32).pin_memory()
+    h_R = torch.empty((U, 16), dtype=torch.int32).pin_memory()
+    h_sigma = torch.empty((U, 8), dtype=torch.int32).pin_memory()
+    record = torch.zeros((U, 9), dtype=torch.int32, device="cuda")       # status + digest per unit
+    from mpecdsa_b200 import sharding
+
+    def call(sessions, r, status, R, sigma, digest, mem):
+        eng._ck(eng.lib.tecdsa_gg20_offline_batch(eng._ctx, ks.handle, sessions.data_ptr(), n_sessions, r.data_ptr(),
+                                                  status.data_ptr(), R.data_ptr(), sigma.data_ptr(), None, digest.data_ptr(), mem),
+                "gg20_offline_batch")
+
+    gathered = [None]
+
+    def step_device():
+        call(d_sess, d_rnd, d_status, d_R, d_sigma, d_digest, pkg.DEVICE)
+        record[:, 0] = d_status
+        record[:, 1:] = d_digest
+        gathered[0] = sharding.gather_records(record, world)              # the single NCCL all-gather
+
+    def step_host():
+        call(h_sess, h_rnd, h_status, h_R, h_sigma, h_digest, pkg.HOST)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    steps = max(1, min(args.steps, 3))
+    step_device(); barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launch_count()
+    ev0.record()
+    for _ in range(steps):
+        step_device()
+    ev1.record(); barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    k_ms, k_launches = eng.last_kernel_ms()
+    step_host(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([dev_ms, e2e_ms, k_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, k_ms = (float(x) for x in t.tolist())
+    all_ok = bool((gathered[0][:, :, 0] == 0).all().item()) and bool((h_status == 0).all().item())
+    same = bool(torch.equal(h_digest, d_digest.cpu()))
+    ks.free()
+    total_units = U * world
+    return {
+        "metric": "GG20 (t=1,n=3) offline-signing phases/s", "value": total_units * steps / (dev_ms * 1e-3), "unit": "phases/s",
+        "units_per_gpu": U, "sessions_per_gpu": n_sessions, "steps": steps, "ms_per_step": dev_ms / steps,
+        "e2e": {"value": total_units * steps / (e2e_ms * 1e-3), "unit": "phases/s", "h2d_bytes_per_step": int(rnd.nbytes + sess.nbytes),
+                "d2h_bytes_per_step": int(U * (1 + 32 + 64 + 32)), "ms_per_step": e2e_ms / steps},
+        "gpu_launches_per_step": int(launches // steps), "kernels_ms_per_step": k_ms,
+        "all_units_ok": all_ok, "host_and_device_paths_agree": same,
+        "work": {"W_unit_reference_oplist_mac32": W_UNIT, "W_unit_executed_mac32": W_UNIT_EXECUTED,
+                 "achieved_reference_oplist_tmac32": W_UNIT * U / (k_ms * 1e-3) / 1e12,
+                 "achieved_executed_tmac32": W_UNIT_EXECUTED * U / (k_ms * 1e-3) / 1e12,
+                 "hbm_algorithmic_gbs": BYTES_PER_UNIT * U / (k_ms * 1e-3) / 1e9},
+    }
+
+
+def cpu_unit_baseline(threads: int):
+    lib = load_oracle_lib()
+    lib.oracle_unit_oplist.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64]
+    units = max(threads, 8)
+    t0 = time.perf_counter()
+    lib.oracle_unit_oplist(units, threads, 7)
+    dt = time.perf_counter() - t0
+    return {"value": units / dt, "unit": "phases/s", "cores": threads, "kind": "port",
+            "sample": f"{units} units: the reference's big-integer operation list of one OfflineStage (76 mpz_powm + 22 mpz_invert at the "
+                      f"reference's operand sizes, redundant verifications included; EC/hash <1 % omitted), GMP {lib.oracle_gmp_version().decode()}"}
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path (GMP mpz_powm behind
     BigInt::mod_pow) on all host threads; each step a bounded sample of the workload."""
@@ -178,6 +282,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--offline-sessions", type=int, default=OFFLINE_SESSIONS, help="sessions per GPU for the offline-stage section (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -277,6 +382,10 @@ def main():
         got_host = h_out.numpy().view(np.uint32)[idx]
         ok = ok and np.array_equal(want, got_dev) and np.array_equal(want, got_host)
 
+    offline = None
+    if args.offline_sessions > 0:
+        offline = bench_offline(args, eng, pkg, torch, dist, rank, world, args.offline_sessions)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -329,12 +438,20 @@ def main():
                              "peak_source": hbm_src, "algorithmic_bytes_per_launch": BYTES_PER_MODEXP * batch}},
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "offline_stage": offline,
     }
+    if offline is not None:
+        offline["roofline_frac_reference_oplist"] = offline["work"]["achieved_reference_oplist_tmac32"] * 1e12 / peak_mac
+        offline["roofline_frac_executed"] = offline["work"]["achieved_executed_tmac32"] * 1e12 / peak_mac
+        if not args.no_cpu_baseline:
+            offline["cpu_baseline"] = cpu_unit_baseline(host_threads())
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     if not ok:
         raise SystemExit("parity check against the oracle FAILED")
+    if offline is not None and not (offline["all_units_ok"] and offline["host_and_device_paths_agree"]):
+        raise SystemExit("offline stage: a unit failed or the host/device paths disagree")
 
 
 if __name__ == "__main__":

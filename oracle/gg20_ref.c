@@ -94,3 +94,75 @@ int oracle_paillier_roundtrip(const uint32_t* p_l, const uint32_t* q_l, const ui
     mpz_clear(pp); mpz_clear(qq); mpz_clear(hp); mpz_clear(hq); mpz_clear(mp); mpz_clear(mq); mpz_clear(pinv); mpz_clear(one);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * CPU cost model of ONE offline-signing unit: the reference's big-integer operation list
+ * (SURVEY.md section 8a "Per-unit totals", counted from src/utilities/mta/{mod,range_proofs}.rs,
+ * src/utilities/zk_pdl_with_slack/mod.rs and sign/rounds.rs INCLUDING the reference's redundant
+ * work: each MessageB::b re-verifies the three AliceProofs, Round5 re-verifies the party's own PDL
+ * proof, Paillier decrypt recomputes its CRT constants per call) executed with GMP mpz_powm /
+ * mpz_invert on random operands of the reference's sizes.  secp256k1 and SHA-256 work (<1 % of
+ * the unit) is not included.  Used only as bench.py's CPU baseline for phases/s. */
+typedef struct { size_t lo, hi; uint64_t seed; } oplist_job;
+
+static uint64_t lcg(uint64_t* s) { *s = *s * 6364136223846793005ULL + 1442695040888963407ULL; return *s; }
+static void rnd_mpz(mpz_t z, int bits, uint64_t* s, int odd_top) {
+    uint32_t buf[160];
+    int limbs = (bits + 31) / 32;
+    for (int i = 0; i < limbs; i++) buf[i] = (uint32_t)(lcg(s) >> 32);
+    if (bits & 31) buf[limbs - 1] &= (1u << (bits & 31)) - 1;
+    if (odd_top) { buf[0] |= 1; buf[limbs - 1] |= 1u << ((bits - 1) & 31); }
+    imp(z, buf, limbs);
+}
+static void powm_n(mpz_t r, mpz_t b, mpz_t e, mpz_t m, int mod_bits, int exp_bits, uint64_t* s, int times) {
+    for (int i = 0; i < times; i++) {
+        rnd_mpz(b, mod_bits - 1, s, 0);
+        rnd_mpz(e, exp_bits, s, 0);
+        mpz_powm(r, b, e, m);
+    }
+}
+static void inv_n(mpz_t r, mpz_t b, mpz_t m, int mod_bits, uint64_t* s, int times) {
+    for (int i = 0; i < times; i++) { rnd_mpz(b, mod_bits - 1, s, 0); mpz_invert(r, b, m); }
+}
+static void* oplist_worker(void* arg) {
+    oplist_job* j = (oplist_job*)arg;
+    mpz_t nt, n, nn, pp, p, b, e, r;
+    mpz_init(nt); mpz_init(n); mpz_init(nn); mpz_init(pp); mpz_init(p); mpz_init(b); mpz_init(e); mpz_init(r);
+    uint64_t s = j->seed + 0x9e3779b97f4a7c15ULL * (j->lo + 1);
+    rnd_mpz(nt, 2048, &s, 1); rnd_mpz(n, 2048, &s, 1); mpz_mul(nn, n, n);
+    rnd_mpz(p, 1024, &s, 1); mpz_mul(pp, p, p);
+    for (size_t u = j->lo; u < j->hi; u++) {
+        /* class A: N_tilde */
+        powm_n(r, b, e, nt, 2048, 256, &s, 3 + 6 + 1 + 2);   /* a2 h1^a, a3 z^e, a7, a8 z^-e */
+        powm_n(r, b, e, nt, 2048, 2304, &s, 3 + 1);          /* h2^ro */
+        powm_n(r, b, e, nt, 2048, 768, &s, 3 + 6 + 1 + 2);   /* h1^alpha, h1^s1 */
+        powm_n(r, b, e, nt, 2048, 2816, &s, 3 + 6 + 1 + 2);  /* h2^gamma, h2^s2/s3 */
+        inv_n(r, b, nt, 2048, &s, 6 + 2);
+        /* class B: N */
+        powm_n(r, b, e, n, 2048, 256, &s, 3 + 1);
+        /* class C: N^2 */
+        powm_n(r, b, e, nn, 4096, 2048, &s, 1 + 3 + 6 + 2 + 1 + 2);  /* r^N, beta^N, s^N, r'^N, beta^N, s2^N */
+        powm_n(r, b, e, nn, 4096, 256, &s, 6 + 2 + 2);              /* c^e, c_a^b, c^-e */
+        powm_n(r, b, e, nn, 4096, 768, &s, 1 + 2);                  /* (N+1)^alpha, (N+1)^s1 */
+        inv_n(r, b, nn, 4096, &s, 6 + 2);
+        /* class D: Paillier decrypt x2 (CRT, constants recomputed per call) */
+        powm_n(r, b, e, pp, 2048, 1024, &s, 4);
+        inv_n(r, b, p, 1024, &s, 6);
+    }
+    mpz_clear(nt); mpz_clear(n); mpz_clear(nn); mpz_clear(pp); mpz_clear(p); mpz_clear(b); mpz_clear(e); mpz_clear(r);
+    return NULL;
+}
+int oracle_unit_oplist(size_t units, int nthreads, uint64_t seed) {
+    if (nthreads < 1) nthreads = 1;
+    if ((size_t)nthreads > units) nthreads = (int)(units ? units : 1);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+    oplist_job* jobs = (oplist_job*)malloc(sizeof(oplist_job) * nthreads);
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t] = (oplist_job){units * t / nthreads, units * (t + 1) / nthreads, seed};
+        if (nthreads == 1) oplist_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, oplist_worker, &jobs[t]);
+    }
+    if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+    return 0;
+}
