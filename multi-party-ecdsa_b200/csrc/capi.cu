@@ -113,7 +113,9 @@ static cudaError_t launch_modexp(cudaStream_t s, const uint32_t* base, const uin
     return cudaGetLastError();
 }
 
-static int default_tpi(int mod_bits) { return mod_bits == 1024 ? 4 : mod_bits == 2048 ? 8 : 16; }
+// measured on B200 (gpurun_out/first.log, round 1): 2048-bit 394k/359k/321k/244k modexp/s for TPI 4/8/16/32;
+// 4096-bit 99k/91k/78k for TPI 8/16/32; 1024-bit 2.73M/2.43M/1.79M for TPI 4/8/16
+static int default_tpi(int mod_bits) { return mod_bits == 1024 ? 4 : mod_bits == 2048 ? 4 : 8; }
 
 static cudaError_t dispatch_modexp(int mod_bits, int tpi, cudaStream_t s, const uint32_t* base, const uint32_t* exp,
                                    const uint32_t* mod, const uint32_t* mod_idx, uint32_t* out, uint8_t* status,
@@ -201,29 +203,32 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
 }
 
 // ------------------------------------------------------------------------------------ IMAD peak
-// Eight independent 64-bit accumulators per thread, acc += a*b as IMAD.WIDE.U32 (the
+// NACC independent 64-bit accumulators per thread, acc += a*b as IMAD.WIDE.U32 (the
 // instruction every Montgomery row is made of; the .X carry variant issues on the same
-// pipe at the same rate), ~24 registers so the SM runs at full occupancy.
+// pipe at the same rate); few registers so the SM runs at full occupancy.
+template <int NACC>
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
-    uint64_t acc[8];
+    uint64_t acc[NACC];
     uint32_t a[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { a[j] = (seed + j) * (threadIdx.x | 1u); acc[j] = (uint64_t)seed * (j + 1) + threadIdx.x; }
+    for (int j = 0; j < 8; j++) a[j] = (seed + j) * (threadIdx.x | 1u);
+#pragma unroll
+    for (int j = 0; j < NACC; j++) acc[j] = (uint64_t)seed * (j + 1) + threadIdx.x;
     uint32_t b = seed ^ 0x85ebca6bu ^ threadIdx.x;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 32 / NACC; u++) {
             const uint32_t bu = b ^ a[u];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
+            for (int j = 0; j < NACC; j++)
                 asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[(j + u) & 7]), "r"(bu));
         }
         b = b * 5u + (uint32_t)acc[0];
     }
     uint64_t x = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) x ^= acc[j];
+    for (int j = 0; j < NACC; j++) x ^= acc[j];
     if (x == 0x12345678u) sink[0] = (uint32_t)x;
 }
 
@@ -235,11 +240,12 @@ extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_ou
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c->device));
     const int iters = 1 << 13, block = 256, grid = prop.multiProcessorCount * 16;
-    imad_peak_kernel<<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u, 64);   // warm-up
+    imad_peak_kernel<8><<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u, 64);   // warm-up
     float best = 1e30f;
-    for (int rep = 0; rep < 3; rep++) {
+    for (int rep = 0; rep < 6; rep++) {
         CK(cudaEventRecord(c->ev0, c->stream));
-        imad_peak_kernel<<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, iters);
+        if (rep & 1) imad_peak_kernel<16><<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, iters);
+        else imad_peak_kernel<8><<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, iters);
         CK(cudaEventRecord(c->ev1, c->stream));
         CK(cudaEventSynchronize(c->ev1));
         float t;
@@ -247,7 +253,7 @@ extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_ou
         if (t < best) best = t;
     }
     CK(cudaGetLastError());
-    c->launches += 4;
+    c->launches += 7;
     double macs = (double)grid * block * (double)iters * 32.0;   // 4 x 8 wide MACs per iteration
     if (mac32_per_s) *mac32_per_s = macs / (best * 1e-3);
     if (ms_out) *ms_out = best;

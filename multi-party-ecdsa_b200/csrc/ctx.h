@@ -27,6 +27,7 @@ struct tecdsa_keyset {
     uint32_t* mem = nullptr;
     uint32_t* tab[tecdsa::KT_COUNT] = {};
     uint32_t* ypk = nullptr;
+    uint32_t* fb = nullptr;      // fixed-base tables of (h1, h2) per key row, see jobs.cuh
     int n_keysets = 0;
 };
 

@@ -43,8 +43,16 @@ struct Builder {
         ExpClass& k = l.cls[l.n_classes++];
         k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
         k.mul[0] = m0; k.mul[1] = m1; k.nbases = nb; k.nmul = nm; k.wide0 = wide0;
+        k.fb = nullptr; k.fb_row = Operand{nullptr, nullptr, 0, 0, 0}; k.fb_sel[0] = k.fb_sel[1] = 0;
         k.out = out(out_field); k.out_stride = A.size[out_field]; k.count = U; k.item_begin = l.total_items;
         l.total_items += (U + gpw - 1) / gpw;
+    }
+    // out = [m0 *] h2^e_h2 * h1^e_h1 mod N_tilde(rows) through the per-key fixed-base tables
+    void fb_class(ExpLaunch& l, int gpw, const uint32_t* rows, Operand e_h2, int el_h2, Operand e_h1, int el_h1, int nm, Operand m0, int out_field) {
+        const Operand none = {nullptr, nullptr, 0, 0, 0};
+        exp_class(l, gpw, key(KT_NT, rows), 2, none, e_h2, el_h2, none, e_h1, el_h1, nm, m0, none, out_field);
+        ExpClass& k = l.cls[l.n_classes - 1];
+        k.fb = ks->fb; k.fb_row = Operand{nullptr, rows, 0, 1, 0}; k.fb_sel[0] = 1; k.fb_sel[1] = 0;
     }
     void inv_class(InvLaunch& l, int gpw, Operand mod, Operand in, int out_field, int flag_byte) {
         InvClass& k = l.cls[l.n_classes++];
@@ -96,11 +104,19 @@ extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_ke
     gg20_key_setup<<<(rows + 31) / 32, 32, 0, c->stream>>>(d_ptrs, rows);
     c->count_launch();
     CK(cudaGetLastError());
+    {   // fixed-base tables for (h1, h2) mod N_tilde of every key row
+        const size_t fb_limbs = (size_t)rows * 2 * FB_WINDOWS * (1 << WINDOW_BITS) * 64;
+        CK(cudaMalloc(&ks->fb, fb_limbs * 4));
+        const int groups = rows * 2, per_block = 128 / TPI_2048;
+        fb_build_kernel<64, TPI_2048><<<(groups + per_block - 1) / per_block, 128, 0, c->stream>>>(ks->tab[KT_NT], ks->tab[KT_H1], ks->tab[KT_H2], ks->fb, rows);
+        c->count_launch();
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(c->stream));
     // parity bits of the uploaded moduli are validated on the host copy of the inputs only
     for (int r = 0; r < rows; r++) {
         if (!(k->paillier_p[(size_t)r * 32] & 1) || !(k->paillier_q[(size_t)r * 32] & 1) || !(k->n_tilde[(size_t)r * 64] & 1)) {
-            cudaFree(ks->mem); delete ks;
+            cudaFree(ks->mem); cudaFree(ks->fb); delete ks;
             return tecdsa_fail(TECDSA_E_ARG, "keys_upload: even modulus");
         }
     }
@@ -111,6 +127,7 @@ extern "C" int tecdsa_keys_free(tecdsa_ctx* c, tecdsa_keyset* ks) {
     if (!ks) return 0;
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
     if (ks->mem) cudaFree(ks->mem);
+    if (ks->fb) cudaFree(ks->fb);
     delete ks;
     return 0;
 }
@@ -203,11 +220,9 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         // u = (alpha N + 1) * beta^N mod N^2                            (range_proofs.rs:53-55)
         B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(al + RND_AL_BETA, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_ALIN0 + x), NONE, F_U0 + x);
         // w = h1^alpha * h2^gamma mod N_tilde                           (range_proofs.rs:56-57)
-        B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 2, B.key(KT_H2, st_rows(x)), B.rnd(al + RND_AL_GAMMA, 88), 88,
-                    B.key(KT_H1, st_rows(x)), B.rnd(al + RND_AL_ALPHA, 24), 24, 0, NONE, NONE, F_WP0 + x);
+        B.fb_class(L64, GPW64, st_rows(x), B.rnd(al + RND_AL_GAMMA, 88), 88, B.rnd(al + RND_AL_ALPHA, 24), 24, 0, NONE, F_WP0 + x);
         // z = h1^a * h2^ro mod N_tilde                                  (range_proofs.rs:52)
-        B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 2, B.key(KT_H2, st_rows(x)), B.rnd(al + RND_AL_RHO, 72), 72,
-                    B.key(KT_H1, st_rows(x)), B.rnd(RND_K, 8), 8, 0, NONE, NONE, F_Z0 + x);
+        B.fb_class(L64, GPW64, st_rows(x), B.rnd(al + RND_AL_RHO, 72), 72, B.rnd(RND_K, 8), 8, 0, NONE, F_Z0 + x);
     }
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
     RUN(glue(c, gg20_r0_mid, A));
@@ -231,8 +246,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     RUN(run_inv(c, I128, 128)); RUN(run_inv(c, I64, 64));
     for (int x = 0; x < 3; x++) {
         // w' = h1^s1 * h2^s2 * (z^e)^-1 mod N_tilde                     (range_proofs.rs:129-132)
-        B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 2, B.key(KT_H2, st_rows(x)), B.peer(F_S20 + x), 92,
-                    B.key(KT_H1, st_rows(x)), B.peer(F_S10 + x), 28, 1, B.fld(F_ZEI0 + x), NONE, F_WV0 + x);
+        B.fb_class(L64, GPW64, st_rows(x), B.peer(F_S20 + x), 92, B.peer(F_S10 + x), 28, 1, B.fld(F_ZEI0 + x), F_WV0 + x);
         // u' = (s1 N + 1) * s^N * (c^e)^-1 mod N^2                      (range_proofs.rs:134-141)
         B.exp_class(L128, GPW128, B.key(KT_NN, rp), 1, B.peer(F_S0 + x, 64), B.key(KT_N, rp), 64, NONE, NONE, 0, 2, B.fld(F_GS10 + x), B.fld(F_CEI0 + x), F_UV0 + x);
     }
@@ -253,8 +267,8 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     RUN(glue(c, gg20_r3, A));
     // ================= Round 4 (rounds.rs:431-498): R, R_dash, PDLwSlackProof::prove against the peer's statement
     RUN(glue(c, gg20_r4_pre, A));
-    B.exp_class(L64, GPW64, B.key(KT_NT, rp), 2, B.key(KT_H2, rp), B.rnd(RND_PDL_RHO, 72), 72, B.key(KT_H1, rp), B.rnd(RND_K, 8), 8, 0, NONE, NONE, F_PZ);          // z  (:78-84)
-    B.exp_class(L64, GPW64, B.key(KT_NT, rp), 2, B.key(KT_H2, rp), B.rnd(RND_PDL_GAMMA, 88), 88, B.key(KT_H1, rp), B.rnd(RND_PDL_ALPHA, 24), 24, 0, NONE, NONE, F_PU3); // u3 (:93-99)
+    B.fb_class(L64, GPW64, rp, B.rnd(RND_PDL_RHO, 72), 72, B.rnd(RND_K, 8), 8, 0, NONE, F_PZ);                  // z  (:78-84)
+    B.fb_class(L64, GPW64, rp, B.rnd(RND_PDL_GAMMA, 88), 88, B.rnd(RND_PDL_ALPHA, 24), 24, 0, NONE, F_PU3);     // u3 (:93-99)
     // u2 = (N+1)^alpha * beta^N mod N^2, with (N+1)^alpha == 1 + alpha N (declared shortcut, identical value) (:86-92)
     B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(RND_PDL_BETA, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_PLIN), NONE, F_PU2);
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
@@ -282,7 +296,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         const uint32_t* stmt = j ? ro : rp;
         Operand s1 = j ? B.peer(F_PS1) : B.fld(F_PS1), s2 = j ? B.peer(F_PS2, 64) : B.fld(F_PS2, 64), s3 = j ? B.peer(F_PS3) : B.fld(F_PS3);
         // u3' = h1^s1 * h2^s3 * z^-e mod N_tilde                         (:158-172)
-        B.exp_class(L64, GPW64, B.key(KT_NT, stmt), 2, B.key(KT_H2, stmt), s3, 92, B.key(KT_H1, stmt), s1, 28, 1, B.fld(F_VZEI0 + j), NONE, F_VU30 + j);
+        B.fb_class(L64, GPW64, stmt, s3, 92, s1, 28, 1, B.fld(F_VZEI0 + j), F_VU30 + j);
         // u2' = (N+1)^s1 * s2^N * c^-e mod N^2                           (:144-157)
         B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, s2, B.key(KT_N, prover), 64, NONE, NONE, 0, 2, B.fld(F_VLIN0 + j), B.fld(F_VCEI0 + j), F_VU20 + j);
     }

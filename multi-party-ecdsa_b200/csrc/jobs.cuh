@@ -54,11 +54,17 @@ struct ExpClass {
     int nbases;             // 0..2
     int nmul;               // 0..2
     int wide0;              // base[0] is 2K limbs wide and is reduced mod n first (c mod p^2, kzen-paillier decrypt)
+    // fixed-base mode: both bases are per-key constants (h1, h2 of a DLogStatement) whose powers
+    // base^(j * 2^(5w)) were tabulated at key upload; the job is then a pure product, no squarings.
+    const uint32_t* fb;     // nullptr = off; else tables [row][2][FB_WINDOWS][32][K] in Montgomery form
+    Operand fb_row;         // idx -> key row of instance i (ptr unused)
+    int fb_sel[2];          // which of the row's two tables base[b] is (0 = h1, 1 = h2)
     int count;              // instances
     int item_begin;         // first warp-item of this class in the launch (prefix sum)
 };
 
 static constexpr int MAX_CLASSES = 64;
+static constexpr int FB_WINDOWS = 589;          // covers 92-limb (2944-bit) exponents
 struct ExpLaunch {
     ExpClass cls[MAX_CLASSES];
     int n_classes;
@@ -95,6 +101,24 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
         mont_setup<TPI, L>(m);
 
         uint32_t acc[L];
+#pragma unroll
+        for (int j = 0; j < L; j++) acc[j] = m.one[j];
+        if (c.fb) {
+            // fixed-base product: acc = prod_b prod_w T_b[w][window_w(e_b)]
+            const size_t row = __ldg(c.fb_row.idx + (size_t)i * c.fb_row.idx_stride);
+            uint32_t bb[L];
+#pragma unroll 1
+            for (int b = 0; b < c.nbases; b++) {
+                const uint32_t* tb = c.fb + (row * 2 + c.fb_sel[b]) * (size_t)FB_WINDOWS * TBL * K;
+                const uint32_t* e = operand_at(c.exp[b], i);
+                const int nwb = (c.exp_limbs[b] * 32 + WINDOW_BITS - 1) / WINDOW_BITS;
+#pragma unroll 1
+                for (int w = 0; w < nwb; w++) {
+                    load_limbs<TPI, L>(bb, tb + ((size_t)w * TBL + exp_window(e, c.exp_limbs[b], w)) * K);
+                    mont_mul<TPI, L>(acc, acc, bb, m.n, m.n0inv);
+                }
+            }
+        } else {
         // window tables: base*R powers 0..31 for each base
         for (int b = 0; b < c.nbases; b++) {
             uint32_t x[L], xr[L], t[L];
@@ -132,8 +156,6 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
             }
         }
         __syncwarp();
-#pragma unroll
-        for (int j = 0; j < L; j++) acc[j] = m.one[j];
         if (c.nbases > 0) {
             const uint32_t* e0 = operand_at(c.exp[0], i);
             const uint32_t* e1 = c.nbases > 1 ? operand_at(c.exp[1], i) : e0;
@@ -162,6 +184,7 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
                 if (do_mul) mont_mul<TPI, L>(acc, acc, bb, m.n, m.n0inv);
             }
         }
+        }
         // plain multipliers; the last Montgomery product also leaves the Montgomery domain
         uint32_t u[L];
         if (c.nmul == 0) {
@@ -180,6 +203,40 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
         }
         if (live) store_limbs<TPI, L>(c.out + (size_t)g * c.out_stride, acc);
         __syncwarp();
+    }
+}
+
+// One lane-group per (key row, base): T[w][j] = base^(j * 2^(5w)) * R mod N_tilde for
+// w < FB_WINDOWS, j < 32 (entry 0 = R mod n).  Run once per key upload.
+template <int K, int TPI>
+__global__ void __launch_bounds__(128)
+fb_build_kernel(const uint32_t* __restrict__ mod_tab, const uint32_t* __restrict__ h1_tab, const uint32_t* __restrict__ h2_tab,
+                uint32_t* __restrict__ fb, int rows) {
+    constexpr int L = K / TPI;
+    constexpr int TBL = 1 << WINDOW_BITS;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
+    const bool live = g < rows * 2;
+    const int gi = live ? g : rows * 2 - 1;
+    const int row = gi >> 1, sel = gi & 1;
+    MontCtx<L> m;
+    load_limbs<TPI, L>(m.n, mod_tab + (size_t)row * K);
+    mont_setup<TPI, L>(m);
+    uint32_t x[L], bw[L], t[L];
+    load_limbs<TPI, L>(x, (sel ? h2_tab : h1_tab) + (size_t)row * K);
+    mont_mul<TPI, L>(bw, x, m.rr, m.n, m.n0inv);                 // base * R
+    uint32_t* tb = fb + (size_t)gi * FB_WINDOWS * TBL * K;
+#pragma unroll 1
+    for (int w = 0; w < FB_WINDOWS; w++) {
+        uint32_t* tw = tb + (size_t)w * TBL * K;
+        if (live) { store_limbs<TPI, L>(tw, m.one); store_limbs<TPI, L>(tw + K, bw); }
+#pragma unroll
+        for (int j = 0; j < L; j++) t[j] = bw[j];
+#pragma unroll 1
+        for (int e = 2; e < TBL; e++) {
+            mont_mul<TPI, L>(t, t, bw, m.n, m.n0inv);
+            if (live) store_limbs<TPI, L>(tw + (size_t)e * K, t);
+        }
+        mont_mul<TPI, L>(bw, t, bw, m.n, m.n0inv);               // base^(31 * 2^(5w)) * base^(2^(5w)) = base^(2^(5(w+1)))
     }
 }
 
