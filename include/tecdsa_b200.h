@@ -32,6 +32,7 @@ extern "C" {
 #endif
 
 typedef struct tecdsa_ctx tecdsa_ctx;
+typedef struct tecdsa_keyset tecdsa_keyset;   /* device-resident key material, see tecdsa_keys_upload */
 
 enum { TECDSA_HOST = 0, TECDSA_DEVICE = 1 };
 
@@ -82,6 +83,45 @@ int tecdsa_modexp_batch(tecdsa_ctx* ctx, int mod_bits, int exp_limbs, const uint
                         const uint32_t* modulus, const uint32_t* mod_idx, size_t n_mod, uint32_t* out,
                         uint8_t* status, size_t count, int mem);
 
+/* out[i] = a[i] * b[i] mod modulus   (BigInt::mod_mul, src/utilities/zk_pdl_with_slack/mod.rs:198; the `(x * y) % n`
+ * products of src/utilities/mta/range_proofs.rs:52-57,129-141).  mod_bits in {2048, 4096}, odd moduli.            */
+int tecdsa_modmul_batch(tecdsa_ctx* ctx, int mod_bits, const uint32_t* a, const uint32_t* b, const uint32_t* modulus,
+                        const uint32_t* mod_idx, size_t n_mod, uint32_t* out, size_t count, int mem);
+/* out[i] = a[i]^-1 mod modulus, ok[i] = 1; or ok[i] = 0 (and out = 0) when gcd != 1 — `BigInt::mod_inv -> Option`
+ * (src/utilities/mta/range_proofs.rs:122,135; src/utilities/zk_pdl_with_slack/mod.rs:192).  Odd moduli.            */
+int tecdsa_modinv_batch(tecdsa_ctx* ctx, int mod_bits, const uint32_t* a, const uint32_t* modulus, const uint32_t* mod_idx,
+                        size_t n_mod, uint32_t* out, uint8_t* ok, size_t count, int mem);
+/* out[i] = scalars[i] * points[i] on secp256k1 (`Point * Scalar`, gg_2020/party_i.rs:560-562,682,784); points == NULL
+ * means the generator (`Point::generator() * s`).  Points are affine x||y (16 limbs, all-zero = identity); scalars
+ * are reduced mod q; a point that is not on the curve yields the identity.                                          */
+int tecdsa_secp_mul_batch(tecdsa_ctx* ctx, const uint32_t* points, const uint32_t* scalars, uint32_t* out, size_t count, int mem);
+
+/* ---- L1: Paillier (kzen-paillier 0.4.2 as called from src/utilities/mta/mod.rs:68,133,140,145,165) ----------------
+ * n = [n_keys][64] public moduli, key_idx[i] selects the key of element i (NULL: element i uses row i).
+ * encrypt: c = (1 + m n) r^n mod n^2 (`encrypt_with_chosen_randomness`); mul: c^k mod n^2 (k has k_limbs <= 64 limbs);
+ * add: c1 c2 mod n^2; decrypt: CRT form over an uploaded key set (row = keyset*3 + party), m in [0, n).              */
+int tecdsa_paillier_encrypt_batch(tecdsa_ctx* ctx, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* m,
+                                  const uint32_t* r, uint32_t* c, size_t count, int mem);
+int tecdsa_paillier_mul_batch(tecdsa_ctx* ctx, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* c,
+                              const uint32_t* k, int k_limbs, uint32_t* out, size_t count, int mem);
+int tecdsa_paillier_add_batch(tecdsa_ctx* ctx, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* c1,
+                              const uint32_t* c2, uint32_t* out, size_t count, int mem);
+int tecdsa_paillier_decrypt_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* key_row, const uint32_t* c,
+                                  uint32_t* m, size_t count, int mem);
+
+/* ---- L2: MtA range proof, Alice side (src/utilities/mta/range_proofs.rs:105-193) ---------------------------------
+ * ek_row / st_row: key rows (keyset*3 + party) of Alice's Paillier key and of the verifier's (N~, h1, h2) statement.
+ * generate: a (8 limbs), cipher (128), r (64) and the sampled alpha (24) < q^3, beta (64) in Z*_N, gamma (88) < q^3 N~,
+ * rho (72) < q N~  ->  z (64), e (8), s (64), s1 (28), s2 (92).  verify: status[i] = TECDSA_ST_OK or the first failing
+ * check (RANGE: s1 > q^3; NOT_INVERTIBLE; HASH_MISMATCH), i.e. `false` of AliceProof::verify.                         */
+int tecdsa_alice_proof_generate_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row,
+                                      const uint32_t* a, const uint32_t* cipher, const uint32_t* r, const uint32_t* alpha,
+                                      const uint32_t* beta, const uint32_t* gamma, const uint32_t* rho, uint32_t* z, uint32_t* e,
+                                      uint32_t* s, uint32_t* s1, uint32_t* s2, size_t count, int mem);
+int tecdsa_alice_proof_verify_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row,
+                                    const uint32_t* cipher, const uint32_t* z, const uint32_t* e, const uint32_t* s,
+                                    const uint32_t* s1, const uint32_t* s2, uint8_t* status, size_t count, int mem);
+
 /* ---- L3: the batched GG20 offline-signing stage ----------------------------------------
  * One "unit" = one party's OfflineStage Round0..Round6
  *   (src/protocols/multi_party_ecdsa/gg_2020/state_machine/sign/rounds.rs:68-636,
@@ -91,7 +131,6 @@ int tecdsa_modexp_batch(tecdsa_ctx* ctx, int mod_bits, int exp_limbs, const uint
  * device memory.  The LocalKey material (keygen/rounds.rs:310-322) is uploaded once per key
  * set; per-key constants (N^2, p^2, q^2, the CRT constants of Paillier decrypt) are derived
  * on the device.                                                                          */
-typedef struct tecdsa_keyset tecdsa_keyset;
 typedef struct {
     size_t n_keysets;             /* rows below are indexed by keyset*3 + party (party 0..2)      */
     const uint32_t* paillier_p;   /* [rows][32]  DecryptionKey.p  (1024-bit prime)                 */

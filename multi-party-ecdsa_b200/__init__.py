@@ -31,6 +31,8 @@ EXPORTS = [
     "tecdsa_ctx_create", "tecdsa_ctx_destroy", "tecdsa_ctx_sync", "tecdsa_last_error", "tecdsa_ctx_set_tpi",
     "tecdsa_ctx_last_kernel_ms", "tecdsa_ctx_launch_count", "tecdsa_modexp_batch", "tecdsa_imad_peak",
     "tecdsa_keys_upload", "tecdsa_keys_free", "tecdsa_keys_table", "tecdsa_gg20_offline_batch", "tecdsa_gg20_debug_field",
+    "tecdsa_modmul_batch", "tecdsa_modinv_batch", "tecdsa_secp_mul_batch", "tecdsa_paillier_encrypt_batch", "tecdsa_paillier_mul_batch",
+    "tecdsa_paillier_add_batch", "tecdsa_paillier_decrypt_batch", "tecdsa_alice_proof_generate_batch", "tecdsa_alice_proof_verify_batch",
 ]
 
 
@@ -157,3 +159,92 @@ class Engine:
         st = np.full(n, 255, dtype=np.uint8)
         self.modexp_raw(mod_bits, el, b, e, m, out, st)
         return limbs_to_ints(out), st
+
+
+# ----------------------------------------------------------------------------- L0 / L1 wrappers (batched BigInt / Paillier calls)
+def _bind_l01(lib):
+    if getattr(lib, "_l01_bound", False):
+        return
+    V, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.tecdsa_modmul_batch.argtypes = [V, I, V, V, V, V, S, V, S, I]
+    lib.tecdsa_modinv_batch.argtypes = [V, I, V, V, V, S, V, V, S, I]
+    lib.tecdsa_secp_mul_batch.argtypes = [V, V, V, V, S, I]
+    lib.tecdsa_paillier_encrypt_batch.argtypes = [V, V, V, S, V, V, V, S, I]
+    lib.tecdsa_paillier_mul_batch.argtypes = [V, V, V, S, V, V, I, V, S, I]
+    lib.tecdsa_paillier_add_batch.argtypes = [V, V, V, S, V, V, V, S, I]
+    lib.tecdsa_paillier_decrypt_batch.argtypes = [V, V, V, V, V, S, I]
+    lib._l01_bound = True
+
+
+def _mod_mul(self, a, b, modulus, mod_bits=2048):
+    """Batched `BigInt::mod_mul(a, b, modulus)`."""
+    _bind_l01(self.lib)
+    k = mod_bits // 32
+    A, B, M = ints_to_limbs(a, k), ints_to_limbs(b, k), ints_to_limbs(modulus, k)
+    out = np.zeros_like(A)
+    self._ck(self.lib.tecdsa_modmul_batch(self._ctx, mod_bits, _ptr(A), _ptr(B), _ptr(M), None, 0, _ptr(out), len(a), HOST), "modmul_batch")
+    return limbs_to_ints(out)
+
+
+def _mod_inv(self, a, modulus, mod_bits=2048):
+    """Batched `BigInt::mod_inv(a, modulus)` -> list of int or None."""
+    _bind_l01(self.lib)
+    k = mod_bits // 32
+    A, M = ints_to_limbs(a, k), ints_to_limbs(modulus, k)
+    out = np.zeros_like(A)
+    ok = np.zeros(len(a), dtype=np.uint8)
+    self._ck(self.lib.tecdsa_modinv_batch(self._ctx, mod_bits, _ptr(A), _ptr(M), None, 0, _ptr(out), _ptr(ok), len(a), HOST), "modinv_batch")
+    return [v if o else None for v, o in zip(limbs_to_ints(out), ok)]
+
+
+def _secp_mul(self, points, scalars):
+    """Batched `Point * Scalar`; points = None means the generator.  Points are (x, y) tuples or None (identity)."""
+    _bind_l01(self.lib)
+    n = len(scalars)
+    K_ = ints_to_limbs(scalars, 8)
+    P = None if points is None else ints_to_limbs([0 if p is None else p[0] | (p[1] << 256) for p in points], 16)
+    out = np.zeros((n, 16), dtype=np.uint32)
+    self._ck(self.lib.tecdsa_secp_mul_batch(self._ctx, _ptr(P), _ptr(K_), _ptr(out), n, HOST), "secp_mul_batch")
+    return [None if v == 0 else (v & ((1 << 256) - 1), v >> 256) for v in limbs_to_ints(out)]
+
+
+def _paillier_encrypt(self, n_list, key_idx, m, r):
+    """`Paillier::encrypt_with_chosen_randomness` batched: c = (1 + m n) r^n mod n^2."""
+    _bind_l01(self.lib)
+    N, idx = ints_to_limbs(n_list, 64), np.asarray(key_idx, dtype=np.uint32)
+    Mv, R = ints_to_limbs(m, 64), ints_to_limbs(r, 64)
+    out = np.zeros((len(m), 128), dtype=np.uint32)
+    self._ck(self.lib.tecdsa_paillier_encrypt_batch(self._ctx, _ptr(N), _ptr(idx), len(n_list), _ptr(Mv), _ptr(R), _ptr(out), len(m), HOST), "paillier_encrypt")
+    return limbs_to_ints(out)
+
+
+def _paillier_mul(self, n_list, key_idx, c, k, k_limbs=8):
+    _bind_l01(self.lib)
+    N, idx = ints_to_limbs(n_list, 64), np.asarray(key_idx, dtype=np.uint32)
+    C, Kk = ints_to_limbs(c, 128), ints_to_limbs(k, k_limbs)
+    out = np.zeros_like(C)
+    self._ck(self.lib.tecdsa_paillier_mul_batch(self._ctx, _ptr(N), _ptr(idx), len(n_list), _ptr(C), _ptr(Kk), k_limbs, _ptr(out), len(c), HOST), "paillier_mul")
+    return limbs_to_ints(out)
+
+
+def _paillier_add(self, n_list, key_idx, c1, c2):
+    _bind_l01(self.lib)
+    N, idx = ints_to_limbs(n_list, 64), np.asarray(key_idx, dtype=np.uint32)
+    C1, C2 = ints_to_limbs(c1, 128), ints_to_limbs(c2, 128)
+    out = np.zeros_like(C1)
+    self._ck(self.lib.tecdsa_paillier_add_batch(self._ctx, _ptr(N), _ptr(idx), len(n_list), _ptr(C1), _ptr(C2), _ptr(out), len(c1), HOST), "paillier_add")
+    return limbs_to_ints(out)
+
+
+def _paillier_decrypt(self, keysets_handle, key_rows, c):
+    """`Paillier::decrypt` (CRT) batched over an uploaded key set (gg20.KeySets)."""
+    _bind_l01(self.lib)
+    rows = np.asarray(key_rows, dtype=np.uint32)
+    C = ints_to_limbs(c, 128)
+    out = np.zeros((len(c), 64), dtype=np.uint32)
+    self._ck(self.lib.tecdsa_paillier_decrypt_batch(self._ctx, keysets_handle, _ptr(rows), _ptr(C), _ptr(out), len(c), HOST), "paillier_decrypt")
+    return limbs_to_ints(out)
+
+
+Engine.mod_mul, Engine.mod_inv, Engine.secp_mul = _mod_mul, _mod_inv, _secp_mul
+Engine.paillier_encrypt, Engine.paillier_mul, Engine.paillier_add, Engine.paillier_decrypt = _paillier_encrypt, _paillier_mul, _paillier_add, _paillier_decrypt

@@ -55,7 +55,7 @@ __device__ __forceinline__ void put_point_compressed(Sha256& h, const Affine& a)
     h.put_fixed(a.x.v, 8);
 }
 // curv `H::new().chain_points(..).result_scalar()` [R]: 65-byte uncompressed points, digest mod q
-__device__ __noinline__ U256 hash_points_scalar(const Affine* pts, int n) {
+static __device__ __noinline__ U256 hash_points_scalar(const Affine* pts, int n) {
     Sha256 h; h.init();
     for (int i = 0; i < n; i++) put_point_uncompressed(h, pts[i]);
     U256 d; h.finish(d.v);
@@ -77,7 +77,7 @@ __device__ __forceinline__ U256 lagrange2(uint32_t own_party, uint32_t peer_part
     return sc_mul(xp, sc_inv(sc_sub(xp, xo)));
 }
 // curv `DLogProof::prove` [R] (call sites utilities/mta/mod.rs:147-148).  out: pk 16 | T 16 | response 8
-__device__ __noinline__ void dlog_prove(uint32_t* out, const U256& sk, const U256& nonce) {
+static __device__ __noinline__ void dlog_prove(uint32_t* out, const U256& sk, const U256& nonce) {
     Affine pts[3];
     pts[0] = mul_G(nonce); pts[1] = affine_G(); pts[2] = mul_G(sk);
     U256 e = hash_points_scalar(pts, 3);
@@ -85,7 +85,7 @@ __device__ __noinline__ void dlog_prove(uint32_t* out, const U256& sk, const U25
     affine_store(out, pts[2]); affine_store(out + 16, pts[0]); u256_store(out + 32, resp);
 }
 // curv `DLogProof::verify` [R] (utilities/mta/mod.rs:170-171)
-__device__ __noinline__ bool dlog_verify(const uint32_t* in) {
+static __device__ __noinline__ bool dlog_verify(const uint32_t* in) {
     Affine pts[3];
     pts[2] = affine_load(in); pts[0] = affine_load(in + 16); pts[1] = affine_G();
     if (pts[2].inf || pts[0].inf || !on_curve(pts[2]) || !on_curve(pts[0])) return false;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void hash_commit_point(uint32_t* out8, const Affine& 
 // ------------------------------------------------------------------------------ round 0
 // SignKeys::create + phase1_broadcast (party_i.rs:546-589) and the plain factors of MessageA::a
 // (utilities/mta/mod.rs:68-75, range_proofs.rs:53).
-__global__ void gg20_r0_pre(Arena A) {
+static __global__ void gg20_r0_pre(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const uint32_t* rnd = A.p(F_RND, u);
@@ -123,7 +123,7 @@ __global__ void gg20_r0_pre(Arena A) {
         st::mul_add(A.p(F_ALIN0 + x, u), 128, rnd + RND_AL + x * RND_AL_STRIDE + RND_AL_ALPHA, 24, N, 64, &one, 1);
 }
 // e = H(N | N+1 | c | z | u | w); s1 = e*a + alpha; s2 = e*ro + gamma (range_proofs.rs:174-182,87-88)
-__device__ __noinline__ void alice_hash(uint32_t* e8, const uint32_t* N, const uint32_t* c, const uint32_t* z,
+static __device__ __noinline__ void alice_hash(uint32_t* e8, const uint32_t* N, const uint32_t* c, const uint32_t* z,
                                         const uint32_t* uu, const uint32_t* w) {
     Sha256 h; h.init();
     h.put_bigint(N, 64);
@@ -138,7 +138,7 @@ __device__ __noinline__ void alice_hash(uint32_t* e8, const uint32_t* N, const u
     h.put_bigint(w, 64);
     h.finish(e8);
 }
-__global__ void gg20_r0_mid(Arena A) {
+static __global__ void gg20_r0_mid(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const uint32_t* rnd = A.p(F_RND, u);
@@ -155,7 +155,7 @@ __global__ void gg20_r0_mid(Arena A) {
 // ------------------------------------------------------------------------------ round 1
 // AliceProof::verify prologue for the peer's proofs (range_proofs.rs:118,134) and the plain
 // factor of Paillier encrypt inside MessageB::b (utilities/mta/mod.rs:133).
-__global__ void gg20_r1_pre(Arena A) {
+static __global__ void gg20_r1_pre(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -174,7 +174,7 @@ __global__ void gg20_r1_pre(Arena A) {
     st::mul_add(A.p(F_LBW, u), 128, rnd + RND_BT_W, 64, Np, 64, &one, 1);
 }
 // end of AliceProof::verify (range_proofs.rs:143-153), rest of MessageB::b (mta/mod.rs:132,146-148)
-__global__ void gg20_r1_post(Arena A) {
+static __global__ void gg20_r1_post(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -201,7 +201,7 @@ __global__ void gg20_r1_post(Arena A) {
 // ------------------------------------------------------------------------------ round 2
 // kzen-paillier CRT decrypt tail [R]: mp = L_p(c^(p-1) mod p^2) * hp mod p, likewise mq,
 // m = mp + p * ((mq - mp) * p^-1 mod q)   (call site utilities/mta/mod.rs:165)
-__device__ __noinline__ void decrypt_finish(uint32_t* m64, const Arena& A, uint32_t row, const uint32_t* dp, const uint32_t* dq) {
+static __device__ __noinline__ void decrypt_finish(uint32_t* m64, const Arena& A, uint32_t row, const uint32_t* dp, const uint32_t* dq) {
     uint32_t t[32], lp[32], mp[32], mq[32], scratch[65];
     const uint32_t *p = A.k(KT_P, row), *q = A.k(KT_Q, row);
     // L_p(dp) = (dp - 1) / p, exact: low 1024 bits of (dp - 1) * p^-1 mod 2^1024
@@ -227,7 +227,7 @@ __device__ __noinline__ void decrypt_finish(uint32_t* m64, const Arena& A, uint3
 // MessageB::verify_proofs_get_alpha (mta/mod.rs:160-179) for the gamma and the w message, the
 // g_w_vec assert (sign/rounds.rs:281), phase2_delta_i / phase2_sigma_i (party_i.rs:591-618),
 // phase3_compute_t_i + PedersenProof::prove [R] (party_i.rs:620-634)
-__global__ void gg20_r2(Arena A) {
+static __global__ void gg20_r2(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -272,7 +272,7 @@ __global__ void gg20_r2(Arena A) {
 
 // ------------------------------------------------------------------------------ round 3
 // PedersenProof::verify [R] for every signer (sign/rounds.rs:365-378), phase3_reconstruct_delta (party_i.rs:635-640)
-__device__ __noinline__ bool pedersen_verify(const uint32_t* ped, const Affine& com) {
+static __device__ __noinline__ bool pedersen_verify(const uint32_t* ped, const Affine& com) {
     Affine pts[5];
     pts[0] = affine_G(); pts[1] = affine_H(); pts[2] = com; pts[3] = affine_load(ped + 8); pts[4] = affine_load(ped + 24);
     if (com.inf || !on_curve(com) || !on_curve(pts[3]) || !on_curve(pts[4])) return false;
@@ -281,7 +281,7 @@ __device__ __noinline__ bool pedersen_verify(const uint32_t* ped, const Affine& 
     Jac rhs = jac_add(jac_add(jac_from_affine(pts[3]), jac_from_affine(pts[4])), jac_mul(jac_from_affine(com), e));
     return affine_eq(lhs, jac_to_affine(rhs));
 }
-__global__ void gg20_r3(Arena A) {
+static __global__ void gg20_r3(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -295,7 +295,7 @@ __global__ void gg20_r3(Arena A) {
 // ------------------------------------------------------------------------------ round 4
 // SignKeys::phase4 (party_i.rs:642-687), R_dash (sign/rounds.rs:452), first half of PDLwSlackProof::prove
 // (utilities/zk_pdl_with_slack/mod.rs:85-92)
-__global__ void gg20_r4_pre(Arena A) {
+static __global__ void gg20_r4_pre(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -315,7 +315,7 @@ __global__ void gg20_r4_pre(Arena A) {
     st::mul_add(A.p(F_PLIN, u), 128, rnd + RND_PDL_ALPHA, 24, A.k(KT_N, A.row_own[u]), 64, &one, 1);
 }
 // e = H(G | Q | c | z | u1 | u2 | u3) with points as from_bytes(compressed) (zk_pdl_with_slack/mod.rs:102-110)
-__device__ __noinline__ void pdl_hash(uint32_t* e8, const Affine& Gp, const Affine& Qp, const uint32_t* c, const uint32_t* z,
+static __device__ __noinline__ void pdl_hash(uint32_t* e8, const Affine& Gp, const Affine& Qp, const uint32_t* c, const uint32_t* z,
                                       const Affine& u1, const uint32_t* u2, const uint32_t* u3) {
     Sha256 h; h.init();
     put_point_compressed(h, Gp);
@@ -327,7 +327,7 @@ __device__ __noinline__ void pdl_hash(uint32_t* e8, const Affine& Gp, const Affi
     h.put_bigint(u3, 64);
     h.finish(e8);
 }
-__global__ void gg20_r4_mid(Arena A) {
+static __global__ void gg20_r4_mid(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const uint32_t* rnd = A.p(F_RND, u);
@@ -340,7 +340,7 @@ __global__ void gg20_r4_mid(Arena A) {
 
 // ------------------------------------------------------------------------------ round 5
 // PDLwSlackProof::verify for both signers' proofs (party_i.rs:719-766 -> zk_pdl_with_slack/mod.rs:127-179)
-__global__ void gg20_r5_pre(Arena A) {
+static __global__ void gg20_r5_pre(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -355,12 +355,12 @@ __global__ void gg20_r5_pre(Arena A) {
     }
 }
 // curv HomoELGamalProof [R] (party_i.rs:778-833)
-__device__ __noinline__ U256 heg_hash(const Affine& T, const Affine& A3, const Affine& Gp, const Affine& D, const Affine& E) {
+static __device__ __noinline__ U256 heg_hash(const Affine& T, const Affine& A3, const Affine& Gp, const Affine& D, const Affine& E) {
     Affine pts[7];
     pts[0] = T; pts[1] = A3; pts[2] = Gp; pts[3] = affine_H(); pts[4] = affine_G(); pts[5] = D; pts[6] = E;
     return hash_points_scalar(pts, 7);
 }
-__global__ void gg20_r5_post(Arena A) {
+static __global__ void gg20_r5_post(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -397,7 +397,7 @@ __global__ void gg20_r5_post(Arena A) {
 }
 
 // ------------------------------------------------------------------------------ round 6 + outputs
-__device__ __noinline__ bool heg_verify(const uint32_t* heg, const Affine& R, const Affine& D, const Affine& E) {
+static __device__ __noinline__ bool heg_verify(const uint32_t* heg, const Affine& R, const Affine& D, const Affine& E) {
     Affine T = affine_load(heg), A3 = affine_load(heg + 16);
     if (!on_curve(T) || !on_curve(A3) || !on_curve(D) || !on_curve(E)) return false;
     U256 z1 = load_scalar(heg + 32), z2 = load_scalar(heg + 40);
@@ -415,7 +415,7 @@ __device__ __forceinline__ void put_padded(Sha256& h, const uint32_t* limbs, int
 }
 // phase6_verify_proof + phase6_check_S_i_sum (party_i.rs:801-848), then the unit's result record:
 // a SHA-256 over every message it emitted, in the fixed-width encoding of oracle/gg20_oracle.py
-__global__ void gg20_r6(Arena A) {
+static __global__ void gg20_r6(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
@@ -463,7 +463,7 @@ __global__ void gg20_r6(Arena A) {
 
 // ------------------------------------------------------------------------------ per-key constants
 // One thread per key row: N^2, p^2, q^2, p-1, q-1 and the CRT constants of Paillier decrypt.
-__global__ void gg20_key_setup(uint32_t* const* tables, int rows) {
+static __global__ void gg20_key_setup(uint32_t* const* tables, int rows) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     auto T = [&](int t) { return tables[t] + (size_t)r * KEY_SIZE_D[t]; };

@@ -1,0 +1,381 @@
+// L0 / L1 / L2 batch entry points (include/tecdsa_b200.h): the scalar calls of curv-kzen
+// `BigInt`, kzen-paillier `Paillier::*` and the in-tree MtA range proof, batched.  They are thin
+// compositions of the same job-list kernels and glue device functions the L3 offline-stage
+// driver uses (jobs.cuh, modinv.cuh, gg20_glue.cuh); results are canonical residues /
+// proof bytes identical to the L3 path and to the oracle.
+#include "ctx.h"
+#include "gg20_glue.cuh"
+#include "modinv.cuh"
+
+#include <vector>
+
+using namespace tecdsa;
+
+namespace {
+
+// Stream-ordered staging of caller buffers: HOST pointers are copied to device scratch (and
+// results copied back by finish()), DEVICE pointers are used in place.
+struct Stage {
+    tecdsa_ctx* c;
+    int mem;
+    std::vector<void*> scratch;
+    struct Back { void* host; void* dev; size_t bytes; };
+    std::vector<Back> back;
+    int err = 0;
+    Stage(tecdsa_ctx* ctx, int m) : c(ctx), mem(m) {}
+    void* alloc(size_t bytes) {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, bytes ? bytes : 16, c->stream) != cudaSuccess) { err = tecdsa_fail(TECDSA_E_NOMEM, "cudaMallocAsync"); return nullptr; }
+        scratch.push_back(p);
+        return p;
+    }
+    template <typename T> const T* in(const T* p, size_t n) {
+        if (!p || mem == TECDSA_DEVICE) return p;
+        T* d = static_cast<T*>(alloc(n * sizeof(T)));
+        if (d && cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "H2D copy");
+        return d;
+    }
+    template <typename T> T* out(T* p, size_t n) {
+        if (!p || mem == TECDSA_DEVICE) return p;
+        T* d = static_cast<T*>(alloc(n * sizeof(T)));
+        if (d) back.push_back({p, d, n * sizeof(T)});
+        return d;
+    }
+    template <typename T> T* tmp(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+    int finish() {
+        for (auto& b : back)
+            if (cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "D2H copy");
+        for (void* p : scratch) cudaFreeAsync(p, c->stream);
+        scratch.clear();
+        if (mem == TECDSA_HOST && cudaStreamSynchronize(c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "sync");
+        return err;
+    }
+};
+
+const Operand NONE = {nullptr, nullptr, 0, 0, 0};
+Operand arr(const uint32_t* p, uint32_t limbs) { return Operand{p, nullptr, limbs, 0, limbs}; }
+Operand tab(const uint32_t* p, const uint32_t* idx, uint32_t limbs) { return Operand{p, idx, limbs, 1, limbs}; }
+
+struct Launches {
+    ExpLaunch e64, e128;
+    InvLaunch i64, i128;
+    Launches() { e64.n_classes = e64.total_items = e128.n_classes = e128.total_items = 0; i64.n_classes = i64.total_items = i128.n_classes = i128.total_items = 0; }
+};
+void add_exp(ExpLaunch& l, int K, int count, Operand mod, int nb, Operand b0, Operand e0, int el0, Operand b1, Operand e1, int el1,
+             int nm, Operand m0, Operand m1, uint32_t* out, uint32_t out_stride) {
+    const int gpw = 32 / (K == 64 ? TPI_2048 : TPI_4096);
+    ExpClass& k = l.cls[l.n_classes++];
+    k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
+    k.mul[0] = m0; k.mul[1] = m1; k.nbases = nb; k.nmul = nm; k.wide0 = 0;
+    k.fb = nullptr; k.fb_row = NONE; k.fb_sel[0] = k.fb_sel[1] = 0;
+    k.out = out; k.out_stride = out_stride; k.count = count; k.item_begin = l.total_items;
+    l.total_items += (count + gpw - 1) / gpw;
+}
+void add_fb(ExpLaunch& l, int count, const tecdsa_keyset* ks, const uint32_t* rows, Operand e_h2, int el_h2, Operand e_h1, int el_h1,
+            int nm, Operand m0, uint32_t* out) {
+    add_exp(l, 64, count, tab(ks->tab[KT_NT], rows, 64), 2, NONE, e_h2, el_h2, NONE, e_h1, el_h1, nm, m0, NONE, out, 64);
+    ExpClass& k = l.cls[l.n_classes - 1];
+    k.fb = ks->fb; k.fb_row = Operand{nullptr, rows, 0, 1, 0}; k.fb_sel[0] = 1; k.fb_sel[1] = 0;
+}
+void add_inv(InvLaunch& l, int K, int count, Operand mod, Operand in, uint32_t* out, uint8_t* ok) {
+    const int gpw = 32 / (K == 64 ? TPI_2048 : TPI_4096);
+    InvClass& k = l.cls[l.n_classes++];
+    k.mod = mod; k.in = in; k.out = out; k.out_stride = K; k.ok = ok; k.ok_stride = 1; k.count = count; k.item_begin = l.total_items;
+    l.total_items += (count + gpw - 1) / gpw;
+}
+int run(tecdsa_ctx* c, ExpLaunch& l, int K) {
+    if (!l.n_classes) return 0;
+    int rc = c->launch_exp(l, K);
+    l.n_classes = l.total_items = 0;
+    return rc;
+}
+int run(tecdsa_ctx* c, InvLaunch& l, int K) {
+    if (!l.n_classes) return 0;
+    int rc = c->launch_inv(l, K);
+    l.n_classes = l.total_items = 0;
+    return rc;
+}
+int check_bits(int mod_bits) { return (mod_bits == 2048 || mod_bits == 4096) ? 0 : tecdsa_fail(TECDSA_E_UNSUPPORTED, "mod_bits must be 2048 or 4096"); }
+
+// ---- glue kernels of the stand-alone entry points ----------------------------------------------
+// out[i] (128 limbs) = 1 + m[i] * N[row]      (the (1 + m n) factor of Paillier encrypt)
+__global__ void k_lin(uint32_t* out, const uint32_t* m, int m_limbs, const uint32_t* n_tab, const uint32_t* rows, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t one = 1;
+    st::mul_add(out + (size_t)i * 128, 128, m + (size_t)i * m_limbs, m_limbs, n_tab + (size_t)(rows ? rows[i] : i) * 64, 64, &one, 1);
+}
+__global__ void k_square(uint32_t* nn, const uint32_t* n, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    st::mul(nn + (size_t)i * 128, n + (size_t)i * 64, 64, n + (size_t)i * 64, 64);
+}
+__global__ void k_secp_mul(uint32_t* out, const uint32_t* pts, const uint32_t* scalars, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Affine P = pts ? affine_load(pts + (size_t)i * 16) : affine_G();
+    U256 k = sc_from_limbs(scalars + (size_t)i * 8, 8);
+    Affine r;
+    if (!P.inf && !on_curve(P)) { r.inf = true; r.x = u256_zero(); r.y = u256_zero(); }
+    else r = pt_mul(P, k);
+    affine_store(out + (size_t)i * 16, r);
+}
+// Paillier decrypt tail over the keyset's CRT constants
+__global__ void k_decrypt_finish(Arena A, uint32_t* out, const uint32_t* dp, const uint32_t* dq, const uint32_t* rows, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    decrypt_finish(out + (size_t)i * 64, A, rows[i], dp + (size_t)i * 64, dq + (size_t)i * 64);
+}
+// AliceProof::generate middle: e, s1, s2   (range_proofs.rs:174-182, 87-88)
+__global__ void k_alice_mid(Arena A, const uint32_t* ek_rows, const uint32_t* cipher, const uint32_t* z, const uint32_t* u, const uint32_t* w,
+                            const uint32_t* a, const uint32_t* alpha, const uint32_t* gamma, const uint32_t* rho, uint32_t* e, uint32_t* s1,
+                            uint32_t* s2, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t* ei = e + (size_t)i * 8;
+    alice_hash(ei, A.k(KT_N, ek_rows[i]), cipher + (size_t)i * 128, z + (size_t)i * 64, u + (size_t)i * 128, w + (size_t)i * 64);
+    st::mul_add(s1 + (size_t)i * 28, 28, ei, 8, a + (size_t)i * 8, 8, alpha + (size_t)i * 24, 24);
+    st::mul_add(s2 + (size_t)i * 92, 92, ei, 8, rho + (size_t)i * 72, 72, gamma + (size_t)i * 88, 88);
+}
+// AliceProof::verify prologue: range check + gs1 = s1 N + 1   (range_proofs.rs:118,134)
+__global__ void k_alice_vpre(Arena A, const uint32_t* ek_rows, const uint32_t* s1, uint32_t* gs1, uint8_t* range_bad, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t* s = s1 + (size_t)i * 28;
+    range_bad[i] = st::cmp2(s, 28, Q3_LIMBS, 24) > 0;
+    uint32_t one = 1;
+    st::mul_add(gs1 + (size_t)i * 128, 128, s, 28, A.k(KT_N, ek_rows[i]), 64, &one, 1);
+}
+// AliceProof::verify epilogue: recompute e and compare   (range_proofs.rs:143-153)
+__global__ void k_alice_vpost(Arena A, const uint32_t* ek_rows, const uint32_t* cipher, const uint32_t* z, const uint32_t* u, const uint32_t* w,
+                              const uint32_t* e, const uint8_t* range_bad, const uint8_t* okz, const uint8_t* okc, uint32_t* e_scratch,
+                              uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint8_t st_ = TECDSA_ST_OK;
+    if (range_bad[i]) st_ = TECDSA_ST_RANGE;
+    else if (!okz[i] || !okc[i]) st_ = TECDSA_ST_NOT_INVERTIBLE;
+    else {
+        uint32_t* ei = e_scratch + (size_t)i * 8;
+        alice_hash(ei, A.k(KT_N, ek_rows[i]), cipher + (size_t)i * 128, z + (size_t)i * 64, u + (size_t)i * 128, w + (size_t)i * 64);
+        if (st::cmp(ei, e + (size_t)i * 8, 8) != 0) st_ = TECDSA_ST_HASH_MISMATCH;
+    }
+    status[i] = st_;
+}
+
+Arena key_arena(const tecdsa_keyset* ks) {
+    Arena A;
+    memset(&A, 0, sizeof(A));
+    for (int t = 0; t < KT_COUNT; t++) A.key[t] = ks->tab[t];
+    A.ypk = ks->ypk;
+    return A;
+}
+int grid_for(size_t count) { return (int)((count + 63) / 64); }
+
+}  // namespace
+
+#define RUN(x) do { int _rc = (x); if (_rc) { S.finish(); return _rc; } } while (0)
+#define KCHECK() do { c->count_launch(); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { S.finish(); return tecdsa_fail(TECDSA_E_CUDA, "kernel launch", _e); } } while (0)
+
+// ------------------------------------------------------------------------------------------ L0
+extern "C" int tecdsa_modmul_batch(tecdsa_ctx* c, int mod_bits, const uint32_t* a, const uint32_t* b, const uint32_t* modulus,
+                                   const uint32_t* mod_idx, size_t n_mod, uint32_t* out, size_t count, int mem) {
+    if (!c || !a || !b || !modulus || !out) return tecdsa_fail(TECDSA_E_ARG, "modmul: null argument");
+    if (check_bits(mod_bits)) return TECDSA_E_UNSUPPORTED;
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int K = mod_bits / 32;
+    Stage S(c, mem);
+    const uint32_t *da = S.in(a, count * K), *db = S.in(b, count * K), *dm = S.in(modulus, (mod_idx ? n_mod : count) * K), *di = S.in(mod_idx, count);
+    uint32_t* dout = S.out(out, count * K);
+    if (S.err) return S.finish();
+    Launches L;
+    ExpLaunch& l = K == 64 ? L.e64 : L.e128;
+    add_exp(l, K, (int)count, di ? tab(dm, di, K) : arr(dm, K), 0, NONE, NONE, 0, NONE, NONE, 0, 2, arr(da, K), arr(db, K), dout, K);
+    RUN(run(c, l, K));
+    return S.finish();
+}
+
+extern "C" int tecdsa_modinv_batch(tecdsa_ctx* c, int mod_bits, const uint32_t* a, const uint32_t* modulus, const uint32_t* mod_idx,
+                                   size_t n_mod, uint32_t* out, uint8_t* ok, size_t count, int mem) {
+    if (!c || !a || !modulus || !out || !ok) return tecdsa_fail(TECDSA_E_ARG, "modinv: null argument");
+    if (check_bits(mod_bits)) return TECDSA_E_UNSUPPORTED;
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int K = mod_bits / 32;
+    Stage S(c, mem);
+    const uint32_t *da = S.in(a, count * K), *dm = S.in(modulus, (mod_idx ? n_mod : count) * K), *di = S.in(mod_idx, count);
+    uint32_t* dout = S.out(out, count * K);
+    uint8_t* dok = S.out(ok, count);
+    if (S.err) return S.finish();
+    Launches L;
+    InvLaunch& l = K == 64 ? L.i64 : L.i128;
+    add_inv(l, K, (int)count, di ? tab(dm, di, K) : arr(dm, K), arr(da, K), dout, dok);
+    RUN(run(c, l, K));
+    return S.finish();
+}
+
+extern "C" int tecdsa_secp_mul_batch(tecdsa_ctx* c, const uint32_t* points, const uint32_t* scalars, uint32_t* out, size_t count, int mem) {
+    if (!c || !scalars || !out) return tecdsa_fail(TECDSA_E_ARG, "secp_mul: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    Stage S(c, mem);
+    const uint32_t *dp = S.in(points, count * 16), *dk = S.in(scalars, count * 8);
+    uint32_t* dout = S.out(out, count * 16);
+    if (S.err) return S.finish();
+    k_secp_mul<<<grid_for(count), 64, 0, c->stream>>>(dout, dp, dk, (int)count);
+    KCHECK();
+    return S.finish();
+}
+
+// ------------------------------------------------------------------------------------------ L1: Paillier
+extern "C" int tecdsa_paillier_encrypt_batch(tecdsa_ctx* c, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* m,
+                                             const uint32_t* r, uint32_t* c_out, size_t count, int mem) {
+    if (!c || !n || !m || !r || !c_out) return tecdsa_fail(TECDSA_E_ARG, "paillier_encrypt: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const size_t nk = key_idx ? n_keys : count;
+    Stage S(c, mem);
+    const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *dm = S.in(m, count * 64), *dr = S.in(r, count * 64);
+    uint32_t* dc = S.out(c_out, count * 128);
+    uint32_t *nn = S.tmp<uint32_t>(nk * 128), *lin = S.tmp<uint32_t>(count * 128);
+    if (S.err) return S.finish();
+    k_square<<<grid_for(nk), 64, 0, c->stream>>>(nn, dn, (int)nk);
+    KCHECK();
+    k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dm, 64, dn, di, (int)count);
+    KCHECK();
+    Launches L;
+    Operand N = di ? tab(dn, di, 64) : arr(dn, 64), NN = di ? tab(nn, di, 128) : arr(nn, 128);
+    Operand rb = arr(dr, 64);
+    add_exp(L.e128, 128, (int)count, NN, 1, rb, N, 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, dc, 128);     // (1 + m n) * r^n mod n^2
+    RUN(run(c, L.e128, 128));
+    return S.finish();
+}
+
+extern "C" int tecdsa_paillier_mul_batch(tecdsa_ctx* c, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* ct,
+                                         const uint32_t* k, int k_limbs, uint32_t* c_out, size_t count, int mem) {
+    if (!c || !n || !ct || !k || !c_out || k_limbs <= 0 || k_limbs > 64) return tecdsa_fail(TECDSA_E_ARG, "paillier_mul: bad argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const size_t nk = key_idx ? n_keys : count;
+    Stage S(c, mem);
+    const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *dct = S.in(ct, count * 128), *dk = S.in(k, count * (size_t)k_limbs);
+    uint32_t* dc = S.out(c_out, count * 128);
+    uint32_t* nn = S.tmp<uint32_t>(nk * 128);
+    if (S.err) return S.finish();
+    k_square<<<grid_for(nk), 64, 0, c->stream>>>(nn, dn, (int)nk);
+    KCHECK();
+    Launches L;
+    add_exp(L.e128, 128, (int)count, di ? tab(nn, di, 128) : arr(nn, 128), 1, arr(dct, 128), arr(dk, k_limbs), k_limbs, NONE, NONE, 0, 0, NONE, NONE, dc, 128);
+    RUN(run(c, L.e128, 128));
+    return S.finish();
+}
+
+extern "C" int tecdsa_paillier_add_batch(tecdsa_ctx* c, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* c1,
+                                         const uint32_t* c2, uint32_t* c_out, size_t count, int mem) {
+    if (!c || !n || !c1 || !c2 || !c_out) return tecdsa_fail(TECDSA_E_ARG, "paillier_add: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const size_t nk = key_idx ? n_keys : count;
+    Stage S(c, mem);
+    const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *d1 = S.in(c1, count * 128), *d2 = S.in(c2, count * 128);
+    uint32_t* dc = S.out(c_out, count * 128);
+    uint32_t* nn = S.tmp<uint32_t>(nk * 128);
+    if (S.err) return S.finish();
+    k_square<<<grid_for(nk), 64, 0, c->stream>>>(nn, dn, (int)nk);
+    KCHECK();
+    Launches L;
+    add_exp(L.e128, 128, (int)count, di ? tab(nn, di, 128) : arr(nn, 128), 0, NONE, NONE, 0, NONE, NONE, 0, 2, arr(d1, 128), arr(d2, 128), dc, 128);
+    RUN(run(c, L.e128, 128));
+    return S.finish();
+}
+
+extern "C" int tecdsa_paillier_decrypt_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* key_row, const uint32_t* ct,
+                                             uint32_t* m_out, size_t count, int mem) {
+    if (!c || !ks || !key_row || !ct || !m_out) return tecdsa_fail(TECDSA_E_ARG, "paillier_decrypt: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    Stage S(c, mem);
+    const uint32_t *dr = S.in(key_row, count), *dct = S.in(ct, count * 128);
+    uint32_t* dm = S.out(m_out, count * 64);
+    uint32_t *dp = S.tmp<uint32_t>(count * 64), *dq = S.tmp<uint32_t>(count * 64);
+    if (S.err) return S.finish();
+    Launches L;
+    Operand cw = arr(dct, 128);
+    add_exp(L.e64, 64, (int)count, tab(ks->tab[KT_PP], dr, 64), 1, cw, tab(ks->tab[KT_PM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dp, 64);
+    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
+    add_exp(L.e64, 64, (int)count, tab(ks->tab[KT_QQ], dr, 64), 1, cw, tab(ks->tab[KT_QM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dq, 64);
+    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
+    RUN(run(c, L.e64, 64));
+    k_decrypt_finish<<<grid_for(count), 64, 0, c->stream>>>(key_arena(ks), dm, dp, dq, dr, (int)count);
+    KCHECK();
+    return S.finish();
+}
+
+// ------------------------------------------------------------------------------------------ L2: MtA range proof (Alice)
+extern "C" int tecdsa_alice_proof_generate_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row,
+                                                 const uint32_t* a, const uint32_t* cipher, const uint32_t* r, const uint32_t* alpha,
+                                                 const uint32_t* beta, const uint32_t* gamma, const uint32_t* rho, uint32_t* z, uint32_t* e,
+                                                 uint32_t* s, uint32_t* s1, uint32_t* s2, size_t count, int mem) {
+    if (!c || !ks || !ek_row || !st_row || !a || !cipher || !r || !alpha || !beta || !gamma || !rho || !z || !e || !s || !s1 || !s2)
+        return tecdsa_fail(TECDSA_E_ARG, "alice_proof_generate: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *da = S.in(a, count * 8), *dc = S.in(cipher, count * 128),
+                   *dr = S.in(r, count * 64), *dal = S.in(alpha, count * 24), *dbe = S.in(beta, count * 64), *dga = S.in(gamma, count * 88),
+                   *dro = S.in(rho, count * 72);
+    uint32_t *dz = S.out(z, count * 64), *de = S.out(e, count * 8), *ds = S.out(s, count * 64), *ds1 = S.out(s1, count * 28), *ds2 = S.out(s2, count * 92);
+    uint32_t *lin = S.tmp<uint32_t>(count * 128), *u = S.tmp<uint32_t>(count * 128), *w = S.tmp<uint32_t>(count * 64);
+    if (S.err) return S.finish();
+    Arena A = key_arena(ks);
+    k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dal, 24, ks->tab[KT_N], er, n);
+    KCHECK();
+    Launches L;
+    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, u, 128);  // u (:53-55)
+    add_fb(L.e64, n, ks, sr, arr(dga, 88), 88, arr(dal, 24), 24, 0, NONE, w);       // w = h1^alpha h2^gamma (:56-57)
+    add_fb(L.e64, n, ks, sr, arr(dro, 72), 72, arr(da, 8), 8, 0, NONE, dz);         // z = h1^a h2^ro       (:52)
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    k_alice_mid<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, da, dal, dga, dro, de, ds1, ds2, n);
+    KCHECK();
+    add_exp(L.e64, 64, n, tab(ks->tab[KT_N], er, 64), 1, arr(dr, 64), arr(de, 8), 8, NONE, NONE, 0, 1, arr(dbe, 64), NONE, ds, 64);   // s = r^e beta mod N (:86)
+    RUN(run(c, L.e64, 64));
+    return S.finish();
+}
+
+extern "C" int tecdsa_alice_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row,
+                                               const uint32_t* cipher, const uint32_t* z, const uint32_t* e, const uint32_t* s,
+                                               const uint32_t* s1, const uint32_t* s2, uint8_t* status, size_t count, int mem) {
+    if (!c || !ks || !ek_row || !st_row || !cipher || !z || !e || !s || !s1 || !s2 || !status)
+        return tecdsa_fail(TECDSA_E_ARG, "alice_proof_verify: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *dc = S.in(cipher, count * 128), *dz = S.in(z, count * 64),
+                   *de = S.in(e, count * 8), *ds = S.in(s, count * 64), *ds1 = S.in(s1, count * 28), *ds2 = S.in(s2, count * 92);
+    uint8_t* dst = S.out(status, count);
+    uint32_t *gs1 = S.tmp<uint32_t>(count * 128), *ze = S.tmp<uint32_t>(count * 64), *ce = S.tmp<uint32_t>(count * 128),
+             *zei = S.tmp<uint32_t>(count * 64), *cei = S.tmp<uint32_t>(count * 128), *w = S.tmp<uint32_t>(count * 64),
+             *u = S.tmp<uint32_t>(count * 128), *e2 = S.tmp<uint32_t>(count * 8);
+    uint8_t *bad = S.tmp<uint8_t>(count), *okz = S.tmp<uint8_t>(count), *okc = S.tmp<uint8_t>(count);
+    if (S.err) return S.finish();
+    Arena A = key_arena(ks);
+    k_alice_vpre<<<grid_for(count), 64, 0, c->stream>>>(A, er, ds1, gs1, bad, n);
+    KCHECK();
+    Launches L;
+    Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
+    add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);            // z^e (:122)
+    add_exp(L.e128, 128, n, NN, 1, arr(dc, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);        // c^e (:135)
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, okz);
+    add_inv(L.i128, 128, n, NN, arr(ce, 128), cei, okc);
+    RUN(run(c, L.i128, 128)); RUN(run(c, L.i64, 64));
+    add_fb(L.e64, n, ks, sr, arr(ds2, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), w);                             // w' (:129-132)
+    add_exp(L.e128, 128, n, NN, 1, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(gs1, 128), arr(cei, 128), u, 128);   // u' (:141)
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    k_alice_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, de, bad, okz, okc, e2, dst, n);
+    KCHECK();
+    return S.finish();
+}

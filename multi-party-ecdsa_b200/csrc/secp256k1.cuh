@@ -125,7 +125,7 @@ __device__ __forceinline__ U256 fe_sub(const U256& a, const U256& b) {
 __device__ __forceinline__ U256 fe_neg(const U256& a) { return u256_is_zero(a) ? a : fe_sub(u256_zero(), a); }
 __device__ __forceinline__ U256 fe_dbl(const U256& a) { return fe_add(a, a); }
 // a^(p-2)
-__device__ __noinline__ U256 fe_inv(const U256& a) {
+static __device__ __noinline__ U256 fe_inv(const U256& a) {
     // p - 2 = 2^256 - 2^32 - 979: plain square-and-multiply over its bits (MSB first)
     U256 r = u256_one();
     for (int i = 255; i >= 0; i--) {
@@ -205,7 +205,7 @@ __device__ __forceinline__ U256 sc_from_limbs(const uint32_t* x, int n) {
     return r;
 }
 // a^(q-2)  (`Scalar::invert`, party_i.rs:639)
-__device__ __noinline__ U256 sc_inv(const U256& a) {
+static __device__ __noinline__ U256 sc_inv(const U256& a) {
     U256 r = u256_one();
     for (int i = 255; i >= 0; i--) {
         r = sc_mul(r, r);
@@ -229,7 +229,7 @@ __device__ __forceinline__ Jac jac_from_affine(const Affine& a) {
 __device__ __forceinline__ Affine affine_G() { Affine a; a.x = u256_load(GX_LIMBS); a.y = u256_load(GY_LIMBS); a.inf = false; return a; }
 __device__ __forceinline__ Affine affine_H() { Affine a; a.x = u256_load(HX_LIMBS); a.y = u256_load(HY_LIMBS); a.inf = false; return a; }
 
-__device__ __noinline__ Jac jac_dbl(const Jac& p) {
+static __device__ __noinline__ Jac jac_dbl(const Jac& p) {
     if (jac_is_inf(p) || u256_is_zero(p.y)) return jac_identity();
     U256 A = fe_sqr(p.x), B = fe_sqr(p.y), C = fe_sqr(B);
     U256 t = fe_add(p.x, B);
@@ -244,7 +244,7 @@ __device__ __noinline__ Jac jac_dbl(const Jac& p) {
     return r;
 }
 // general Jacobian + Jacobian, all special cases handled
-__device__ __noinline__ Jac jac_add(const Jac& p, const Jac& q) {
+static __device__ __noinline__ Jac jac_add(const Jac& p, const Jac& q) {
     if (jac_is_inf(p)) return q;
     if (jac_is_inf(q)) return p;
     U256 z1z1 = fe_sqr(p.z), z2z2 = fe_sqr(q.z);
@@ -264,7 +264,7 @@ __device__ __noinline__ Jac jac_add(const Jac& p, const Jac& q) {
 }
 __device__ __forceinline__ Jac jac_add_affine(const Jac& p, const Affine& a) { return jac_add(p, jac_from_affine(a)); }
 __device__ __forceinline__ Jac jac_neg(const Jac& p) { Jac r = p; r.y = fe_neg(p.y); return r; }
-__device__ __noinline__ Affine jac_to_affine(const Jac& p) {
+static __device__ __noinline__ Affine jac_to_affine(const Jac& p) {
     Affine a;
     if (jac_is_inf(p)) { a.inf = true; a.x = u256_zero(); a.y = u256_zero(); return a; }
     U256 zi = fe_inv(p.z), zi2 = fe_sqr(zi);
@@ -272,7 +272,7 @@ __device__ __noinline__ Affine jac_to_affine(const Jac& p) {
     return a;
 }
 // `Point * Scalar`: 4-bit fixed-window, table of 16 Jacobian multiples in local memory
-__device__ __noinline__ Jac jac_mul(const Jac& base, const U256& k) {
+static __device__ __noinline__ Jac jac_mul(const Jac& base, const U256& k) {
     Jac tbl[16];
     tbl[0] = jac_identity();
     tbl[1] = base;

@@ -194,3 +194,38 @@ def synthetic_batch(keysets: Sequence[Sequence], n_sessions: int, seed: int):
                 fill(rows, RND_PDL_PARTS[2][0], 72, (_Q * nt).bit_length() - 1)
                 fill(rows, RND_PDL_PARTS[3][0], 88, (_Q ** 3 * nt).bit_length() - 1)
     return sessions, rnd
+
+
+# ----------------------------------------------------------------------------- L2: AliceProof (MtA range proof) batched
+def _bind_l2(lib):
+    if getattr(lib, "_l2_bound", False):
+        return
+    V, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.tecdsa_alice_proof_generate_batch.argtypes = [V] * 16 + [S, I]
+    lib.tecdsa_alice_proof_verify_batch.argtypes = [V] * 11 + [S, I]
+    lib._l2_bound = True
+
+
+def alice_proof_generate(eng: Engine, keys: KeySets, ek_row, st_row, a, cipher, r, alpha, beta, gamma, rho):
+    """Batched `AliceProof::generate` (range_proofs.rs:160-193) with explicit randomness; returns dict of int lists."""
+    _bind_l2(eng.lib)
+    n = len(a)
+    er, sr = np.asarray(ek_row, dtype=np.uint32), np.asarray(st_row, dtype=np.uint32)
+    ins = [ints_to_limbs(a, 8), ints_to_limbs(cipher, 128), ints_to_limbs(r, 64), ints_to_limbs(alpha, 24), ints_to_limbs(beta, 64),
+           ints_to_limbs(gamma, 88), ints_to_limbs(rho, 72)]
+    outs = {k: np.zeros((n, l), dtype=np.uint32) for k, l in (("z", 64), ("e", 8), ("s", 64), ("s1", 28), ("s2", 92))}
+    eng._ck(eng.lib.tecdsa_alice_proof_generate_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), *[_ptr(x) for x in ins],
+                                                      *[_ptr(outs[k]) for k in ("z", "e", "s", "s1", "s2")], n, HOST), "alice_proof_generate")
+    return {k: limbs_to_ints(v) for k, v in outs.items()}
+
+
+def alice_proof_verify(eng: Engine, keys: KeySets, ek_row, st_row, cipher, z, e, s, s1, s2) -> np.ndarray:
+    """Batched `AliceProof::verify` (range_proofs.rs:105-156): status byte per proof (0 = accept)."""
+    _bind_l2(eng.lib)
+    n = len(z)
+    er, sr = np.asarray(ek_row, dtype=np.uint32), np.asarray(st_row, dtype=np.uint32)
+    ins = [ints_to_limbs(cipher, 128), ints_to_limbs(z, 64), ints_to_limbs(e, 8), ints_to_limbs(s, 64), ints_to_limbs(s1, 28), ints_to_limbs(s2, 92)]
+    status = np.full(n, 255, dtype=np.uint8)
+    eng._ck(eng.lib.tecdsa_alice_proof_verify_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), *[_ptr(x) for x in ins], _ptr(status), n, HOST),
+            "alice_proof_verify")
+    return status

@@ -1,0 +1,116 @@
+"""GPU parity tests of the L0 / L1 / L2 batch entry points against the oracle."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import gg20_oracle as o
+from oracle.sampling import Drbg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("bits", [2048, 4096])
+def test_modmul_modinv(engine, bits):
+    rng = random.Random(bits + 1)
+    n = 70
+    mods = [rng.getrandbits(bits) | 1 | (1 << (bits - 1)) for _ in range(n)]
+    mods[0] = 3; mods[1] = (1 << bits) - 1; mods[2] = rng.getrandbits(bits - 2) | 1         # small / all-ones / short modulus
+    a = [rng.getrandbits(bits) for _ in range(n)]
+    b = [rng.getrandbits(bits) for _ in range(n)]
+    assert engine.mod_mul(a, b, mods, bits) == [x * y % m for x, y, m in zip(a, b, mods)]
+    # inverses: mix invertible and non-invertible operands (p*q moduli, multiples of p)
+    p1, q1 = 1000003, 998244353
+    mods[5] = p1 * q1; a[5] = p1 * 12345                      # gcd != 1
+    mods[6] = p1 * q1; a[6] = 0
+    a[7] = 1
+    got = engine.mod_inv(a, mods, bits)
+    for x, m, g in zip(a, mods, got):
+        try:
+            want = pow(x, -1, m)
+        except ValueError:
+            want = None
+        assert g == want, (x % 1000, m % 1000)
+
+
+def test_secp_mul_1m_style(engine):
+    """BASELINE.json configs[2] shape (scaled to what the oracle checks in seconds): generator and
+    variable-base scalar multiplications vs the oracle (itself pinned to OpenSSL)."""
+    rng = random.Random(3)
+    ks = [1, 2, o.Q - 1, 0] + [rng.randrange(1, o.Q) for _ in range(60)]
+    got = engine.secp_mul(None, ks)
+    assert got == [o.pt_mul(o.G, k) for k in ks]
+    pts = [o.pt_mul(o.G, rng.randrange(1, o.Q)) for _ in range(len(ks))]
+    pts[3] = None
+    got = engine.secp_mul(pts, ks)
+    assert got == [o.pt_mul(p, k) for p, k in zip(pts, ks)]
+    # size-independent property at a larger batch: (k1 + k2) G == k1 G + k2 G via three batched calls
+    n = 4096
+    k1 = [rng.randrange(1, o.Q) for _ in range(n)]
+    k2 = [rng.randrange(1, o.Q) for _ in range(n)]
+    s = engine.secp_mul(None, [(x + y) % o.Q for x, y in zip(k1, k2)])
+    a = engine.secp_mul(None, k1)
+    twice = engine.secp_mul(a, k2)                       # k2 * (k1 G)
+    both = engine.secp_mul(None, [x * y % o.Q for x, y in zip(k1, k2)])
+    assert twice == both
+    for i in range(0, n, 97):
+        assert s[i] == o.pt_add(a[i], o.pt_mul(o.G, k2[i]))
+
+
+def test_paillier_ops(engine, pkg, keyset):
+    from mpecdsa_b200 import gg20
+    rng = random.Random(4)
+    ns = [k.dk.p * k.dk.q for k in keyset]
+    n = 48
+    idx = [rng.randrange(3) for _ in range(n)]
+    m = [rng.randrange(ns[i]) for i in idx]
+    r = [rng.randrange(1, ns[i]) for i in idx]
+    c = engine.paillier_encrypt(ns, idx, m, r)
+    eks = [o.EncryptionKey(x, x * x) for x in ns]
+    assert c == [o.paillier_encrypt(eks[i], mm, rr) for i, mm, rr in zip(idx, m, r)]
+    k = [rng.randrange(o.Q) for _ in range(n)]
+    ck = engine.paillier_mul(ns, idx, c, k)
+    assert ck == [pow(cc, kk, eks[i].nn) for i, cc, kk in zip(idx, c, k)]
+    cs = engine.paillier_add(ns, idx, c, ck)
+    assert cs == [x * y % eks[i].nn for i, x, y in zip(idx, c, ck)]
+    ks = gg20.KeySets(engine, [keyset])
+    dec = engine.paillier_decrypt(ks.handle, idx, cs)
+    assert dec == [(mm + mm * kk) % ns[i] for i, mm, kk in zip(idx, m, k)]
+    assert dec == [o.paillier_decrypt(keyset[i].dk, x) for i, x in zip(idx, cs)]
+    ks.free()
+
+
+def test_alice_proof_generate_verify_batch(engine, pkg, keyset):
+    """BASELINE.json configs[3] shape at a size the oracle checks in seconds: proofs generated on the
+    GPU are byte-identical to the oracle's, verify on the GPU and under the oracle; tampered ones are
+    rejected with the reference's failure reason."""
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    rng = Drbg(0xB2000004, "alice-batch")
+    n = 24
+    q3 = o.Q ** 3
+    ek_row = [i % 3 for i in range(n)]
+    st_row = [(i // 3) % 3 for i in range(n)]
+    a, r, cph, al, be, ga, ro = [], [], [], [], [], [], []
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]
+        st = keyset[0].h1_h2_n_tilde_vec[st_row[i]]
+        a.append(rng.scalar()); r.append(rng.unit_mod(ek.n))
+        cph.append(o.paillier_encrypt(ek, a[-1], r[-1]))
+        al.append(rng.below(q3)); be.append(rng.unit_mod(ek.n)); ga.append(rng.below(q3 * st.N)); ro.append(rng.below(o.Q * st.N))
+    pf = gg20.alice_proof_generate(engine, ks, ek_row, st_row, a, cph, r, al, be, ga, ro)
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]
+        st = keyset[0].h1_h2_n_tilde_vec[st_row[i]]
+        want = o.alice_proof_generate(a[i], cph[i], ek, st, r[i], al[i], be[i], ga[i], ro[i])
+        assert (pf["z"][i], pf["e"][i], pf["s"][i], pf["s1"][i], pf["s2"][i]) == (want.z, want.e, want.s, want.s1, want.s2)
+        assert o.alice_proof_verify(want, cph[i], ek, st)
+    st_ok = gg20.alice_proof_verify(engine, ks, ek_row, st_row, cph, pf["z"], pf["e"], pf["s"], pf["s1"], pf["s2"])
+    assert not st_ok.any()
+    # tampering: wrong ciphertext, out-of-range s1, non-invertible z
+    bad_c = list(cph); bad_c[0] += 1
+    bad_s1 = list(pf["s1"]); bad_s1[1] = q3 + 1
+    bad_z = list(pf["z"]); bad_z[2] = 0
+    st1 = gg20.alice_proof_verify(engine, ks, ek_row, st_row, bad_c, bad_z, pf["e"], pf["s"], bad_s1, pf["s2"])
+    assert st1[0] == pkg.ST_HASH_MISMATCH and st1[1] == pkg.ST_RANGE and st1[2] == pkg.ST_NOT_INVERTIBLE and not st1[3:].any()
+    ks.free()
