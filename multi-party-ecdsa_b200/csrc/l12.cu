@@ -47,7 +47,10 @@ struct Stage {
             if (cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "D2H copy");
         for (void* p : scratch) cudaFreeAsync(p, c->stream);
         scratch.clear();
-        if (mem == TECDSA_HOST && cudaStreamSynchronize(c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "sync");
+        if (mem == TECDSA_HOST) {
+            cudaError_t e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "stream sync after batch", e);
+        }
         return err;
     }
 };

@@ -103,7 +103,11 @@ __device__ __forceinline__ bool group_modinv(uint32_t (&out)[L], const uint32_t 
             k++;
         }
     }
-    const bool ok = group_is_one<TPI, L>(u) && group_is_zero<TPI, L>(v);
+    // both predicates contain warp ballots: evaluate them unconditionally (no short-circuit), the
+    // groups of a warp disagree on the outcome
+    const bool u_one = group_is_one<TPI, L>(u);
+    const bool v_zero = group_is_zero<TPI, L>(v);
+    const bool ok = u_one & v_zero;
     // r < 2n (rh is its bit above the K limbs): bring below n, then x = n - r == a^-1 * 2^k (mod n)
     {
         uint32_t D[L];
@@ -120,24 +124,20 @@ __device__ __forceinline__ bool group_modinv(uint32_t (&out)[L], const uint32_t 
     for (int j = 0; j < L; j++) x[j] = m.n[j];
     (void)group_sub_masked<TPI, L>(x, r, 0xffffffffu, 1u);           // n - r  (r <= n)
     cond_sub<TPI, L>(x, m.n);                                        // r == 0 -> x == n -> 0
-    // remove 2^k:  j = 2*MBITS - k.   j >= MBITS: one product by 2^(j-MBITS); else two products.
+    // remove 2^k with two Montgomery products by powers of two: x * 2^j1 / R * 2^j2 / R with
+    // j1 + j2 = 2*MBITS - k.  k differs between the groups of a warp, so this tail must be
+    // branch-free (every lane runs the same shuffles): both products are always executed.
     int jj = 2 * MBITS - k;
+    if (jj > 2 * MBITS - 2) jj = 2 * MBITS - 2;            // k < 2 only for a == 0 / n == 1 (no inverse, result unused)
+    const int j1 = jj < MBITS ? jj : MBITS - 1;
+    const int j2 = jj - j1;
     uint32_t p[L];
-    if (jj >= MBITS) {
-        int bit = jj - MBITS;                      // < MBITS because k >= 1 whenever a != 0
-        if (bit >= MBITS) bit = MBITS - 1;
 #pragma unroll
-        for (int j = 0; j < L; j++) p[j] = ((bit >> 5) == gl * L + j) ? (1u << (bit & 31)) : 0u;
-        mont_mul<TPI, L>(out, x, p, m.n, m.n0inv);
-    } else {
+    for (int j = 0; j < L; j++) p[j] = ((j1 >> 5) == gl * L + j) ? (1u << (j1 & 31)) : 0u;
+    mont_mul<TPI, L>(x, x, p, m.n, m.n0inv);
 #pragma unroll
-        for (int j = 0; j < L; j++) p[j] = 0;
-        if (gl == 0) p[0] = 1;
-        mont_mul<TPI, L>(x, x, p, m.n, m.n0inv);
-#pragma unroll
-        for (int j = 0; j < L; j++) p[j] = ((jj >> 5) == gl * L + j) ? (1u << (jj & 31)) : 0u;
-        mont_mul<TPI, L>(out, x, p, m.n, m.n0inv);
-    }
+    for (int j = 0; j < L; j++) p[j] = ((j2 >> 5) == gl * L + j) ? (1u << (j2 & 31)) : 0u;
+    mont_mul<TPI, L>(out, x, p, m.n, m.n0inv);
     return ok;
 }
 

@@ -1,0 +1,49 @@
+// TEST INFRASTRUCTURE: compiles the product's single-thread "glue" device code (secp256k1, SHA-256,
+// plain-integer helpers, sigma proofs, Paillier CRT tail, per-key setup) for the HOST with shims
+// for the CUDA qualifiers, so that the CPU test-suite can check it against the oracle without a
+// GPU.  Nothing here is reachable from the product library.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+#define __constant__
+#define __global__
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, int n) { n &= 31; return n ? (lo >> n) | (hi << (32 - n)) : lo; }
+struct Dim3 { unsigned x, y, z; };
+static Dim3 blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, threadIdx = {0, 0, 0};
+#include "gg20_glue.cuh"
+using namespace tecdsa;
+
+extern "C" {
+void h_key_setup(uint32_t** tables, int rows) {
+    blockDim.x = rows;
+    for (int r = 0; r < rows; r++) { threadIdx.x = r; gg20_key_setup(tables, rows); }
+}
+void h_decrypt_finish(uint32_t* m64, uint32_t** tables, uint32_t row, const uint32_t* dp, const uint32_t* dq) {
+    Arena A; memset(&A, 0, sizeof(A));
+    for (int t = 0; t < KT_COUNT; t++) A.key[t] = tables[t];
+    decrypt_finish(m64, A, row, dp, dq);
+}
+void h_sc_from_limbs(uint32_t* out8, const uint32_t* x, int n) { U256 r = sc_from_limbs(x, n); memcpy(out8, r.v, 32); }
+void h_sc_mul(uint32_t* out8, const uint32_t* a, const uint32_t* b) { U256 r = sc_mul(u256_load(a), u256_load(b)); memcpy(out8, r.v, 32); }
+void h_sc_inv(uint32_t* out8, const uint32_t* a) { U256 r = sc_inv(u256_load(a)); memcpy(out8, r.v, 32); }
+void h_fe_mul(uint32_t* out8, const uint32_t* a, const uint32_t* b) { U256 r = fe_mul(u256_load(a), u256_load(b)); memcpy(out8, r.v, 32); }
+void h_pt_mul(uint32_t* out16, const uint32_t* p16, const uint32_t* k8) { affine_store(out16, pt_mul(affine_load(p16), u256_load(k8))); }
+void h_pt_add(uint32_t* out16, const uint32_t* a16, const uint32_t* b16) { affine_store(out16, pt_add_aff(affine_load(a16), affine_load(b16))); }
+void h_lagrange2(uint32_t* out8, uint32_t own, uint32_t peer) { U256 r = lagrange2(own, peer); memcpy(out8, r.v, 32); }
+void h_alice_hash(uint32_t* e8, const uint32_t* N, const uint32_t* c, const uint32_t* z, const uint32_t* u, const uint32_t* w) { alice_hash(e8, N, c, z, u, w); }
+void h_pdl_hash(uint32_t* e8, const uint32_t* G16, const uint32_t* Q16, const uint32_t* c, const uint32_t* z, const uint32_t* u1_16,
+                const uint32_t* u2, const uint32_t* u3) {
+    pdl_hash(e8, affine_load(G16), affine_load(Q16), c, z, affine_load(u1_16), u2, u3);
+}
+void h_hash_commit(uint32_t* out8, const uint32_t* p16, const uint32_t* blind8) { hash_commit_point(out8, affine_load(p16), blind8); }
+void h_dlog_prove(uint32_t* out40, const uint32_t* sk8, const uint32_t* nonce8) { dlog_prove(out40, u256_load(sk8), u256_load(nonce8)); }
+int h_dlog_verify(const uint32_t* in40) { return dlog_verify(in40) ? 1 : 0; }
+int h_pedersen_verify(const uint32_t* ped64, const uint32_t* com16) { return pedersen_verify(ped64, affine_load(com16)) ? 1 : 0; }
+int h_heg_verify(const uint32_t* heg48, const uint32_t* R16, const uint32_t* D16, const uint32_t* E16) {
+    return heg_verify(heg48, affine_load(R16), affine_load(D16), affine_load(E16)) ? 1 : 0;
+}
+void h_mul_add(uint32_t* d, int nd, const uint32_t* a, int na, const uint32_t* b, int nb, const uint32_t* c, int nc) { st::mul_add(d, nd, a, na, b, nb, c, nc); }
+}
