@@ -122,6 +122,37 @@ int tecdsa_alice_proof_verify_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, co
                                     const uint32_t* cipher, const uint32_t* z, const uint32_t* e, const uint32_t* s,
                                     const uint32_t* s1, const uint32_t* s2, uint8_t* status, size_t count, int mem);
 
+/* ---- L2: PDL with slack (src/utilities/zk_pdl_with_slack/mod.rs:68-179) --------------------------------------
+ * Statement (cipher, ek = key row ek_row, Q, G, (h1,h2,N~) = key row st_row); witness x (8 limbs), r (64).
+ * prove: sampled alpha (24) < q^3, beta (64) in [1,N-1), rho (72) < q N~, gamma (88) < q^3 N~
+ *        -> z (64), u1 (point, 16), u2 (128), u3 (64), s1 (28), s2 (64), s3 (92).
+ * verify: status TECDSA_ST_OK or TECDSA_ST_PDL_VERIFY (incl. the reference's unwrap() panic on a non-invertible
+ * z or ciphertext, mod.rs:192).                                                                                  */
+int tecdsa_pdl_prove_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, const uint32_t* x,
+                           const uint32_t* r, const uint32_t* cipher, const uint32_t* Q, const uint32_t* G, const uint32_t* alpha,
+                           const uint32_t* beta, const uint32_t* rho, const uint32_t* gamma, uint32_t* z, uint32_t* u1, uint32_t* u2,
+                           uint32_t* u3, uint32_t* s1, uint32_t* s2, uint32_t* s3, size_t count, int mem);
+int tecdsa_pdl_verify_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, const uint32_t* cipher,
+                            const uint32_t* Q, const uint32_t* G, const uint32_t* z, const uint32_t* u1, const uint32_t* u2,
+                            const uint32_t* u3, const uint32_t* s1, const uint32_t* s2, const uint32_t* s3, uint8_t* status, size_t count, int mem);
+
+/* ---- L2: Bob's MtA / MtAwc range proof (src/utilities/mta/range_proofs.rs:214-535; not called by OfflineStage,
+ * part of the public proof surface).  generate: a_enc, mta_enc (128), b (8), beta_prim (64), r (64) and the sampled
+ * alpha (24) < q^3, beta (64) in Z*_N, gamma (80) < q^2 N, ro (72) < q N~, ro_prim (88) < q^3 N~, sigma (72) < q N~,
+ * tau (88) < q^3 N~  ->  t, z (64), e (8), s (64), s1 (28), s2 (92), t1 (84), t2 (92) and, when check != 0 (MtAwc,
+ * `BobProofExt`), u = G * alpha (16).  verify: X == u == NULL is `BobProof::verify(.., None)`; otherwise
+ * `BobProofExt::verify` with X = G * b.  status: OK / RANGE / NOT_INVERTIBLE / HASH_MISMATCH / PROOF (EC check). */
+int tecdsa_bob_proof_generate_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, int check,
+                                    const uint32_t* a_enc, const uint32_t* mta_enc, const uint32_t* b, const uint32_t* beta_prim,
+                                    const uint32_t* r, const uint32_t* alpha, const uint32_t* beta, const uint32_t* gamma,
+                                    const uint32_t* ro, const uint32_t* ro_prim, const uint32_t* sigma, const uint32_t* tau,
+                                    uint32_t* t, uint32_t* z, uint32_t* e, uint32_t* s, uint32_t* s1, uint32_t* s2, uint32_t* t1,
+                                    uint32_t* t2, uint32_t* u, size_t count, int mem);
+int tecdsa_bob_proof_verify_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, const uint32_t* a_enc,
+                                  const uint32_t* mta_out, const uint32_t* t, const uint32_t* z, const uint32_t* e, const uint32_t* s,
+                                  const uint32_t* s1, const uint32_t* s2, const uint32_t* t1, const uint32_t* t2, const uint32_t* X,
+                                  const uint32_t* u, uint8_t* status, size_t count, int mem);
+
 /* ---- L3: the batched GG20 offline-signing stage ----------------------------------------
  * One "unit" = one party's OfflineStage Round0..Round6
  *   (src/protocols/multi_party_ecdsa/gg_2020/state_machine/sign/rounds.rs:68-636,

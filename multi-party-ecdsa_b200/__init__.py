@@ -33,6 +33,7 @@ EXPORTS = [
     "tecdsa_keys_upload", "tecdsa_keys_free", "tecdsa_keys_table", "tecdsa_gg20_offline_batch", "tecdsa_gg20_debug_field",
     "tecdsa_modmul_batch", "tecdsa_modinv_batch", "tecdsa_secp_mul_batch", "tecdsa_paillier_encrypt_batch", "tecdsa_paillier_mul_batch",
     "tecdsa_paillier_add_batch", "tecdsa_paillier_decrypt_batch", "tecdsa_alice_proof_generate_batch", "tecdsa_alice_proof_verify_batch",
+    "tecdsa_pdl_prove_batch", "tecdsa_pdl_verify_batch", "tecdsa_bob_proof_generate_batch", "tecdsa_bob_proof_verify_batch",
 ]
 
 

@@ -166,6 +166,132 @@ __global__ void k_alice_vpost(Arena A, const uint32_t* ek_rows, const uint32_t* 
     status[i] = st_;
 }
 
+
+// ---- PDL with slack (utilities/zk_pdl_with_slack/mod.rs:68-179) -------------------------------------
+// prove, first part: u1 = G * alpha, lin = 1 + alpha N
+__global__ void k_pdl_pre(Arena A, const uint32_t* ek_rows, const uint32_t* Gp, const uint32_t* alpha, uint32_t* u1, uint32_t* lin, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    affine_store(u1 + (size_t)i * 16, pt_mul(affine_load(Gp + (size_t)i * 16), sc_from_limbs(alpha + (size_t)i * 24, 24)));
+    uint32_t one = 1;
+    st::mul_add(lin + (size_t)i * 128, 128, alpha + (size_t)i * 24, 24, A.k(KT_N, ek_rows[i]), 64, &one, 1);
+}
+// e, s1 = e x + alpha, s3 = e rho + gamma  (:102-114)
+__global__ void k_pdl_mid(const uint32_t* Gp, const uint32_t* Qp, const uint32_t* cipher, const uint32_t* z, const uint32_t* u1, const uint32_t* u2,
+                          const uint32_t* u3, const uint32_t* x, const uint32_t* alpha, const uint32_t* rho, const uint32_t* gamma,
+                          uint32_t* e, uint32_t* s1, uint32_t* s3, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t* ei = e + (size_t)i * 8;
+    pdl_hash(ei, affine_load(Gp + (size_t)i * 16), affine_load(Qp + (size_t)i * 16), cipher + (size_t)i * 128, z + (size_t)i * 64,
+             affine_load(u1 + (size_t)i * 16), u2 + (size_t)i * 128, u3 + (size_t)i * 64);
+    st::mul_add(s1 + (size_t)i * 28, 28, ei, 8, x + (size_t)i * 8, 8, alpha + (size_t)i * 24, 24);
+    st::mul_add(s3 + (size_t)i * 92, 92, ei, 8, rho + (size_t)i * 72, 72, gamma + (size_t)i * 88, 88);
+}
+// verify prologue: e (into scratch) and lin = 1 + s1 N  (:128-150)
+__global__ void k_pdl_vpre(Arena A, const uint32_t* ek_rows, const uint32_t* Gp, const uint32_t* Qp, const uint32_t* cipher, const uint32_t* z,
+                           const uint32_t* u1, const uint32_t* u2, const uint32_t* u3, const uint32_t* s1, uint32_t* e, uint32_t* lin, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    pdl_hash(e + (size_t)i * 8, affine_load(Gp + (size_t)i * 16), affine_load(Qp + (size_t)i * 16), cipher + (size_t)i * 128, z + (size_t)i * 64,
+             affine_load(u1 + (size_t)i * 16), u2 + (size_t)i * 128, u3 + (size_t)i * 64);
+    uint32_t one = 1;
+    st::mul_add(lin + (size_t)i * 128, 128, s1 + (size_t)i * 28, 28, A.k(KT_N, ek_rows[i]), 64, &one, 1);
+}
+// verify epilogue: u1 == G s1 + Q (-e), u2 == u2', u3 == u3'  (:138-178)
+__global__ void k_pdl_vpost(const uint32_t* Gp, const uint32_t* Qp, const uint32_t* u1, const uint32_t* u2, const uint32_t* u3, const uint32_t* s1,
+                            const uint32_t* e, const uint32_t* u2t, const uint32_t* u3t, const uint8_t* okz, const uint8_t* okc, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Affine G_ = affine_load(Gp + (size_t)i * 16), Q_ = affine_load(Qp + (size_t)i * 16), U1 = affine_load(u1 + (size_t)i * 16);
+    bool ok = okz[i] && okc[i] && on_curve(G_) && on_curve(Q_) && on_curve(U1);
+    if (ok) {
+        Affine t = lin2(G_, sc_from_limbs(s1 + (size_t)i * 28, 28), Q_, sc_neg(sc_from_limbs(e + (size_t)i * 8, 8)));
+        ok = affine_eq(t, U1) && st::cmp(u2t + (size_t)i * 128, u2 + (size_t)i * 128, 128) == 0 &&
+             st::cmp(u3t + (size_t)i * 64, u3 + (size_t)i * 64, 64) == 0;
+    }
+    status[i] = ok ? TECDSA_ST_OK : TECDSA_ST_PDL_VERIFY;
+}
+
+// ---- Bob's MtA / MtAwc range proof (utilities/mta/range_proofs.rs:214-535) ----------------------------
+// lin = (x mod N) * N + 1 for x of xl limbs (x may exceed N: gamma < q^2 N, t1 = e beta' + gamma)
+__global__ void k_lin_wide(Arena A, const uint32_t* ek_rows, const uint32_t* x, int xl, uint32_t* lin, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t* N = A.k(KT_N, ek_rows[i]);
+    uint32_t red[64], one = 1;
+    st::mod_slow(red, x + (size_t)i * xl, xl, N, 64);
+    st::mul_add(lin + (size_t)i * 128, 128, red, 64, N, 64, &one, 1);
+}
+__device__ void bob_hash(uint32_t* e8, const uint32_t* N, const uint32_t* a_enc, const uint32_t* mta, const uint32_t* z, const uint32_t* zp,
+                         const uint32_t* t, const uint32_t* v, const uint32_t* w, const Affine* X, const Affine* U) {
+    Sha256 h; h.init();
+    h.put_bigint(N, 64);
+    uint32_t n1[65];
+    uint64_t cy = 1;
+    for (int i = 0; i < 64; i++) { cy += N[i]; n1[i] = (uint32_t)cy; cy >>= 32; }
+    n1[64] = (uint32_t)cy;
+    h.put_bigint(n1, 65);
+    h.put_bigint(a_enc, 128); h.put_bigint(mta, 128); h.put_bigint(z, 64); h.put_bigint(zp, 64); h.put_bigint(t, 64);
+    h.put_bigint(v, 128); h.put_bigint(w, 64);
+    if (X) { h.put_bigint(X->x.v, 8); h.put_bigint(X->y.v, 8); h.put_bigint(U->x.v, 8); h.put_bigint(U->y.v, 8); }   // coordinates as BigInt (:386-395)
+    h.finish(e8);
+}
+// generate: e and the five plain-integer responses (:433-470, 289-296); with `check` also X = G b, u = G alpha
+__global__ void k_bob_mid(Arena A, const uint32_t* ek_rows, int check, const uint32_t* a_enc, const uint32_t* mta, const uint32_t* z, const uint32_t* zp,
+                          const uint32_t* t, const uint32_t* v, const uint32_t* w, const uint32_t* b, const uint32_t* beta_prim, const uint32_t* alpha,
+                          const uint32_t* gamma, const uint32_t* ro, const uint32_t* ro_prim, const uint32_t* sigma, const uint32_t* tau,
+                          uint32_t* e, uint32_t* s1, uint32_t* s2, uint32_t* t1, uint32_t* t2, uint32_t* u_out, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t* ei = e + (size_t)i * 8;
+    Affine X, U;
+    if (check) {
+        X = mul_G(sc_from_limbs(b + (size_t)i * 8, 8));
+        U = mul_G(sc_from_limbs(alpha + (size_t)i * 24, 24));
+        affine_store(u_out + (size_t)i * 16, U);
+    }
+    bob_hash(ei, A.k(KT_N, ek_rows[i]), a_enc + (size_t)i * 128, mta + (size_t)i * 128, z + (size_t)i * 64, zp + (size_t)i * 64, t + (size_t)i * 64,
+             v + (size_t)i * 128, w + (size_t)i * 64, check ? &X : nullptr, check ? &U : nullptr);
+    st::mul_add(s1 + (size_t)i * 28, 28, ei, 8, b + (size_t)i * 8, 8, alpha + (size_t)i * 24, 24);
+    st::mul_add(s2 + (size_t)i * 92, 92, ei, 8, ro + (size_t)i * 72, 72, ro_prim + (size_t)i * 88, 88);
+    st::mul_add(t1 + (size_t)i * 84, 84, ei, 8, beta_prim + (size_t)i * 64, 64, gamma + (size_t)i * 80, 80);
+    st::mul_add(t2 + (size_t)i * 92, 92, ei, 8, sigma + (size_t)i * 72, 72, tau + (size_t)i * 88, 88);
+}
+__global__ void k_bob_vpre(const uint32_t* s1, uint8_t* range_bad, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    range_bad[i] = st::cmp2(s1 + (size_t)i * 28, 28, Q3_LIMBS, 24) > 0;
+}
+// verify epilogue (:374-410) and, for BobProofExt, G s1 == X e + u (:522-531)
+__global__ void k_bob_vpost(Arena A, const uint32_t* ek_rows, const uint32_t* a_enc, const uint32_t* mta, const uint32_t* z, const uint32_t* zp,
+                            const uint32_t* t, const uint32_t* v, const uint32_t* w, const uint32_t* e, const uint32_t* s1, const uint32_t* Xp,
+                            const uint32_t* Up, const uint8_t* range_bad, const uint8_t* ok1, const uint8_t* ok2, const uint8_t* ok3,
+                            uint32_t* e_scratch, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint8_t st_ = TECDSA_ST_OK;
+    if (range_bad[i]) st_ = TECDSA_ST_RANGE;
+    else if (!ok1[i] || !ok2[i] || !ok3[i]) st_ = TECDSA_ST_NOT_INVERTIBLE;
+    else {
+        Affine X, U;
+        if (Xp) { X = affine_load(Xp + (size_t)i * 16); U = affine_load(Up + (size_t)i * 16); }
+        uint32_t* ei = e_scratch + (size_t)i * 8;
+        bob_hash(ei, A.k(KT_N, ek_rows[i]), a_enc + (size_t)i * 128, mta + (size_t)i * 128, z + (size_t)i * 64, zp + (size_t)i * 64,
+                 t + (size_t)i * 64, v + (size_t)i * 128, w + (size_t)i * 64, Xp ? &X : nullptr, Xp ? &U : nullptr);
+        if (st::cmp(ei, e + (size_t)i * 8, 8) != 0) st_ = TECDSA_ST_HASH_MISMATCH;
+        else if (Xp) {
+            if (X.inf || U.inf || !on_curve(X) || !on_curve(U)) st_ = TECDSA_ST_PROOF;
+            else {
+                Affine x1 = mul_G(sc_from_limbs(s1 + (size_t)i * 28, 28));
+                Affine x2 = jac_to_affine(jac_add(jac_mul(jac_from_affine(X), sc_from_limbs(e + (size_t)i * 8, 8)), jac_from_affine(U)));
+                if (!affine_eq(x1, x2)) st_ = TECDSA_ST_PROOF;
+            }
+        }
+    }
+    status[i] = st_;
+}
+
 Arena key_arena(const tecdsa_keyset* ks) {
     Arena A;
     memset(&A, 0, sizeof(A));
@@ -379,6 +505,160 @@ extern "C" int tecdsa_alice_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyse
     add_exp(L.e128, 128, n, NN, 1, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(gs1, 128), arr(cei, 128), u, 128);   // u' (:141)
     RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
     k_alice_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, de, bad, okz, okc, e2, dst, n);
+    KCHECK();
+    return S.finish();
+}
+
+
+// ------------------------------------------------------------------------------------------ L2: PDL with slack
+extern "C" int tecdsa_pdl_prove_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, const uint32_t* x,
+                                      const uint32_t* r, const uint32_t* cipher, const uint32_t* Qp, const uint32_t* Gp, const uint32_t* alpha,
+                                      const uint32_t* beta, const uint32_t* rho, const uint32_t* gamma, uint32_t* z, uint32_t* u1, uint32_t* u2,
+                                      uint32_t* u3, uint32_t* s1, uint32_t* s2, uint32_t* s3, size_t count, int mem) {
+    if (!c || !ks || !ek_row || !st_row || !x || !r || !cipher || !Qp || !Gp || !alpha || !beta || !rho || !gamma || !z || !u1 || !u2 || !u3 || !s1 || !s2 || !s3)
+        return tecdsa_fail(TECDSA_E_ARG, "pdl_prove: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *dx = S.in(x, count * 8), *dr = S.in(r, count * 64), *dc = S.in(cipher, count * 128),
+                   *dQ = S.in(Qp, count * 16), *dG = S.in(Gp, count * 16), *dal = S.in(alpha, count * 24), *dbe = S.in(beta, count * 64),
+                   *dro = S.in(rho, count * 72), *dga = S.in(gamma, count * 88);
+    uint32_t *dz = S.out(z, count * 64), *du1 = S.out(u1, count * 16), *du2 = S.out(u2, count * 128), *du3 = S.out(u3, count * 64),
+             *ds1 = S.out(s1, count * 28), *ds2 = S.out(s2, count * 64), *ds3 = S.out(s3, count * 92);
+    uint32_t *lin = S.tmp<uint32_t>(count * 128), *e = S.tmp<uint32_t>(count * 8);
+    if (S.err) return S.finish();
+    Arena A = key_arena(ks);
+    k_pdl_pre<<<grid_for(count), 64, 0, c->stream>>>(A, er, dG, dal, du1, lin, n);
+    KCHECK();
+    Launches L;
+    add_fb(L.e64, n, ks, sr, arr(dro, 72), 72, arr(dx, 8), 8, 0, NONE, dz);                 // z  = h1^x h2^rho       (:78-84)
+    add_fb(L.e64, n, ks, sr, arr(dga, 88), 88, arr(dal, 24), 24, 0, NONE, du3);             // u3 = h1^alpha h2^gamma (:93-99)
+    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, du2, 128);   // u2 (:86-92)
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    k_pdl_mid<<<grid_for(count), 64, 0, c->stream>>>(dG, dQ, dc, dz, du1, du2, du3, dx, dal, dro, dga, e, ds1, ds3, n);
+    KCHECK();
+    add_exp(L.e64, 64, n, tab(ks->tab[KT_N], er, 64), 1, arr(dr, 64), arr(e, 8), 8, NONE, NONE, 0, 1, arr(dbe, 64), NONE, ds2, 64);   // s2 = r^e beta mod N (:113)
+    RUN(run(c, L.e64, 64));
+    return S.finish();
+}
+
+extern "C" int tecdsa_pdl_verify_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, const uint32_t* cipher,
+                                       const uint32_t* Qp, const uint32_t* Gp, const uint32_t* z, const uint32_t* u1, const uint32_t* u2,
+                                       const uint32_t* u3, const uint32_t* s1, const uint32_t* s2, const uint32_t* s3, uint8_t* status, size_t count, int mem) {
+    if (!c || !ks || !ek_row || !st_row || !cipher || !Qp || !Gp || !z || !u1 || !u2 || !u3 || !s1 || !s2 || !s3 || !status)
+        return tecdsa_fail(TECDSA_E_ARG, "pdl_verify: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *dc = S.in(cipher, count * 128), *dQ = S.in(Qp, count * 16), *dG = S.in(Gp, count * 16),
+                   *dz = S.in(z, count * 64), *du1 = S.in(u1, count * 16), *du2 = S.in(u2, count * 128), *du3 = S.in(u3, count * 64),
+                   *ds1 = S.in(s1, count * 28), *ds2 = S.in(s2, count * 64), *ds3 = S.in(s3, count * 92);
+    uint8_t* dst = S.out(status, count);
+    uint32_t *e = S.tmp<uint32_t>(count * 8), *lin = S.tmp<uint32_t>(count * 128), *ze = S.tmp<uint32_t>(count * 64), *ce = S.tmp<uint32_t>(count * 128),
+             *zei = S.tmp<uint32_t>(count * 64), *cei = S.tmp<uint32_t>(count * 128), *u2t = S.tmp<uint32_t>(count * 128), *u3t = S.tmp<uint32_t>(count * 64);
+    uint8_t *okz = S.tmp<uint8_t>(count), *okc = S.tmp<uint8_t>(count);
+    if (S.err) return S.finish();
+    Arena A = key_arena(ks);
+    k_pdl_vpre<<<grid_for(count), 64, 0, c->stream>>>(A, er, dG, dQ, dc, dz, du1, du2, du3, ds1, e, lin, n);
+    KCHECK();
+    Launches L;
+    Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
+    add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(e, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);          // z^e; (z^-1)^e == (z^e)^-1
+    add_exp(L.e128, 128, n, NN, 1, arr(dc, 128), arr(e, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);      // c^e
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, okz);
+    add_inv(L.i128, 128, n, NN, arr(ce, 128), cei, okc);
+    RUN(run(c, L.i128, 128)); RUN(run(c, L.i64, 64));
+    add_fb(L.e64, n, ks, sr, arr(ds3, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), u3t);                        // u3' (:158-172)
+    add_exp(L.e128, 128, n, NN, 1, arr(ds2, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(lin, 128), arr(cei, 128), u2t, 128);   // u2' (:144-157)
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    k_pdl_vpost<<<grid_for(count), 64, 0, c->stream>>>(dG, dQ, du1, du2, du3, ds1, e, u2t, u3t, okz, okc, dst, n);
+    KCHECK();
+    return S.finish();
+}
+
+// ------------------------------------------------------------------------------------------ L2: Bob's range proof (MtA / MtAwc)
+extern "C" int tecdsa_bob_proof_generate_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, int check,
+                                               const uint32_t* a_enc, const uint32_t* mta_enc, const uint32_t* b, const uint32_t* beta_prim,
+                                               const uint32_t* r, const uint32_t* alpha, const uint32_t* beta, const uint32_t* gamma,
+                                               const uint32_t* ro, const uint32_t* ro_prim, const uint32_t* sigma, const uint32_t* tau,
+                                               uint32_t* t, uint32_t* z, uint32_t* e, uint32_t* s, uint32_t* s1, uint32_t* s2, uint32_t* t1,
+                                               uint32_t* t2, uint32_t* u, size_t count, int mem) {
+    if (!c || !ks || !ek_row || !st_row || !a_enc || !mta_enc || !b || !beta_prim || !r || !alpha || !beta || !gamma || !ro || !ro_prim || !sigma ||
+        !tau || !t || !z || !e || !s || !s1 || !s2 || !t1 || !t2 || (check && !u))
+        return tecdsa_fail(TECDSA_E_ARG, "bob_proof_generate: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *da = S.in(a_enc, count * 128), *dm = S.in(mta_enc, count * 128),
+                   *db = S.in(b, count * 8), *dbp = S.in(beta_prim, count * 64), *dr = S.in(r, count * 64), *dal = S.in(alpha, count * 24),
+                   *dbe = S.in(beta, count * 64), *dga = S.in(gamma, count * 80), *dro = S.in(ro, count * 72), *drp = S.in(ro_prim, count * 88),
+                   *dsi = S.in(sigma, count * 72), *dta = S.in(tau, count * 88);
+    uint32_t *dt = S.out(t, count * 64), *dz = S.out(z, count * 64), *de = S.out(e, count * 8), *ds = S.out(s, count * 64), *ds1 = S.out(s1, count * 28),
+             *ds2 = S.out(s2, count * 92), *dt1 = S.out(t1, count * 84), *dt2 = S.out(t2, count * 92), *du = check ? S.out(u, count * 16) : nullptr;
+    uint32_t *zp = S.tmp<uint32_t>(count * 64), *w = S.tmp<uint32_t>(count * 64), *v = S.tmp<uint32_t>(count * 128), *lin = S.tmp<uint32_t>(count * 128);
+    if (S.err) return S.finish();
+    Arena A = key_arena(ks);
+    k_lin_wide<<<grid_for(count), 64, 0, c->stream>>>(A, er, dga, 80, lin, n);
+    KCHECK();
+    Launches L;
+    add_fb(L.e64, n, ks, sr, arr(dro, 72), 72, arr(db, 8), 8, 0, NONE, dz);                 // z  = h1^b h2^ro             (:238)
+    add_fb(L.e64, n, ks, sr, arr(drp, 88), 88, arr(dal, 24), 24, 0, NONE, zp);              // z' = h1^alpha h2^ro'        (:239-241)
+    add_fb(L.e64, n, ks, sr, arr(dsi, 72), 72, arr(dbp, 64), 64, 0, NONE, dt);              // t  = h1^beta' h2^sigma      (:242-243)
+    add_fb(L.e64, n, ks, sr, arr(dta, 88), 88, arr(dga, 80), 80, 0, NONE, w);               // w  = h1^gamma h2^tau        (:244-245)
+    // v = a_enc^alpha * (gamma N + 1) * beta^N mod N^2                                      (:246-249)
+    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 2, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, arr(da, 128), arr(dal, 24), 24, 1, arr(lin, 128), NONE, v, 128);
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    k_bob_mid<<<grid_for(count), 64, 0, c->stream>>>(A, er, check, da, dm, dz, zp, dt, v, w, db, dbp, dal, dga, dro, drp, dsi, dta, de, ds1, ds2, dt1, dt2, du, n);
+    KCHECK();
+    add_exp(L.e64, 64, n, tab(ks->tab[KT_N], er, 64), 1, arr(dr, 64), arr(de, 8), 8, NONE, NONE, 0, 1, arr(dbe, 64), NONE, ds, 64);   // s = r^e beta mod N (:291)
+    RUN(run(c, L.e64, 64));
+    return S.finish();
+}
+
+extern "C" int tecdsa_bob_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, const uint32_t* a_enc,
+                                             const uint32_t* mta_out, const uint32_t* t, const uint32_t* z, const uint32_t* e, const uint32_t* s,
+                                             const uint32_t* s1, const uint32_t* s2, const uint32_t* t1, const uint32_t* t2, const uint32_t* X,
+                                             const uint32_t* u, uint8_t* status, size_t count, int mem) {
+    if (!c || !ks || !ek_row || !st_row || !a_enc || !mta_out || !t || !z || !e || !s || !s1 || !s2 || !t1 || !t2 || !status || ((X == nullptr) != (u == nullptr)))
+        return tecdsa_fail(TECDSA_E_ARG, "bob_proof_verify: bad argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *da = S.in(a_enc, count * 128), *dm = S.in(mta_out, count * 128), *dt = S.in(t, count * 64),
+                   *dz = S.in(z, count * 64), *de = S.in(e, count * 8), *ds = S.in(s, count * 64), *ds1 = S.in(s1, count * 28), *ds2 = S.in(s2, count * 92),
+                   *dt1 = S.in(t1, count * 84), *dt2 = S.in(t2, count * 92), *dX = S.in(X, count * 16), *dU = S.in(u, count * 16);
+    uint8_t* dst = S.out(status, count);
+    uint32_t *ze = S.tmp<uint32_t>(count * 64), *te = S.tmp<uint32_t>(count * 64), *me = S.tmp<uint32_t>(count * 128), *zei = S.tmp<uint32_t>(count * 64),
+             *tei = S.tmp<uint32_t>(count * 64), *mei = S.tmp<uint32_t>(count * 128), *lin = S.tmp<uint32_t>(count * 128), *zp = S.tmp<uint32_t>(count * 64),
+             *w = S.tmp<uint32_t>(count * 64), *v = S.tmp<uint32_t>(count * 128), *e2 = S.tmp<uint32_t>(count * 8);
+    uint8_t *bad = S.tmp<uint8_t>(count), *ok1 = S.tmp<uint8_t>(count), *ok2 = S.tmp<uint8_t>(count), *ok3 = S.tmp<uint8_t>(count);
+    if (S.err) return S.finish();
+    Arena A = key_arena(ks);
+    k_bob_vpre<<<grid_for(count), 64, 0, c->stream>>>(ds1, bad, n);
+    KCHECK();
+    k_lin_wide<<<grid_for(count), 64, 0, c->stream>>>(A, er, dt1, 84, lin, n);
+    KCHECK();
+    Launches L;
+    Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
+    add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);           // z^e   (:339)
+    add_exp(L.e64, 64, n, NT, 1, arr(dt, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, te, 64);           // t^e   (:363)
+    add_exp(L.e128, 128, n, NN, 1, arr(dm, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, me, 128);       // mta^e (:351)
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, ok1);
+    add_inv(L.i64, 64, n, NT, arr(te, 64), tei, ok3);
+    add_inv(L.i128, 128, n, NN, arr(me, 128), mei, ok2);
+    RUN(run(c, L.i128, 128)); RUN(run(c, L.i64, 64));
+    add_fb(L.e64, n, ks, sr, arr(ds2, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), zp);                          // z' (:346-349)
+    add_fb(L.e64, n, ks, sr, arr(dt2, 92), 92, arr(dt1, 84), 84, 1, arr(tei, 64), w);                           // w  (:369-372)
+    // v = a_enc^s1 * s^N * (t1 N + 1) * (mta^e)^-1 mod N^2                                                      (:357-361)
+    add_exp(L.e128, 128, n, NN, 2, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, arr(da, 128), arr(ds1, 28), 28, 2, arr(lin, 128), arr(mei, 128), v, 128);
+    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    k_bob_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, da, dm, dz, zp, dt, v, w, de, ds1, dX, dU, bad, ok1, ok2, ok3, e2, dst, n);
     KCHECK();
     return S.finish();
 }

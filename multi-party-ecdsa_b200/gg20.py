@@ -229,3 +229,78 @@ def alice_proof_verify(eng: Engine, keys: KeySets, ek_row, st_row, cipher, z, e,
     eng._ck(eng.lib.tecdsa_alice_proof_verify_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), *[_ptr(x) for x in ins], _ptr(status), n, HOST),
             "alice_proof_verify")
     return status
+
+
+# ----------------------------------------------------------------------------- L2: PDLwSlack and Bob proofs, batched
+def _bind_l2b(lib):
+    if getattr(lib, "_l2b_bound", False):
+        return
+    V, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.tecdsa_pdl_prove_batch.argtypes = [V] * 20 + [S, I]
+    lib.tecdsa_pdl_verify_batch.argtypes = [V] * 15 + [S, I]
+    lib.tecdsa_bob_proof_generate_batch.argtypes = [V, V, V, V, I] + [V] * 21 + [S, I]
+    lib.tecdsa_bob_proof_verify_batch.argtypes = [V] * 17 + [S, I]
+    lib._l2b_bound = True
+
+
+def _rows(x):
+    return np.asarray(x, dtype=np.uint32)
+
+
+def _pts(ps):
+    return ints_to_limbs([pack_point(p) for p in ps], 16)
+
+
+def pdl_prove(eng, keys, ek_row, st_row, x, r, cipher, Q, G, alpha, beta, rho, gamma):
+    """Batched `PDLwSlackProof::prove` (zk_pdl_with_slack/mod.rs:68-125) with explicit randomness."""
+    _bind_l2b(eng.lib)
+    n = len(x)
+    ins = [_rows(ek_row), _rows(st_row), ints_to_limbs(x, 8), ints_to_limbs(r, 64), ints_to_limbs(cipher, 128), _pts(Q), _pts(G),
+           ints_to_limbs(alpha, 24), ints_to_limbs(beta, 64), ints_to_limbs(rho, 72), ints_to_limbs(gamma, 88)]
+    outs = {k: np.zeros((n, l), dtype=np.uint32) for k, l in (("z", 64), ("u1", 16), ("u2", 128), ("u3", 64), ("s1", 28), ("s2", 64), ("s3", 92))}
+    eng._ck(eng.lib.tecdsa_pdl_prove_batch(eng._ctx, keys.handle, *[_ptr(a) for a in ins], *[_ptr(outs[k]) for k in ("z", "u1", "u2", "u3", "s1", "s2", "s3")],
+                                           n, HOST), "pdl_prove")
+    res = {k: limbs_to_ints(v) for k, v in outs.items()}
+    res["u1"] = [unpack_point(v) for v in res["u1"]]
+    return res
+
+
+def pdl_verify(eng, keys, ek_row, st_row, cipher, Q, G, z, u1, u2, u3, s1, s2, s3) -> np.ndarray:
+    _bind_l2b(eng.lib)
+    n = len(z)
+    ins = [_rows(ek_row), _rows(st_row), ints_to_limbs(cipher, 128), _pts(Q), _pts(G), ints_to_limbs(z, 64), _pts(u1), ints_to_limbs(u2, 128),
+           ints_to_limbs(u3, 64), ints_to_limbs(s1, 28), ints_to_limbs(s2, 64), ints_to_limbs(s3, 92)]
+    status = np.full(n, 255, dtype=np.uint8)
+    eng._ck(eng.lib.tecdsa_pdl_verify_batch(eng._ctx, keys.handle, *[_ptr(a) for a in ins], _ptr(status), n, HOST), "pdl_verify")
+    return status
+
+
+def bob_proof_generate(eng, keys, ek_row, st_row, check, a_enc, mta_enc, b, beta_prim, r, alpha, beta, gamma, ro, ro_prim, sigma, tau):
+    """Batched `BobProof::generate` (range_proofs.rs:414-487); check=True is the MtAwc variant (returns u too)."""
+    _bind_l2b(eng.lib)
+    n = len(b)
+    ins = [ints_to_limbs(a_enc, 128), ints_to_limbs(mta_enc, 128), ints_to_limbs(b, 8), ints_to_limbs(beta_prim, 64), ints_to_limbs(r, 64),
+           ints_to_limbs(alpha, 24), ints_to_limbs(beta, 64), ints_to_limbs(gamma, 80), ints_to_limbs(ro, 72), ints_to_limbs(ro_prim, 88),
+           ints_to_limbs(sigma, 72), ints_to_limbs(tau, 88)]
+    names = (("t", 64), ("z", 64), ("e", 8), ("s", 64), ("s1", 28), ("s2", 92), ("t1", 84), ("t2", 92), ("u", 16))
+    outs = {k: np.zeros((n, l), dtype=np.uint32) for k, l in names}
+    er, sr = _rows(ek_row), _rows(st_row)
+    eng._ck(eng.lib.tecdsa_bob_proof_generate_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), 1 if check else 0, *[_ptr(a) for a in ins],
+                                                    *[_ptr(outs[k]) for k, _ in names], n, HOST), "bob_proof_generate")
+    res = {k: limbs_to_ints(v) for k, v in outs.items()}
+    res["u"] = [unpack_point(v) for v in res["u"]] if check else None
+    return res
+
+
+def bob_proof_verify(eng, keys, ek_row, st_row, a_enc, mta_out, pf, X=None, u=None) -> np.ndarray:
+    """Batched `BobProof::verify` (X is None) / `BobProofExt::verify` (X = G*b, u from the proof)."""
+    _bind_l2b(eng.lib)
+    n = len(pf["z"])
+    ins = [_rows(ek_row), _rows(st_row), ints_to_limbs(a_enc, 128), ints_to_limbs(mta_out, 128), ints_to_limbs(pf["t"], 64), ints_to_limbs(pf["z"], 64),
+           ints_to_limbs(pf["e"], 8), ints_to_limbs(pf["s"], 64), ints_to_limbs(pf["s1"], 28), ints_to_limbs(pf["s2"], 92), ints_to_limbs(pf["t1"], 84),
+           ints_to_limbs(pf["t2"], 92)]
+    Xa = _pts(X) if X is not None else None
+    Ua = _pts(u) if u is not None else None
+    status = np.full(n, 255, dtype=np.uint8)
+    eng._ck(eng.lib.tecdsa_bob_proof_verify_batch(eng._ctx, keys.handle, *[_ptr(a) for a in ins], _ptr(Xa), _ptr(Ua), _ptr(status), n, HOST), "bob_proof_verify")
+    return status

@@ -114,3 +114,85 @@ def test_alice_proof_generate_verify_batch(engine, pkg, keyset):
     st1 = gg20.alice_proof_verify(engine, ks, ek_row, st_row, bad_c, bad_z, pf["e"], pf["s"], bad_s1, pf["s2"])
     assert st1[0] == pkg.ST_HASH_MISMATCH and st1[1] == pkg.ST_RANGE and st1[2] == pkg.ST_NOT_INVERTIBLE and not st1[3:].any()
     ks.free()
+
+
+def test_pdl_prove_verify_batch(engine, pkg, keyset):
+    """mirrors zk_pdl_with_slack/test.rs: accept (:11-68) and the x+1 soundness negative (:70-129), batched; proof
+    bytes identical to the oracle's."""
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    rng = Drbg(14, "pdl-batch")
+    n = 12
+    q3 = o.Q ** 3
+    ek_row = [i % 3 for i in range(n)]
+    st_row = [(i + 1) % 3 for i in range(n)]
+    x, r, c, Qs, Gs, al, be, rh, ga = [], [], [], [], [], [], [], [], []
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]; st = keyset[0].h1_h2_n_tilde_vec[st_row[i]]
+        x.append(rng.scalar()); r.append(rng.unit_mod(ek.n)); c.append(o.paillier_encrypt(ek, x[-1], r[-1]))
+        Gs.append(o.pt_mul(o.G, rng.scalar())); Qs.append(o.pt_mul(Gs[-1], x[-1]))
+        al.append(rng.below(q3)); be.append(1 + rng.below(ek.n - 2)); rh.append(rng.below(o.Q * st.N)); ga.append(rng.below(q3 * st.N))
+    pf = gg20.pdl_prove(engine, ks, ek_row, st_row, x, r, c, Qs, Gs, al, be, rh, ga)
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]; st = keyset[0].h1_h2_n_tilde_vec[st_row[i]]
+        w = o.pdl_prove(x[i], r[i], c[i], ek, Qs[i], Gs[i], st.g, st.ni, st.N, al[i], be[i], rh[i], ga[i])
+        assert (pf["z"][i], pf["u1"][i], pf["u2"][i], pf["u3"][i], pf["s1"][i], pf["s2"][i], pf["s3"][i]) == (w.z, w.u1, w.u2, w.u3, w.s1, w.s2, w.s3)
+    st_ok = gg20.pdl_verify(engine, ks, ek_row, st_row, c, Qs, Gs, pf["z"], pf["u1"], pf["u2"], pf["u3"], pf["s1"], pf["s2"], pf["s3"])
+    assert not st_ok.any()
+    # soundness negative: ciphertext of x+1 with a proof for x; and a non-invertible z
+    c_bad = list(c)
+    ek0 = keyset[0].paillier_key_vec[ek_row[0]]
+    c_bad[0] = o.paillier_encrypt(ek0, x[0] + 1, r[0])
+    z_bad = list(pf["z"]); z_bad[1] = 0
+    st1 = gg20.pdl_verify(engine, ks, ek_row, st_row, c_bad, Qs, Gs, z_bad, pf["u1"], pf["u2"], pf["u3"], pf["s1"], pf["s2"], pf["s3"])
+    assert st1[0] == pkg.ST_PDL_VERIFY and st1[1] == pkg.ST_PDL_VERIFY and not st1[2:].any()
+    ks.free()
+
+
+@pytest.mark.parametrize("check", [False, True])
+def test_bob_proofs_batch(engine, pkg, keyset, check):
+    """mirrors range_proofs.rs `bob_zkp` (:636-709): BobProof (MtA) and BobProofExt (MtAwc), batched, byte-identical
+    to the oracle and accepted by both verifiers; tampered proofs rejected."""
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    rng = Drbg(15 + check, "bob-batch")
+    n = 9
+    q3 = o.Q ** 3
+    ek_row = [i % 3 for i in range(n)]
+    st_row = [(i + 2) % 3 for i in range(n)]
+    cols = {k: [] for k in ("a_enc", "mta", "b", "bp", "r", "al", "be", "ga", "ro", "rp", "si", "ta")}
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]; st = keyset[0].h1_h2_n_tilde_vec[st_row[i]]
+        a, b = rng.scalar(), rng.scalar()
+        enc_a = o.paillier_encrypt(ek, a, rng.unit_mod(ek.n))
+        bp, r = rng.below(ek.n), rng.unit_mod(ek.n)
+        mta = o.paillier_add(ek, o.paillier_mul(ek, enc_a, b), o.paillier_encrypt(ek, bp, r))
+        vals = (enc_a, mta, b, bp, r, rng.below(q3), rng.unit_mod(ek.n), rng.below(o.Q ** 2 * ek.n), rng.below(o.Q * st.N), rng.below(q3 * st.N),
+                rng.below(o.Q * st.N), rng.below(q3 * st.N))
+        for k, v in zip(cols, vals):
+            cols[k].append(v)
+    pf = gg20.bob_proof_generate(engine, ks, ek_row, st_row, check, cols["a_enc"], cols["mta"], cols["b"], cols["bp"], cols["r"], cols["al"],
+                                 cols["be"], cols["ga"], cols["ro"], cols["rp"], cols["si"], cols["ta"])
+    Xs = [o.pt_mul(o.G, b) for b in cols["b"]]
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]; st = keyset[0].h1_h2_n_tilde_vec[st_row[i]]
+        w, u = o.bob_proof_generate(cols["a_enc"][i], cols["mta"][i], cols["b"][i], cols["bp"][i], ek, st, cols["r"][i], check, cols["al"][i],
+                                    cols["be"][i], cols["ga"][i], cols["ro"][i], cols["rp"][i], cols["si"][i], cols["ta"][i])
+        got = tuple(pf[k][i] for k in ("t", "z", "e", "s", "s1", "s2", "t1", "t2"))
+        assert got == (w.t, w.z, w.e, w.s, w.s1, w.s2, w.t1, w.t2), i
+        if check:
+            assert pf["u"][i] == u
+            assert o.bob_proof_ext_verify(w, u, cols["a_enc"][i], cols["mta"][i], ek, st, Xs[i])
+        else:
+            assert o.bob_proof_verify(w, cols["a_enc"][i], cols["mta"][i], ek, st)
+    st_ok = gg20.bob_proof_verify(engine, ks, ek_row, st_row, cols["a_enc"], cols["mta"], pf, Xs if check else None, pf["u"] if check else None)
+    assert not st_ok.any()
+    bad = dict(pf); bad["t1"] = list(pf["t1"]); bad["t1"][0] += 1
+    mta_bad = list(cols["mta"]); mta_bad[1] += 1
+    st1 = gg20.bob_proof_verify(engine, ks, ek_row, st_row, cols["a_enc"], mta_bad, bad, Xs if check else None, pf["u"] if check else None)
+    assert st1[0] == pkg.ST_HASH_MISMATCH and st1[1] == pkg.ST_HASH_MISMATCH and not st1[2:].any()
+    if check:
+        Xbad = list(Xs); Xbad[2] = o.pt_add(Xs[2], o.G)
+        st2 = gg20.bob_proof_verify(engine, ks, ek_row, st_row, cols["a_enc"], cols["mta"], pf, Xbad, pf["u"])
+        assert st2[2] in (pkg.ST_HASH_MISMATCH, pkg.ST_PROOF) and not st2[3:].any()
+    ks.free()
