@@ -39,10 +39,10 @@ struct Builder {
     static void reset(ExpLaunch& l) { l.n_classes = 0; l.total_items = 0; }
     static void reset(InvLaunch& l) { l.n_classes = 0; l.total_items = 0; }
     void exp_class(ExpLaunch& l, int gpw, Operand mod, int nb, Operand b0, Operand e0, int el0, Operand b1, Operand e1, int el1,
-                   int nm, Operand m0, Operand m1, int out_field, int wide0 = 0) {
+                   int nm, Operand m0, Operand m1, int out_field, int wide0 = 0, Operand m2 = Operand{nullptr, nullptr, 0, 0, 0}) {
         ExpClass& k = l.cls[l.n_classes++];
         k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
-        k.mul[0] = m0; k.mul[1] = m1; k.nbases = nb; k.nmul = nm; k.wide0 = wide0;
+        k.mul[0] = m0; k.mul[1] = m1; k.mul[2] = m2; k.nbases = nb; k.nmul = nm; k.wide0 = wide0;
         k.fb = nullptr; k.fb_row = Operand{nullptr, nullptr, 0, 0, 0}; k.fb_sel[0] = k.fb_sel[1] = 0;
         k.out = out(out_field); k.out_stride = A.size[out_field]; k.count = U; k.item_begin = l.total_items;
         l.total_items += (U + gpw - 1) / gpw;
@@ -53,6 +53,13 @@ struct Builder {
         exp_class(l, gpw, key(KT_NT, rows), 2, none, e_h2, el_h2, none, e_h1, el_h1, nm, m0, none, out_field);
         ExpClass& k = l.cls[l.n_classes - 1];
         k.fb = ks->fb; k.fb_row = Operand{nullptr, rows, 0, 1, 0}; k.fb_sel[0] = 1; k.fb_sel[1] = 0;
+    }
+    // own-key power base^N mod N^2 through its CRT halves mod p^2 and q^2 (the unit knows its own p, q); slot s
+    // writes YP[s], YQ[s]; gg20_crt recombines them into XC[s]  (declared shortcut: identical value)
+    void crt_halves(ExpLaunch& l, int gpw, const uint32_t* rows, int slot, Operand base) {
+        const Operand none = {nullptr, nullptr, 0, 0, 0};
+        exp_class(l, gpw, key(KT_PP, rows), 1, base, key(KT_N, rows), 64, none, none, 0, 0, none, none, F_YP0 + slot);
+        exp_class(l, gpw, key(KT_QQ, rows), 1, base, key(KT_N, rows), 64, none, none, 0, 0, none, none, F_YQ0 + slot);
     }
     void inv_class(InvLaunch& l, int gpw, Operand mod, Operand in, int out_field, int flag_byte) {
         InvClass& k = l.cls[l.n_classes++];
@@ -72,6 +79,13 @@ template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A) {
     c->count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "glue launch", e);
+}
+
+int glue_crt(tecdsa_ctx* c, const Arena& A, int first, int count) {
+    gg20_crt<<<(A.U + 63) / 64, 64, 0, c->stream>>>(A, first, count);
+    c->count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "crt launch", e);
 }
 
 }  // namespace
@@ -213,18 +227,23 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
 
     // ================= Round 0 (rounds.rs:68-104): MessageA::a with one AliceProof per statement
     RUN(glue(c, gg20_r0_pre, A));
-    // c_k = (1 + k N) * r_k^N mod N^2                                   (mta/mod.rs:68-75)
-    B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(RND_RK, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_MK), NONE, F_CK);
+    // c_k = (1 + k N) * r_k^N mod N^2 (mta/mod.rs:68-75) and u = (alpha N + 1) * beta^N mod N^2 (range_proofs.rs:53-55):
+    // the N-th powers are under the unit's OWN key, so they run as CRT halves mod p^2 / q^2 (2048-bit)
+    B.crt_halves(L64, GPW64, ro, 0, B.rnd(RND_RK, 64));
     for (int x = 0; x < 3; x++) {
         const int al = RND_AL + x * RND_AL_STRIDE;
-        // u = (alpha N + 1) * beta^N mod N^2                            (range_proofs.rs:53-55)
-        B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(al + RND_AL_BETA, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_ALIN0 + x), NONE, F_U0 + x);
+        B.crt_halves(L64, GPW64, ro, 1 + x, B.rnd(al + RND_AL_BETA, 64));
         // w = h1^alpha * h2^gamma mod N_tilde                           (range_proofs.rs:56-57)
         B.fb_class(L64, GPW64, st_rows(x), B.rnd(al + RND_AL_GAMMA, 88), 88, B.rnd(al + RND_AL_ALPHA, 24), 24, 0, NONE, F_WP0 + x);
         // z = h1^a * h2^ro mod N_tilde                                  (range_proofs.rs:52)
         B.fb_class(L64, GPW64, st_rows(x), B.rnd(al + RND_AL_RHO, 72), 72, B.rnd(RND_K, 8), 8, 0, NONE, F_Z0 + x);
     }
-    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, L64, 64));
+    RUN(glue_crt(c, A, 0, 4));
+    B.exp_class(L128, GPW128, B.key(KT_NN, ro), 0, NONE, NONE, 0, NONE, NONE, 0, 2, B.fld(F_MK), B.fld(F_XC0), F_CK);
+    for (int x = 0; x < 3; x++)
+        B.exp_class(L128, GPW128, B.key(KT_NN, ro), 0, NONE, NONE, 0, NONE, NONE, 0, 2, B.fld(F_ALIN0 + x), B.fld(F_XC1 + x), F_U0 + x);
+    RUN(run_exp(c, L128, 128));
     RUN(glue(c, gg20_r0_mid, A));
     for (int x = 0; x < 3; x++)    // s = r^e * beta mod N                (range_proofs.rs:86)
         B.exp_class(L64, GPW64, B.key(KT_N, ro), 1, B.rnd(RND_RK, 64), B.fld(F_E0 + x), 8, NONE, NONE, 0, 1,
@@ -269,9 +288,13 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     RUN(glue(c, gg20_r4_pre, A));
     B.fb_class(L64, GPW64, rp, B.rnd(RND_PDL_RHO, 72), 72, B.rnd(RND_K, 8), 8, 0, NONE, F_PZ);                  // z  (:78-84)
     B.fb_class(L64, GPW64, rp, B.rnd(RND_PDL_GAMMA, 88), 88, B.rnd(RND_PDL_ALPHA, 24), 24, 0, NONE, F_PU3);     // u3 (:93-99)
-    // u2 = (N+1)^alpha * beta^N mod N^2, with (N+1)^alpha == 1 + alpha N (declared shortcut, identical value) (:86-92)
-    B.exp_class(L128, GPW128, B.key(KT_NN, ro), 1, B.rnd(RND_PDL_BETA, 64), B.key(KT_N, ro), 64, NONE, NONE, 0, 1, B.fld(F_PLIN), NONE, F_PU2);
-    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    // u2 = (N+1)^alpha * beta^N mod N^2, with (N+1)^alpha == 1 + alpha N (declared shortcut, identical value) (:86-92);
+    // beta^N under the own key through CRT halves
+    B.crt_halves(L64, GPW64, ro, 4, B.rnd(RND_PDL_BETA, 64));
+    RUN(run_exp(c, L64, 64));
+    RUN(glue_crt(c, A, 4, 1));
+    B.exp_class(L128, GPW128, B.key(KT_NN, ro), 0, NONE, NONE, 0, NONE, NONE, 0, 2, B.fld(F_PLIN), B.fld(F_XC4), F_PU2);
+    RUN(run_exp(c, L128, 128));
     RUN(glue(c, gg20_r4_mid, A));
     B.exp_class(L64, GPW64, B.key(KT_N, ro), 1, B.rnd(RND_RK, 64), B.fld(F_PE), 8, NONE, NONE, 0, 1, B.rnd(RND_PDL_BETA, 64), NONE, F_PS2);   // s2 = r^e * beta mod N (:113)
     RUN(run_exp(c, L64, 64));
@@ -285,7 +308,9 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         B.exp_class(L64, GPW64, B.key(KT_NT, stmt), 1, z, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VZE0 + j);       // z^e; (z^-1)^e == (z^e)^-1 (:166-172)
         B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, ck, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VCE0 + j);  // c^e (:151-157)
     }
+    B.crt_halves(L64, GPW64, ro, 5, B.fld(F_PS2, 64));       // own proof's s2^N mod N^2_own through CRT halves
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(glue_crt(c, A, 5, 1));
     for (int j = 0; j < 2; j++) {
         B.inv_class(I64, GPW64, B.key(KT_NT, j ? ro : rp), B.fld(F_VZE0 + j), F_VZEI0 + j, 6 + j);
         B.inv_class(I128, GPW128, B.key(KT_NN, j ? rp : ro), B.fld(F_VCE0 + j), F_VCEI0 + j, 8 + j);
@@ -298,7 +323,8 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         // u3' = h1^s1 * h2^s3 * z^-e mod N_tilde                         (:158-172)
         B.fb_class(L64, GPW64, stmt, s3, 92, s1, 28, 1, B.fld(F_VZEI0 + j), F_VU30 + j);
         // u2' = (N+1)^s1 * s2^N * c^-e mod N^2                           (:144-157)
-        B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, s2, B.key(KT_N, prover), 64, NONE, NONE, 0, 2, B.fld(F_VLIN0 + j), B.fld(F_VCEI0 + j), F_VU20 + j);
+        if (j == 0) B.exp_class(L128, GPW128, B.key(KT_NN, prover), 0, NONE, NONE, 0, NONE, NONE, 0, 3, B.fld(F_VLIN0), B.fld(F_VCEI0), F_VU20, 0, B.fld(F_XC5));
+        else B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, s2, B.key(KT_N, prover), 64, NONE, NONE, 0, 2, B.fld(F_VLIN0 + j), B.fld(F_VCEI0 + j), F_VU20 + j);
     }
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
     RUN(glue(c, gg20_r5_post, A));

@@ -52,7 +52,11 @@ enum : int {
     X(SI, 16) X(HEG, 48)                            /* T 16 | A3 16 | z1 8 | z2 8 */             \
     X(DIGEST, 8)                                                                                  \
     X(FLAGS, 4)                                     /* ok bytes of the inversions, packed */         \
-    X(DBG, 256)                                     /* scratch for tools/debug_gg20.py */
+    X(DBG, 256)                                     /* scratch for tools/debug_gg20.py */            \
+    /* own-key powers b^N mod N^2 through CRT: halves mod p^2 / q^2 and the recombined value */      \
+    X(YP0, 64) X(YP1, 64) X(YP2, 64) X(YP3, 64) X(YP4, 64) X(YP5, 64)                              \
+    X(YQ0, 64) X(YQ1, 64) X(YQ2, 64) X(YQ3, 64) X(YQ4, 64) X(YQ5, 64)                              \
+    X(XC0, 128) X(XC1, 128) X(XC2, 128) X(XC3, 128) X(XC4, 128) X(XC5, 128)
 
 enum Field : int {
 #define X(name, size) F_##name,
@@ -84,10 +88,11 @@ enum KeyTable : int {
     KT_PINV2, KT_QINV2,  // 32   p^-1, q^-1 mod 2^1024 (exact division in the L-function)
     KT_HPR, KT_HQR,  // 32   hp*R mod p, hq*R mod q  (R = 2^1024; hp = L_p((1-N) mod p^2)^-1 mod p)
     KT_PINVQR,       // 32   (p^-1 mod q) * R mod q
+    KT_PPINVQQR,     // 64   ((p^2)^-1 mod q^2) * 2^2048 mod q^2  (CRT recombination of own-key N^2 powers)
     KT_XI,           // 8    x_i
     KT_PK,           // 16   X_i affine
     KT_COUNT
 };
-static const int KEY_SIZE[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 8, 16};
+static const int KEY_SIZE[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 8, 16};
 
 }  // namespace tecdsa

@@ -14,7 +14,7 @@ namespace tecdsa {
 
 using namespace secp;
 
-__device__ __constant__ const int KEY_SIZE_D[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 8, 16};
+__device__ __constant__ const int KEY_SIZE_D[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 8, 16};
 // q^3 (24 limbs): the verifier's range bound `s1 > q^3 => reject` (utilities/mta/range_proofs.rs:118)
 __device__ __constant__ const uint32_t Q3_LIMBS[24] = {
     0x857B73C1u, 0xEB6926B7u, 0xE1E11B11u, 0x3552090Fu, 0x7A1CF066u, 0xD9EF0F38u, 0x02D99574u, 0x46385C85u,
@@ -518,6 +518,58 @@ static __global__ void gg20_key_setup(uint32_t* const* tables, int rows) {
             st::copy(T(KT_PINVQR), acc, 32);     // (p^-1 mod q) * R
         }
     }
+    // ((p^2)^-1 mod q^2) * R64 mod q^2, R64 = 2^2048: lift p^-1 mod q to mod q^2 (Newton), square.
+    {
+        const uint32_t* qq = T(KT_QQ);
+        const uint32_t m0 = st::neg_inv32_st(qq[0]);
+        uint32_t rr64[64], big[129], pM[64], xM[64], tM[64], two[64], ext[64];
+        st::r_mod_m(rr64, qq, 64);
+        st::copy(two, rr64, 64);                                  // 1*R
+        {   // two = 2*R mod q^2
+            uint32_t top = two[63] >> 31;
+            for (int j = 63; j > 0; j--) two[j] = (two[j] << 1) | (two[j - 1] >> 31);
+            two[0] <<= 1;
+            if (top || st::cmp(two, qq, 64) >= 0) st::sub(two, two, qq, 64);
+        }
+        for (int i = 0; i < 2048; i++) {                          // rr64 = R^2 mod q^2
+            uint32_t top = rr64[63] >> 31;
+            for (int j = 63; j > 0; j--) rr64[j] = (rr64[j] << 1) | (rr64[j - 1] >> 31);
+            rr64[0] <<= 1;
+            if (top || st::cmp(rr64, qq, 64) >= 0) st::sub(rr64, rr64, qq, 64);
+        }
+        st::zero(ext, 64); st::copy(ext, p, 32);
+        st::mont_mul(pM, ext, rr64, qq, m0, 64, big);             // p * R
+        // x0 = p^-1 mod q (plain) from its Montgomery form mod q
+        uint32_t x0[32], one32[32], sc[65];
+        st::zero(one32, 32); one32[0] = 1;
+        st::mont_mul(x0, T(KT_PINVQR), one32, q, st::neg_inv32_st(q[0]), 32, sc);
+        st::zero(ext, 64); st::copy(ext, x0, 32);
+        st::mont_mul(xM, ext, rr64, qq, m0, 64, big);             // x0 * R
+        st::mont_mul(tM, pM, xM, qq, m0, 64, big);                // p*x0 * R
+        if (st::sub(tM, two, tM, 64)) st::add(tM, tM, qq, 64);    // (2 - p*x0) * R mod q^2
+        st::mont_mul(xM, xM, tM, qq, m0, 64, big);                // x1 * R,  x1 = p^-1 mod q^2
+        st::mont_mul(T(KT_PPINVQQR), xM, xM, qq, m0, 64, big);    // x1^2 * R = (p^2)^-1 * R mod q^2
+    }
+}
+
+// CRT recombination of an own-key power: x = yp + p^2 * ((yq - yp) * (p^2)^-1 mod q^2)  in [0, N^2)
+static __device__ __noinline__ void crt_combine(uint32_t* x128, const Arena& A, uint32_t row, const uint32_t* yp, const uint32_t* yq) {
+    const uint32_t *pp = A.k(KT_PP, row), *qq = A.k(KT_QQ, row);
+    uint32_t d[65], ypr[65], qx[65], big[129];
+    for (int i = 0; i < 64; i++) { d[i] = yq[i]; ypr[i] = yp[i]; qx[i] = qq[i]; }
+    d[64] = 0; ypr[64] = 0; qx[64] = 0;
+    st::sub(d, d, ypr, 65);
+    for (int it = 0; it < 5 && (d[64] >> 31); it++) st::add(d, d, qx, 65);     // p^2 < 4 q^2: at most 4 additions
+    uint32_t t[64];
+    st::mont_mul(t, d, A.k(KT_PPINVQQR, row), qq, st::neg_inv32_st(qq[0]), 64, big);
+    st::mul_add(x128, 128, t, 64, pp, 64, yp, 64);
+}
+// recombine `count` (1..4) consecutive (YP, YQ) field pairs starting at slot `first` into XC
+static __global__ void gg20_crt(Arena A, int first, int count) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= A.U) return;
+    const uint32_t row = A.row_own[u];
+    for (int s = first; s < first + count; s++) crt_combine(A.p(F_XC0 + s, u), A, row, A.p(F_YP0 + s, u), A.p(F_YQ0 + s, u));
 }
 
 }  // namespace tecdsa

@@ -47,12 +47,12 @@ struct ExpClass {
     Operand mod;            // K limbs
     Operand base[2];        // K limbs each
     Operand exp[2];         // exp_limbs[b] limbs each
-    Operand mul[2];         // K limbs each (plain residues, any value < 2^(32K))
+    Operand mul[3];         // K limbs each (plain residues, any value < 2^(32K))
     uint32_t* out;          // K limbs per instance, out_stride apart
     uint32_t out_stride;
     int exp_limbs[2];
     int nbases;             // 0..2
-    int nmul;               // 0..2
+    int nmul;               // 0..3
     int wide0;              // base[0] is 2K limbs wide and is reduced mod n first (c mod p^2, kzen-paillier decrypt)
     // fixed-base mode: both bases are per-key constants (h1, h2 of a DLogStatement) whose powers
     // base^(j * 2^(5w)) were tabulated at key upload; the job is then a pure product, no squarings.
@@ -195,9 +195,10 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
         } else {
             load_operand<TPI, L>(u, c.mul[0], i);
             mont_mul<TPI, L>(acc, acc, u, m.n, m.n0inv);              // plain acc * m1
-            if (c.nmul > 1) {
-                load_operand<TPI, L>(u, c.mul[1], i);
-                mont_mul<TPI, L>(u, u, m.rr, m.n, m.n0inv);           // m2 * R   (rr < n keeps it canonical)
+#pragma unroll 1
+            for (int k = 1; k < c.nmul; k++) {
+                load_operand<TPI, L>(u, c.mul[k], i);
+                mont_mul<TPI, L>(u, u, m.rr, m.n, m.n0inv);           // m_k * R   (rr < n keeps it canonical)
                 mont_mul<TPI, L>(acc, acc, u, m.n, m.n0inv);
             }
         }

@@ -26,6 +26,11 @@ void h_decrypt_finish(uint32_t* m64, uint32_t** tables, uint32_t row, const uint
     for (int t = 0; t < KT_COUNT; t++) A.key[t] = tables[t];
     decrypt_finish(m64, A, row, dp, dq);
 }
+void h_crt_combine(uint32_t* x128, uint32_t** tables, uint32_t row, const uint32_t* yp, const uint32_t* yq) {
+    Arena A; memset(&A, 0, sizeof(A));
+    for (int t = 0; t < KT_COUNT; t++) A.key[t] = tables[t];
+    crt_combine(x128, A, row, yp, yq);
+}
 void h_sc_from_limbs(uint32_t* out8, const uint32_t* x, int n) { U256 r = sc_from_limbs(x, n); memcpy(out8, r.v, 32); }
 void h_sc_mul(uint32_t* out8, const uint32_t* a, const uint32_t* b) { U256 r = sc_mul(u256_load(a), u256_load(b)); memcpy(out8, r.v, 32); }
 void h_sc_inv(uint32_t* out8, const uint32_t* a) { U256 r = sc_inv(u256_load(a)); memcpy(out8, r.v, 32); }

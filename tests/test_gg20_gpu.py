@@ -38,6 +38,7 @@ def test_key_tables_derived_on_device(engine, pkg, keyset):
     assert ks.table(11, 32) == [pow(k.dk.p, -1, R) for k in keyset]                       # p^-1 mod 2^1024
     assert ks.table(13, 32) == [(-pow(k.dk.q, -1, k.dk.p)) % k.dk.p * R % k.dk.p for k in keyset]   # hp * R mod p
     assert ks.table(15, 32) == [pow(k.dk.p, -1, k.dk.q) * R % k.dk.q for k in keyset]     # (p^-1 mod q) * R mod q
+    assert ks.table(16, 64) == [pow(k.dk.p ** 2, -1, k.dk.q ** 2) * (1 << 2048) % k.dk.q ** 2 for k in keyset]
     ks.free()
 
 

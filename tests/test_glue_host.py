@@ -15,7 +15,7 @@ from oracle import gg20_oracle as o
 from oracle.sampling import Drbg
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness")
-KEY_SIZE = [64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 8, 16]
+KEY_SIZE = [64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 8, 16]
 
 
 @pytest.fixture(scope="module")
@@ -139,6 +139,14 @@ def test_key_setup_and_decrypt_tail(h, keyset):
         assert I(tabs[11][r]) == pow(p, -1, R) and I(tabs[12][r]) == pow(q, -1, R)
         assert I(tabs[13][r]) == (-pow(q, -1, p)) % p * R % p and I(tabs[14][r]) == (-pow(p, -1, q)) % q * R % q
         assert I(tabs[15][r]) == pow(p, -1, q) * R % q
+        R64 = 1 << 2048
+        assert I(tabs[16][r]) == pow(p * p, -1, q * q) * R64 % (q * q)
+        for _ in range(2):          # CRT recombination of an own-key power b^N mod N^2
+            b = rng.randrange(1, p * q)
+            yp, yq = pow(b, p * q, p * p), pow(b, p * q, q * q)
+            out = np.zeros(128, np.uint32)
+            h.h_crt_combine(P(out), ptrs, r, P(L(yp, 64)), P(L(yq, 64)))
+            assert I(out) == pow(b, p * q, (p * q) ** 2)
         ek = lk.paillier_key_vec[r]
         for _ in range(2):
             m = rng.randrange(ek.n)
