@@ -55,6 +55,12 @@ extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
     c->sm_count = prop.multiProcessorCount;
     // the glue kernels call non-inlined EC / hash routines with multi-KB frames
     CK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
+    {
+        const uint32_t* fbp = nullptr;
+        int rc = tecdsa_internal_fb_points_init(device, c->stream, &fbp);
+        if (rc == 0) rc = tecdsa_internal_fb_points_set_l12(fbp);
+        if (rc) { delete c; return rc; }
+    }
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     *out = c;

@@ -73,8 +73,8 @@ struct Builder {
 const Operand NONE = {nullptr, nullptr, 0, 0, 0};
 constexpr int GPW64 = 32 / TPI_2048, GPW128 = 32 / TPI_4096;
 
-template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A) {
-    int grid = (A.U + 63) / 64;
+template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A, int per_unit = 1) {
+    int grid = (A.U * per_unit + 63) / 64;
     kern<<<grid, 64, 0, c->stream>>>(A);
     c->count_launch();
     cudaError_t e = cudaGetLastError();
@@ -89,6 +89,24 @@ int glue_crt(tecdsa_ctx* c, const Arena& A, int first, int count) {
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------ fixed-base point tables
+int tecdsa_internal_fb_points_init(int device, cudaStream_t stream, const uint32_t** table_out) {
+    static uint32_t* tables[64] = {};
+    if (device < 0 || device >= 64) return tecdsa_fail(TECDSA_E_ARG, "fb_points: bad device");
+    if (!tables[device]) {
+        uint32_t* t = nullptr;
+        CK(cudaMalloc(&t, (size_t)2 * secp::FBP_WINDOWS * secp::FBP_DIGITS * 16 * 4));
+        secp::fb_points_build<<<(2 * secp::FBP_WINDOWS + 31) / 32, 32, 0, stream>>>(t);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        tables[device] = t;
+    }
+    const uint32_t* p = tables[device];
+    CK(cudaMemcpyToSymbol(secp::g_fb_points, &p, sizeof(p)));
+    *table_out = p;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------ keys
 extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_keyset** out) {
@@ -273,7 +291,8 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     B.exp_class(L128, GPW128, B.key(KT_NN, rp), 2, B.rnd(RND_R_G, 64), B.key(KT_N, rp), 64, B.peer(F_CK), B.rnd(RND_GAMMA, 8), 8, 1, B.fld(F_LBG), NONE, F_CBG);
     B.exp_class(L128, GPW128, B.key(KT_NN, rp), 2, B.rnd(RND_R_W, 64), B.key(KT_N, rp), 64, B.peer(F_CK), B.fld(F_W), 8, 1, B.fld(F_LBW), NONE, F_CBW);
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
-    RUN(glue(c, gg20_r1_post, A));
+    RUN(glue(c, gg20_r1_post_hash, A, 3));
+    RUN(glue(c, gg20_r1_post_dlog, A, 4));
 
     // ================= Round 2 (rounds.rs:234-317): Paillier decrypt of the peer's two MessageB
     B.exp_class(L64, GPW64, B.key(KT_PP, ro), 1, B.peer(F_CBG), B.key(KT_PM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DPG, 1);
@@ -281,9 +300,11 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     B.exp_class(L64, GPW64, B.key(KT_PP, ro), 1, B.peer(F_CBW), B.key(KT_PM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DPW, 1);
     B.exp_class(L64, GPW64, B.key(KT_QQ, ro), 1, B.peer(F_CBW), B.key(KT_QM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DQW, 1);
     RUN(run_exp(c, L64, 64));
-    RUN(glue(c, gg20_r2, A));
+    RUN(glue(c, gg20_r2_check, A, 3));
+    RUN(glue(c, gg20_r2_finish, A));
     // ================= Round 3 (rounds.rs:347-402)
-    RUN(glue(c, gg20_r3, A));
+    RUN(glue(c, gg20_r3_check, A, 2));
+    RUN(glue(c, gg20_r3_finish, A));
     // ================= Round 4 (rounds.rs:431-498): R, R_dash, PDLwSlackProof::prove against the peer's statement
     RUN(glue(c, gg20_r4_pre, A));
     B.fb_class(L64, GPW64, rp, B.rnd(RND_PDL_RHO, 72), 72, B.rnd(RND_K, 8), 8, 0, NONE, F_PZ);                  // z  (:78-84)
@@ -327,8 +348,10 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         else B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, s2, B.key(KT_N, prover), 64, NONE, NONE, 0, 2, B.fld(F_VLIN0 + j), B.fld(F_VCEI0 + j), F_VU20 + j);
     }
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
-    RUN(glue(c, gg20_r5_post, A));
+    RUN(glue(c, gg20_r5_check, A, 2));
+    RUN(glue(c, gg20_r5_finish, A));
     // ================= Round 6 (rounds.rs:612-636) + result records
+    RUN(glue(c, gg20_r6_check, A, 2));
     RUN(glue(c, gg20_r6, A));
 #undef RUN
     CK(cudaEventRecord(c->ev1, c->stream));

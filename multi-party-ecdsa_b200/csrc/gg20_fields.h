@@ -51,7 +51,7 @@ enum : int {
     X(VZEI0, 64) X(VZEI1, 64) X(VCEI0, 128) X(VCEI1, 128) X(VU20, 128) X(VU21, 128) X(VU30, 64) X(VU31, 64) \
     X(SI, 16) X(HEG, 48)                            /* T 16 | A3 16 | z1 8 | z2 8 */             \
     X(DIGEST, 8)                                                                                  \
-    X(FLAGS, 4)                                     /* ok bytes of the inversions, packed */         \
+    X(FLAGS, 8)                                     /* one ok byte per check, see gg20_glue.cuh */          \
     X(DBG, 256)                                     /* scratch for tools/debug_gg20.py */            \
     /* own-key powers b^N mod N^2 through CRT: halves mod p^2 / q^2 and the recombined value */      \
     X(YP0, 64) X(YP1, 64) X(YP2, 64) X(YP3, 64) X(YP4, 64) X(YP5, 64)                              \

@@ -39,7 +39,8 @@ struct Arena {
     __device__ __forceinline__ uint8_t* flags(int u) const { return reinterpret_cast<uint8_t*>(p(F_FLAGS, u)); }
     __device__ __forceinline__ void fail(int u, uint8_t code) const { if (status[u] == 0) status[u] = code; }
 };
-// FLAGS bytes: 0..2 ZEI ok, 3..5 CEI ok, 6..7 VZEI ok, 8..9 VCEI ok, 10 range bits
+// FLAGS bytes: 0..2 ZEI ok, 3..5 CEI ok, 6..7 VZEI ok, 8..9 VCEI ok, 10 range bits, 11..12 MessageB checks ok,
+// 13 g_w_vec ok, 14..15 Pedersen ok, 16..17 PDL ok, 18..19 HomoElGamal ok, 20..22 AliceProof challenge ok
 
 // ------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ U256 load_scalar(const uint32_t* p) { return sc_reduce_once(u256_load(p), 0); }
@@ -61,8 +62,13 @@ static __device__ __noinline__ U256 hash_points_scalar(const Affine* pts, int n)
     U256 d; h.finish(d.v);
     return sc_reduce_once(d, 0);
 }
-__device__ __forceinline__ Affine mul_G(const U256& k) { return pt_mul(affine_G(), k); }
-__device__ __forceinline__ Affine mul_H(const U256& k) { return pt_mul(affine_H(), k); }
+__device__ __forceinline__ Affine mul_G(const U256& k) { return jac_to_affine(jac_mul_fixed(0, k)); }
+__device__ __forceinline__ Affine mul_H(const U256& k) { return jac_to_affine(jac_mul_fixed(1, k)); }
+// a*G + b*H and a*G + b*P through the fixed-base tables
+__device__ __forceinline__ Affine lin_GH(const U256& a, const U256& b) { return jac_to_affine(jac_add(jac_mul_fixed(0, a), jac_mul_fixed(1, b))); }
+__device__ __forceinline__ Affine lin_GP(const U256& a, const Affine& P, const U256& b) {
+    return jac_to_affine(jac_add(jac_mul_fixed(0, a), jac_mul(jac_from_affine(P), b)));
+}
 __device__ __forceinline__ Affine pt_add_aff(const Affine& a, const Affine& b) {
     return jac_to_affine(jac_add(jac_from_affine(a), jac_from_affine(b)));
 }
@@ -91,7 +97,7 @@ static __device__ __noinline__ bool dlog_verify(const uint32_t* in) {
     if (pts[2].inf || pts[0].inf || !on_curve(pts[2]) || !on_curve(pts[0])) return false;
     U256 resp = load_scalar(in + 32);
     U256 e = hash_points_scalar(pts, 3);
-    Affine v = lin2(affine_G(), resp, pts[2], e);
+    Affine v = lin_GP(resp, pts[2], e);
     return affine_eq(v, pts[0]);
 }
 // `HashCommitment::create_commitment_with_user_defined_randomness(from_bytes(compress(P)), blind)` (party_i.rs:577-580)
@@ -173,29 +179,31 @@ static __global__ void gg20_r1_pre(Arena A) {
     st::mul_add(A.p(F_LBG, u), 128, rnd + RND_BT_G, 64, Np, 64, &one, 1);
     st::mul_add(A.p(F_LBW, u), 128, rnd + RND_BT_W, 64, Np, 64, &one, 1);
 }
-// end of AliceProof::verify (range_proofs.rs:143-153), rest of MessageB::b (mta/mod.rs:132,146-148)
-static __global__ void gg20_r1_post(Arena A) {
-    int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= A.U) return;
-    const int pu = A.peer[u];
+// end of AliceProof::verify (range_proofs.rs:143-153): one thread per (unit, statement)
+static __global__ void gg20_r1_post_hash(Arena A) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.U * 3) return;
+    const int u = t / 3, x = t % 3, pu = A.peer[u];
+    uint32_t* e = A.p(F_DBG, u) + 8 * x;          // recomputed challenge (kept in the arena)
+    alice_hash(e, A.k(KT_N, A.row_peer[u]), A.p(F_CK, pu), A.p(F_Z0 + x, pu), A.p(F_UV0 + x, u), A.p(F_WV0 + x, u));
+    A.flags(u)[20 + x] = st::cmp(e, A.p(F_E0 + x, pu), 8) == 0;
+}
+// rest of MessageB::b (mta/mod.rs:132,146-148): one thread per (unit, DLogProof)
+static __global__ void gg20_r1_post_dlog(Arena A) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.U * 4) return;
+    const int u = t >> 2, j = t & 3;
     const uint32_t* rnd = A.p(F_RND, u);
-    const uint32_t* Np = A.k(KT_N, A.row_peer[u]);
-    const uint8_t* fl = A.flags(u);
-    bool ok = fl[10] == 0;
-    for (int x = 0; x < 3; x++) {
-        ok = ok && fl[x] && fl[3 + x];
-        uint32_t* e = A.p(F_DBG, u) + 8 * x;          // recomputed challenge (kept in the arena)
-        alice_hash(e, Np, A.p(F_CK, pu), A.p(F_Z0 + x, pu), A.p(F_UV0 + x, u), A.p(F_WV0 + x, u));
-        ok = ok && st::cmp(e, A.p(F_E0 + x, pu), 8) == 0;
+    U256 sk;
+    if (j == 0) sk = load_scalar(rnd + RND_GAMMA);
+    else if (j == 2) sk = u256_load(A.p(F_W, u));
+    else {
+        sk = sc_from_limbs(rnd + (j == 1 ? RND_BT_G : RND_BT_W), 64);
+        u256_store(A.p(j == 1 ? F_BTG_FE : F_BTW_FE, u), sk);
+        u256_store(A.p(j == 1 ? F_BETA_G : F_NU, u), sc_neg(sk));
     }
-    if (!ok) A.fail(u, TECDSA_ST_INVALID_KEY);
-    U256 btg = sc_from_limbs(rnd + RND_BT_G, 64), btw = sc_from_limbs(rnd + RND_BT_W, 64);
-    u256_store(A.p(F_BTG_FE, u), btg); u256_store(A.p(F_BTW_FE, u), btw);
-    u256_store(A.p(F_BETA_G, u), sc_neg(btg)); u256_store(A.p(F_NU, u), sc_neg(btw));
-    dlog_prove(A.p(F_DL0, u), load_scalar(rnd + RND_GAMMA), load_scalar(rnd + RND_NB_G));
-    dlog_prove(A.p(F_DL1, u), btg, load_scalar(rnd + RND_NBT_G));
-    dlog_prove(A.p(F_DL2, u), u256_load(A.p(F_W, u)), load_scalar(rnd + RND_NB_W));
-    dlog_prove(A.p(F_DL3, u), btw, load_scalar(rnd + RND_NBT_W));
+    const int nonce_off = j == 0 ? RND_NB_G : j == 1 ? RND_NBT_G : j == 2 ? RND_NB_W : RND_NBT_W;
+    dlog_prove(A.p(F_DL0 + j, u), sk, load_scalar(rnd + nonce_off));
 }
 
 // ------------------------------------------------------------------------------ round 2
@@ -224,42 +232,48 @@ static __device__ __noinline__ void decrypt_finish(uint32_t* m64, const Arena& A
     st::mont_mul(uu, diff, A.k(KT_PINVQR, row), q, st::neg_inv32_st(q[0]), 32, scratch);
     st::mul_add(m64, 64, uu, 32, p, 32, mp, 32);
 }
-// MessageB::verify_proofs_get_alpha (mta/mod.rs:160-179) for the gamma and the w message, the
-// g_w_vec assert (sign/rounds.rs:281), phase2_delta_i / phase2_sigma_i (party_i.rs:591-618),
-// phase3_compute_t_i + PedersenProof::prove [R] (party_i.rs:620-634)
-static __global__ void gg20_r2(Arena A) {
+// MessageB::verify_proofs_get_alpha (mta/mod.rs:160-179): threads (unit, 0) and (unit, 1) handle the gamma and the
+// w message (Paillier CRT tail, G*alpha == B*k + B', both DLogProofs); thread (unit, 2) the g_w_vec assert
+// (sign/rounds.rs:281)
+static __global__ void gg20_r2_check(Arena A) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.U * 3) return;
+    const int u = t / 3, m = t % 3, pu = A.peer[u];
+    const uint32_t row = A.row_own[u], prow = A.row_peer[u];
+    if (m == 2) {
+        Affine gw = pt_mul(affine_load(A.k(KT_PK, prow)), lagrange2(prow % 3, row % 3));
+        A.flags(u)[13] = affine_eq(gw, affine_load(A.p(F_DL2, pu)));
+        return;
+    }
+    // the plaintext goes to the arena (it is also part of the reference's return value, mta/mod.rs:175)
+    uint32_t* plain = A.p(m ? F_APLW : F_APLG, u);
+    decrypt_finish(plain, A, row, A.p(m ? F_DPW : F_DPG, u), A.p(m ? F_DQW : F_DQG, u));
+    U256 alpha = sc_from_limbs(plain, 64);
+    u256_store(A.p(m ? F_MU : F_ALPHA, u), alpha);
+    const U256 k = load_scalar(A.p(F_RND, u) + RND_K);
+    const uint32_t* bp = A.p(m ? F_DL2 : F_DL0, pu);
+    const uint32_t* btp = A.p(m ? F_DL3 : F_DL1, pu);
+    Affine g_alpha = mul_G(alpha);
+    Affine ba_btag = jac_to_affine(jac_add(jac_mul(jac_from_affine(affine_load(bp)), k), jac_from_affine(affine_load(btp))));
+    const bool v1 = dlog_verify(bp), v2 = dlog_verify(btp);
+    A.flags(u)[11 + m] = v1 && v2 && affine_eq(ba_btag, g_alpha);
+}
+// phase2_delta_i / phase2_sigma_i (party_i.rs:591-618), phase3_compute_t_i + PedersenProof::prove [R] (party_i.rs:620-634)
+static __global__ void gg20_r2_finish(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
-    const int pu = A.peer[u];
     const uint32_t* rnd = A.p(F_RND, u);
-    const uint32_t row = A.row_own[u], prow = A.row_peer[u];
-    const U256 k = load_scalar(rnd + RND_K);
-    U256 shares[2];
-    bool ok = true;
-    for (int m = 0; m < 2; m++) {
-        // the plaintext goes to the arena (it is also part of the reference's return value, mta/mod.rs:175)
-        uint32_t* plain = A.p(m ? F_APLW : F_APLG, u);
-        decrypt_finish(plain, A, row, A.p(m ? F_DPW : F_DPG, u), A.p(m ? F_DQW : F_DQG, u));
-        U256 alpha = sc_from_limbs(plain, 64);
-        shares[m] = alpha;
-        const uint32_t* bp = A.p(m ? F_DL2 : F_DL0, pu);
-        const uint32_t* btp = A.p(m ? F_DL3 : F_DL1, pu);
-        Affine g_alpha = mul_G(alpha);
-        Affine ba_btag = jac_to_affine(jac_add(jac_mul(jac_from_affine(affine_load(bp)), k), jac_from_affine(affine_load(btp))));
-        ok = ok && dlog_verify(bp) && dlog_verify(btp) && affine_eq(ba_btag, g_alpha);
-    }
-    {   // assert_eq!(m_b.b_proof.pk, g_w_vec[ind])
-        Affine gw = pt_mul(affine_load(A.k(KT_PK, prow)), lagrange2(prow % 3, row % 3));
-        ok = ok && affine_eq(gw, affine_load(A.p(F_DL2, pu)));
-    }
-    if (!ok) A.fail(u, TECDSA_ST_INVALID_KEY);
-    u256_store(A.p(F_ALPHA, u), shares[0]); u256_store(A.p(F_MU, u), shares[1]);
-    const U256 gamma = load_scalar(rnd + RND_GAMMA), w = u256_load(A.p(F_W, u));
-    U256 delta = sc_add(sc_add(sc_mul(k, gamma), shares[0]), u256_load(A.p(F_BETA_G, u)));
-    U256 sigma = sc_add(sc_add(sc_mul(k, w), shares[1]), u256_load(A.p(F_NU, u)));
+    const uint8_t* fl = A.flags(u);
+    bool ok1 = fl[10] == 0;
+    for (int x = 0; x < 3; x++) ok1 = ok1 && fl[x] && fl[3 + x] && fl[20 + x];
+    if (!ok1) A.fail(u, TECDSA_ST_INVALID_KEY);                    // MessageB::b -> Err(InvalidKey) (mta/mod.rs:123-131)
+    if (!(fl[11] && fl[12] && fl[13])) A.fail(u, TECDSA_ST_INVALID_KEY);
+    const U256 k = load_scalar(rnd + RND_K), gamma = load_scalar(rnd + RND_GAMMA), w = u256_load(A.p(F_W, u));
+    U256 delta = sc_add(sc_add(sc_mul(k, gamma), u256_load(A.p(F_ALPHA, u))), u256_load(A.p(F_BETA_G, u)));
+    U256 sigma = sc_add(sc_add(sc_mul(k, w), u256_load(A.p(F_MU, u))), u256_load(A.p(F_NU, u)));
     u256_store(A.p(F_DELTA, u), delta); u256_store(A.p(F_SIGMA, u), sigma);
     const U256 l = load_scalar(rnd + RND_L);
-    Affine T = lin2(affine_G(), sigma, affine_H(), l);
+    Affine T = lin_GH(sigma, l);
     affine_store(A.p(F_T, u), T);
     const U256 s1 = load_scalar(rnd + RND_PED_S1), s2 = load_scalar(rnd + RND_PED_S2);
     Affine pts[5];
@@ -277,16 +291,23 @@ static __device__ __noinline__ bool pedersen_verify(const uint32_t* ped, const A
     pts[0] = affine_G(); pts[1] = affine_H(); pts[2] = com; pts[3] = affine_load(ped + 8); pts[4] = affine_load(ped + 24);
     if (com.inf || !on_curve(com) || !on_curve(pts[3]) || !on_curve(pts[4])) return false;
     U256 e = hash_points_scalar(pts, 5);
-    Affine lhs = lin2(affine_G(), load_scalar(ped + 40), affine_H(), load_scalar(ped + 48));
+    Affine lhs = lin_GH(load_scalar(ped + 40), load_scalar(ped + 48));
     Jac rhs = jac_add(jac_add(jac_from_affine(pts[3]), jac_from_affine(pts[4])), jac_mul(jac_from_affine(com), e));
     return affine_eq(lhs, jac_to_affine(rhs));
 }
-static __global__ void gg20_r3(Arena A) {
+// one thread per (unit, signer): PedersenProof::verify of the own (j = 0) and the peer's (j = 1) proof
+static __global__ void gg20_r3_check(Arena A) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.U * 2) return;
+    const int u = t >> 1, j = t & 1, src = j ? A.peer[u] : u;
+    A.flags(u)[14 + j] = pedersen_verify(A.p(F_PED, src), affine_load(A.p(F_T, src)));
+}
+static __global__ void gg20_r3_finish(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
-    bool ok = pedersen_verify(A.p(F_PED, u), affine_load(A.p(F_T, u))) && pedersen_verify(A.p(F_PED, pu), affine_load(A.p(F_T, pu)));
-    if (!ok) A.fail(u, TECDSA_ST_PROOF);
+    const uint8_t* fl = A.flags(u);
+    if (!(fl[14] && fl[15])) A.fail(u, TECDSA_ST_PROOF);
     U256 sum = sc_add(u256_load(A.p(F_DELTA, u)), u256_load(A.p(F_DELTA, pu)));
     if (u256_is_zero(sum)) A.fail(u, TECDSA_ST_PROOF);          // reference: .unwrap() panic on a zero sum
     u256_store(A.p(F_DINV, u), sc_inv(sum));
@@ -360,25 +381,30 @@ static __device__ __noinline__ U256 heg_hash(const Affine& T, const Affine& A3, 
     pts[0] = T; pts[1] = A3; pts[2] = Gp; pts[3] = affine_H(); pts[4] = affine_G(); pts[5] = D; pts[6] = E;
     return hash_points_scalar(pts, 7);
 }
-static __global__ void gg20_r5_post(Arena A) {
+// one thread per (unit, proof): the EC relation and the two big-integer comparisons of PDLwSlackProof::verify
+static __global__ void gg20_r5_check(Arena A) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.U * 2) return;
+    const int u = t >> 1, j = t & 1, src = j ? A.peer[u] : u;
+    const uint8_t* fl = A.flags(u);
+    Affine R = affine_load(A.p(F_R, u));
+    U256 e = sc_from_limbs(A.p(F_VE0 + j, u), 8);
+    U256 s1 = sc_from_limbs(A.p(F_PS1, src), 28);
+    Affine u1t = lin2(R, s1, affine_load(A.p(F_RD, src)), sc_neg(e));
+    bool ok = fl[6 + j] && fl[8 + j];
+    ok = ok && affine_eq(u1t, affine_load(A.p(F_PU1, src)));
+    ok = ok && st::cmp(A.p(F_VU20 + j, u), A.p(F_PU2, src), 128) == 0;
+    ok = ok && st::cmp(A.p(F_VU30 + j, u), A.p(F_PU3, src), 64) == 0;
+    A.flags(u)[16 + j] = ok;
+}
+static __global__ void gg20_r5_finish(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
     const uint32_t* rnd = A.p(F_RND, u);
     const uint8_t* fl = A.flags(u);
     Affine R = affine_load(A.p(F_R, u));
-    bool ok = true;
-    for (int j = 0; j < 2; j++) {
-        const int src = j ? pu : u;
-        U256 e = sc_from_limbs(A.p(F_VE0 + j, u), 8);
-        U256 s1 = sc_from_limbs(A.p(F_PS1, src), 28);
-        Affine u1t = lin2(R, s1, affine_load(A.p(F_RD, src)), sc_neg(e));
-        ok = ok && fl[6 + j] && fl[8 + j];
-        ok = ok && affine_eq(u1t, affine_load(A.p(F_PU1, src)));
-        ok = ok && st::cmp(A.p(F_VU20 + j, u), A.p(F_PU2, src), 128) == 0;
-        ok = ok && st::cmp(A.p(F_VU30 + j, u), A.p(F_PU3, src), 64) == 0;
-    }
-    if (!ok) A.fail(u, TECDSA_ST_PDL_VERIFY);
+    if (!(fl[16] && fl[17])) A.fail(u, TECDSA_ST_PDL_VERIFY);
     // phase5_check_R_dash_sum (party_i.rs:768-776): G + sum(R_dash) - G == G
     Affine rsum = pt_add_aff(affine_load(A.p(F_RD, u)), affine_load(A.p(F_RD, pu)));
     if (!affine_eq(rsum, affine_G())) A.fail(u, TECDSA_ST_PHASE5_BAD_SUM);
@@ -387,7 +413,7 @@ static __global__ void gg20_r5_post(Arena A) {
     const U256 s1 = load_scalar(rnd + RND_HEG_S1), s2 = load_scalar(rnd + RND_HEG_S2);
     Affine S = pt_mul(R, sigma);
     affine_store(A.p(F_SI, u), S);
-    Affine T = lin2(affine_H(), s1, affine_G(), s2);
+    Affine T = lin_GH(s2, s1);                       // A1 + A2 = H*s1 + G*s2
     Affine A3 = pt_mul(R, s2);
     U256 e = heg_hash(T, A3, R, affine_load(A.p(F_T, u)), S);
     uint32_t* heg = A.p(F_HEG, u);
@@ -402,7 +428,7 @@ static __device__ __noinline__ bool heg_verify(const uint32_t* heg, const Affine
     if (!on_curve(T) || !on_curve(A3) || !on_curve(D) || !on_curve(E)) return false;
     U256 z1 = load_scalar(heg + 32), z2 = load_scalar(heg + 40);
     U256 e = heg_hash(T, A3, R, D, E);
-    Affine l1 = lin2(affine_H(), z1, affine_G(), z2);
+    Affine l1 = lin_GH(z2, z1);                     // H*z1 + Y*z2 with Y = G
     Affine r1 = jac_to_affine(jac_add(jac_from_affine(T), jac_mul(jac_from_affine(D), e)));
     Affine l2 = pt_mul(R, z2);
     Affine r2 = jac_to_affine(jac_add(jac_from_affine(A3), jac_mul(jac_from_affine(E), e)));
@@ -415,14 +441,19 @@ __device__ __forceinline__ void put_padded(Sha256& h, const uint32_t* limbs, int
 }
 // phase6_verify_proof + phase6_check_S_i_sum (party_i.rs:801-848), then the unit's result record:
 // a SHA-256 over every message it emitted, in the fixed-width encoding of oracle/gg20_oracle.py
+// one thread per (unit, signer): HomoELGamalProof::verify (party_i.rs:801-833)
+static __global__ void gg20_r6_check(Arena A) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.U * 2) return;
+    const int u = t >> 1, j = t & 1, src = j ? A.peer[u] : u;
+    A.flags(u)[18 + j] = heg_verify(A.p(F_HEG, src), affine_load(A.p(F_R, u)), affine_load(A.p(F_T, src)), affine_load(A.p(F_SI, src)));
+}
 static __global__ void gg20_r6(Arena A) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= A.U) return;
     const int pu = A.peer[u];
-    Affine R = affine_load(A.p(F_R, u));
-    bool ok = heg_verify(A.p(F_HEG, u), R, affine_load(A.p(F_T, u)), affine_load(A.p(F_SI, u))) &&
-              heg_verify(A.p(F_HEG, pu), R, affine_load(A.p(F_T, pu)), affine_load(A.p(F_SI, pu)));
-    if (!ok) A.fail(u, TECDSA_ST_PHASE6);
+    const uint8_t* fl = A.flags(u);
+    if (!(fl[18] && fl[19])) A.fail(u, TECDSA_ST_PHASE6);
     Affine ssum = pt_add_aff(affine_load(A.p(F_SI, u)), affine_load(A.p(F_SI, pu)));
     if (!affine_eq(ssum, affine_load(A.ypk + (size_t)A.keyset[u] * 16))) A.fail(u, TECDSA_ST_PHASE6);
 

@@ -116,11 +116,14 @@ __global__ void k_square(uint32_t* nn, const uint32_t* n, int count) {
 __global__ void k_secp_mul(uint32_t* out, const uint32_t* pts, const uint32_t* scalars, int count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    Affine P = pts ? affine_load(pts + (size_t)i * 16) : affine_G();
     U256 k = sc_from_limbs(scalars + (size_t)i * 8, 8);
     Affine r;
-    if (!P.inf && !on_curve(P)) { r.inf = true; r.x = u256_zero(); r.y = u256_zero(); }
-    else r = pt_mul(P, k);
+    if (!pts) r = mul_G(k);                                    // generator: fixed-base tables
+    else {
+        Affine P = affine_load(pts + (size_t)i * 16);
+        if (!P.inf && !on_curve(P)) { r.inf = true; r.x = u256_zero(); r.y = u256_zero(); }
+        else r = pt_mul(P, k);
+    }
     affine_store(out + (size_t)i * 16, r);
 }
 // Paillier decrypt tail over the keyset's CRT constants
@@ -302,6 +305,11 @@ Arena key_arena(const tecdsa_keyset* ks) {
 int grid_for(size_t count) { return (int)((count + 63) / 64); }
 
 }  // namespace
+
+int tecdsa_internal_fb_points_set_l12(const uint32_t* table) {
+    CK(cudaMemcpyToSymbol(secp::g_fb_points, &table, sizeof(table)));
+    return 0;
+}
 
 #define RUN(x) do { int _rc = (x); if (_rc) { S.finish(); return _rc; } } while (0)
 #define KCHECK() do { c->count_launch(); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { S.finish(); return tecdsa_fail(TECDSA_E_CUDA, "kernel launch", _e); } } while (0)

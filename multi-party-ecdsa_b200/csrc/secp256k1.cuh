@@ -286,6 +286,61 @@ static __device__ __noinline__ Jac jac_mul(const Jac& base, const U256& k) {
     return r;
 }
 __device__ __forceinline__ Affine pt_mul(const Affine& p, const U256& k) { return jac_to_affine(jac_mul(jac_from_affine(p), k)); }
+
+// Jacobian + affine (8M + 3S), all special cases handled
+static __device__ __noinline__ Jac jac_madd(const Jac& p, const Affine& a) {
+    if (a.inf) return p;
+    if (jac_is_inf(p)) return jac_from_affine(a);
+    U256 z1z1 = fe_sqr(p.z);
+    U256 u2 = fe_mul(a.x, z1z1), s2 = fe_mul(fe_mul(a.y, p.z), z1z1);
+    U256 h = fe_sub(u2, p.x), r = fe_sub(s2, p.y);
+    if (u256_is_zero(h)) {
+        if (u256_is_zero(r)) return jac_dbl(p);
+        return jac_identity();
+    }
+    U256 hh = fe_sqr(h), hhh = fe_mul(hh, h), v = fe_mul(p.x, hh);
+    Jac o;
+    o.x = fe_sub(fe_sub(fe_sqr(r), hhh), fe_dbl(v));
+    o.y = fe_sub(fe_mul(r, fe_sub(v, o.x)), fe_mul(p.y, hhh));
+    o.z = fe_mul(p.z, h);
+    return o;
+}
+
+// Fixed-base tables for the two constant points of the protocol (the generator and curv's
+// base_point2): T[b][w][d-1] = d * 16^w * B_b, affine, w < 64, d = 1..15 (123 KB, built once per
+// context by fb_points_build).  k * B_b is then at most 64 mixed additions and no doubling.
+static constexpr int FBP_WINDOWS = 64, FBP_DIGITS = 15;
+static __device__ const uint32_t* g_fb_points = nullptr;      // set per translation unit, see set_fb_points()
+
+__device__ __forceinline__ Jac jac_mul_fixed(int which, const U256& k) {
+    const uint32_t* t = g_fb_points + (size_t)which * FBP_WINDOWS * FBP_DIGITS * 16;
+    Jac r = jac_identity();
+    for (int w = 0; w < FBP_WINDOWS; w++) {
+        uint32_t d = (k.v[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (d) {
+            Affine a;
+            const uint32_t* e = t + ((size_t)w * FBP_DIGITS + (d - 1)) * 16;
+            a.x = u256_load(e); a.y = u256_load(e + 8); a.inf = false;
+            r = jac_madd(r, a);
+        }
+    }
+    return r;
+}
+// one thread per (base, window)
+static __global__ void fb_points_build(uint32_t* tables) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * FBP_WINDOWS) return;
+    const int which = id / FBP_WINDOWS, w = id % FBP_WINDOWS;
+    Jac b = jac_from_affine(which ? affine_H() : affine_G());
+    for (int i = 0; i < 4 * w; i++) b = jac_dbl(b);
+    Jac acc = b;
+    uint32_t* out = tables + ((size_t)which * FBP_WINDOWS + w) * FBP_DIGITS * 16;
+    for (int d = 1; d <= FBP_DIGITS; d++) {
+        Affine a = jac_to_affine(acc);
+        u256_store(out + (size_t)(d - 1) * 16, a.x); u256_store(out + (size_t)(d - 1) * 16 + 8, a.y);
+        acc = jac_add(acc, b);
+    }
+}
 __device__ __forceinline__ bool affine_eq(const Affine& a, const Affine& b) {
     if (a.inf || b.inf) return a.inf && b.inf;
     return u256_eq(a.x, b.x) && u256_eq(a.y, b.y);

@@ -16,7 +16,15 @@ static Dim3 blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, threadIdx = {0, 0, 0};
 #include "gg20_glue.cuh"
 using namespace tecdsa;
 
+static uint32_t g_host_fb[2 * secp::FBP_WINDOWS * secp::FBP_DIGITS * 16];
 extern "C" {
+void h_init() {
+    blockDim.x = 2 * secp::FBP_WINDOWS; blockIdx.x = 0;
+    for (int t = 0; t < 2 * secp::FBP_WINDOWS; t++) { threadIdx.x = t; secp::fb_points_build(g_host_fb); }
+    secp::g_fb_points = g_host_fb;
+    threadIdx.x = 0; blockDim.x = 1;
+}
+void h_mul_fixed(uint32_t* out16, int which, const uint32_t* k8) { affine_store(out16, jac_to_affine(secp::jac_mul_fixed(which, u256_load(k8)))); }
 void h_key_setup(uint32_t** tables, int rows) {
     blockDim.x = rows;
     for (int r = 0; r < rows; r++) { threadIdx.x = r; gg20_key_setup(tables, rows); }

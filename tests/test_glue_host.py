@@ -24,7 +24,9 @@ def h():
     srcs = [os.path.join(HERE, "harness.cpp")] + [os.path.join(entry.CSRC, f) for f in os.listdir(entry.CSRC) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O1", "-w", "-I", HERE, "-I", entry.CSRC, "-shared", "-fPIC", "-o", so, os.path.join(HERE, "harness.cpp")])
-    return ctypes.CDLL(so)
+    lib = ctypes.CDLL(so)
+    lib.h_init()
+    return lib
 
 
 def L(v, k):
@@ -75,6 +77,9 @@ def test_point_arithmetic(h):
     A, B = o.pt_mul(o.G, 1234567), o.pt_mul(o.H2, 987654321)
     for x, y in ((A, B), (A, A), (A, o.pt_neg(A)), (None, B), (A, None)):
         h.h_pt_add(P(o16), P(PT(x)), P(PT(y))); assert UNPT(o16) == o.pt_add(x, y)
+    for k in [1, 15, 16, o.Q - 1, 0] + [rng.randrange(o.Q) for _ in range(20)]:      # fixed-base tables (G and base_point2)
+        h.h_mul_fixed(P(o16), 0, P(L(k, 8))); assert UNPT(o16) == o.pt_mul(o.G, k)
+        h.h_mul_fixed(P(o16), 1, P(L(k, 8))); assert UNPT(o16) == o.pt_mul(o.H2, k)
     o8 = np.zeros(8, np.uint32)
     for own, peer in ((0, 1), (1, 0), (0, 2), (2, 1)):
         h.h_lagrange2(P(o8), own, peer); assert I(o8) == o.lagrange_at_zero(own, [own, peer])
