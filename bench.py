@@ -429,7 +429,10 @@ def main():
                 "d2h_bytes_per_step": int(batch * (K * 4 + 1)), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "int32-mad", "achieved": achieved_mac / 1e12, "peak": peak_mac / 1e12, "unit": "TMAC32/s",
-                     "frac": achieved_mac / peak_mac, "traffic": None,
+                     "frac": achieved_mac / peak_mac,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture of this kernel
+                     # (profiles/r01_ncu_modexp2048_summary.md): window tables written once and re-read; algorithmic bytes are 64 MiB
+                     "traffic": 1.863e9 if batch == BATCH else None,
                      "kernel": "modexp_kernel<64,TPI>", "kernel_ms": k_ms, "launches_per_step": k_launches,
                      "work_per_launch_mac32": W_MODEXP * batch,
                      "peak_source": "on-box IMAD.WIDE.U32 saturation micro-benchmark (tecdsa_imad_peak); "

@@ -104,3 +104,30 @@ def test_offline_detects_tampering(engine, pkg, keyset):
     assert res.status[1] == pkg.ST_INVALID_KEY == want[1].status
     assert res.status[0] == 0 and list(res.status[2:]) == [0, 0]
     ks.free()
+
+
+def test_offline_two_keysets_mixed_batch(engine, pkg):
+    """several key sets in one batch (BASELINE.json configs[4] reuses 8): every unit OK, and the digests of a sample of
+    sessions equal the oracle's."""
+    from mpecdsa_b200 import gg20
+    from tests.golden import fixtures
+    keysets = [fixtures.load_keyset(0), fixtures.load_keyset(1)]
+    ks = gg20.KeySets(engine, keysets)
+    rng = Drbg(99, "two-keysets")
+    sess, rnds, oracle_in = [], [], []
+    for s_i, (kidx, a, b) in enumerate([(1, 0, 1), (0, 2, 1), (1, 2, 0), (1, 1, 2)]):
+        keys = [keysets[kidx][a], keysets[kidx][b]]
+        s_l = [a + 1, b + 1]
+        r = [sample_unit(rng, keys, s_l, p) for p in range(2)]
+        sess.append((kidx, a, b)); rnds += r; oracle_in.append((keys, s_l, r))
+    res = gg20.offline_batch(engine, ks, sess, gg20.pack_randomness(rnds))
+    assert not res.status.any()
+    for s_i in (0, 3):
+        want = o.offline_session(*oracle_in[s_i])
+        for p in range(2):
+            assert _digest_int(res.digest[2 * s_i + p]).to_bytes(32, "big") == want[p].transcript
+    # a larger synthetic batch over both key sets: all units must complete (sum R_dash = G, sum S = y checks inside)
+    sessions, rnd = gg20.synthetic_batch(keysets, 96, 5)
+    res = gg20.offline_batch(engine, ks, sessions, rnd)
+    assert not res.status.any()
+    ks.free()
