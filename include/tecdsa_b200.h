@@ -153,6 +153,32 @@ int tecdsa_bob_proof_verify_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, cons
                                   const uint32_t* s1, const uint32_t* s2, const uint32_t* t1, const uint32_t* t2, const uint32_t* X,
                                   const uint32_t* u, uint8_t* status, size_t count, int mem);
 
+/* ---- curv-kzen sigma proofs and hashes used by the protocol (out-of-tree crate; call sites cited) ----------------
+ * Scalars are 8 limbs (reduced mod q on entry), points affine x||y 16 limbs.  Verifiers write TECDSA_ST_OK or
+ * TECDSA_ST_PROOF.  Encodings [R]: challenges hash 65-byte uncompressed points and reduce the digest mod q.
+ * DLogProof (mta/mod.rs:147-148,170-171): proof = pk 16 | pk_t_rand_commitment 16 | challenge_response 8 (40 limbs).
+ * PedersenProof (party_i.rs:631, sign/rounds.rs:371-378): com = m G + r H (H = base_point2);
+ *   proof = e 8 | a1 16 | a2 16 | z1 8 | z2 8 | pad 8 (64 limbs).
+ * HomoELGamalProof (party_i.rs:778-833) for the statement (G, H = base_point2, Y = generator, D, E), witness (x, r):
+ *   proof = T 16 | A3 16 | z1 8 | z2 8 (48 limbs).                                                                  */
+int tecdsa_dlog_prove_batch(tecdsa_ctx* ctx, const uint32_t* sk, const uint32_t* nonce, uint32_t* proof, size_t count, int mem);
+int tecdsa_dlog_verify_batch(tecdsa_ctx* ctx, const uint32_t* proof, uint8_t* status, size_t count, int mem);
+int tecdsa_pedersen_prove_batch(tecdsa_ctx* ctx, const uint32_t* m, const uint32_t* r, const uint32_t* s1, const uint32_t* s2,
+                                uint32_t* com, uint32_t* proof, size_t count, int mem);
+int tecdsa_pedersen_verify_batch(tecdsa_ctx* ctx, const uint32_t* com, const uint32_t* proof, uint8_t* status, size_t count, int mem);
+int tecdsa_heg_prove_batch(tecdsa_ctx* ctx, const uint32_t* G, const uint32_t* D, const uint32_t* E, const uint32_t* x, const uint32_t* r,
+                           const uint32_t* s1, const uint32_t* s2, uint32_t* proof, size_t count, int mem);
+int tecdsa_heg_verify_batch(tecdsa_ctx* ctx, const uint32_t* G, const uint32_t* D, const uint32_t* E, const uint32_t* proof, uint8_t* status,
+                            size_t count, int mem);
+/* `Sha256::new().chain_bigint(x_0)...chain_bigint(x_{k-1}).result_bigint()` (curv DigestExt; range_proofs.rs:143-150,
+ * zk_pdl_with_slack/mod.rs:102-110): element i is n_items integers packed back to back, item j having item_limbs[j]
+ * limbs; each is hashed as its minimal big-endian magnitude; digest = 8 limbs of the 256-bit result.  item_limbs is a
+ * HOST array.                                                                                                        */
+int tecdsa_sha256_bigints_batch(tecdsa_ctx* ctx, const uint32_t* data, const int* item_limbs, int n_items, uint32_t* digest, size_t count, int mem);
+/* `HashCommitment::<Sha256>::create_commitment_with_user_defined_randomness(from_bytes(P.to_bytes(true)), blind)`
+ * (gg_2020/party_i.rs:577-580,654-659): blind 8 limbs, commitment 8 limbs.                                           */
+int tecdsa_hash_commitment_batch(tecdsa_ctx* ctx, const uint32_t* points, const uint32_t* blind, uint32_t* com, size_t count, int mem);
+
 /* ---- L3: the batched GG20 offline-signing stage ----------------------------------------
  * One "unit" = one party's OfflineStage Round0..Round6
  *   (src/protocols/multi_party_ecdsa/gg_2020/state_machine/sign/rounds.rs:68-636,

@@ -34,6 +34,8 @@ EXPORTS = [
     "tecdsa_modmul_batch", "tecdsa_modinv_batch", "tecdsa_secp_mul_batch", "tecdsa_paillier_encrypt_batch", "tecdsa_paillier_mul_batch",
     "tecdsa_paillier_add_batch", "tecdsa_paillier_decrypt_batch", "tecdsa_alice_proof_generate_batch", "tecdsa_alice_proof_verify_batch",
     "tecdsa_pdl_prove_batch", "tecdsa_pdl_verify_batch", "tecdsa_bob_proof_generate_batch", "tecdsa_bob_proof_verify_batch",
+    "tecdsa_dlog_prove_batch", "tecdsa_dlog_verify_batch", "tecdsa_pedersen_prove_batch", "tecdsa_pedersen_verify_batch",
+    "tecdsa_heg_prove_batch", "tecdsa_heg_verify_batch", "tecdsa_sha256_bigints_batch", "tecdsa_hash_commitment_batch",
 ]
 
 

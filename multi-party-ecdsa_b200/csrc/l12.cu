@@ -295,6 +295,78 @@ __global__ void k_bob_vpost(Arena A, const uint32_t* ek_rows, const uint32_t* a_
     status[i] = st_;
 }
 
+
+// ---- curv sigma proofs and hashes as stand-alone batches ------------------------------------------------
+__global__ void k_dlog_prove(uint32_t* out40, const uint32_t* sk, const uint32_t* nonce, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    dlog_prove(out40 + (size_t)i * 40, sc_from_limbs(sk + (size_t)i * 8, 8), sc_from_limbs(nonce + (size_t)i * 8, 8));
+}
+__global__ void k_dlog_verify(const uint32_t* in40, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    status[i] = dlog_verify(in40 + (size_t)i * 40) ? TECDSA_ST_OK : TECDSA_ST_PROOF;
+}
+// PedersenProof::prove [R]: com = m G + r H; a1 = s1 G; a2 = s2 H; e = H(G,H,com,a1,a2); z1 = s1 + e m; z2 = s2 + e r
+__global__ void k_pedersen_prove(uint32_t* com16, uint32_t* ped64, const uint32_t* m, const uint32_t* r, const uint32_t* s1, const uint32_t* s2, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const U256 mm = sc_from_limbs(m + (size_t)i * 8, 8), rr = sc_from_limbs(r + (size_t)i * 8, 8);
+    const U256 a = sc_from_limbs(s1 + (size_t)i * 8, 8), b = sc_from_limbs(s2 + (size_t)i * 8, 8);
+    Affine pts[5];
+    pts[0] = affine_G(); pts[1] = affine_H(); pts[2] = lin_GH(mm, rr); pts[3] = mul_G(a); pts[4] = mul_H(b);
+    U256 e = hash_points_scalar(pts, 5);
+    uint32_t* ped = ped64 + (size_t)i * 64;
+    for (int j = 56; j < 64; j++) ped[j] = 0;
+    affine_store(com16 + (size_t)i * 16, pts[2]);
+    u256_store(ped, e); affine_store(ped + 8, pts[3]); affine_store(ped + 24, pts[4]);
+    u256_store(ped + 40, sc_add(a, sc_mul(e, mm))); u256_store(ped + 48, sc_add(b, sc_mul(e, rr)));
+}
+__global__ void k_pedersen_verify(const uint32_t* com16, const uint32_t* ped64, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    status[i] = pedersen_verify(ped64 + (size_t)i * 64, affine_load(com16 + (size_t)i * 16)) ? TECDSA_ST_OK : TECDSA_ST_PROOF;
+}
+// HomoELGamalProof::prove [R] for the statement (G, H = base_point2, Y = generator, D, E), witness (x, r)
+__global__ void k_heg_prove(uint32_t* heg48, const uint32_t* G16, const uint32_t* D16, const uint32_t* E16, const uint32_t* x, const uint32_t* r,
+                            const uint32_t* s1, const uint32_t* s2, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const U256 xx = sc_from_limbs(x + (size_t)i * 8, 8), rr = sc_from_limbs(r + (size_t)i * 8, 8);
+    const U256 a = sc_from_limbs(s1 + (size_t)i * 8, 8), b = sc_from_limbs(s2 + (size_t)i * 8, 8);
+    Affine Gp = affine_load(G16 + (size_t)i * 16);
+    Affine T = lin_GH(b, a);                       // H*s1 + Y*s2
+    Affine A3 = pt_mul(Gp, b);
+    U256 e = heg_hash(T, A3, Gp, affine_load(D16 + (size_t)i * 16), affine_load(E16 + (size_t)i * 16));
+    uint32_t* heg = heg48 + (size_t)i * 48;
+    affine_store(heg, T); affine_store(heg + 16, A3);
+    u256_store(heg + 32, u256_is_zero(xx) ? a : sc_add(a, sc_mul(xx, e)));
+    u256_store(heg + 40, sc_add(b, sc_mul(rr, e)));
+}
+__global__ void k_heg_verify(const uint32_t* heg48, const uint32_t* G16, const uint32_t* D16, const uint32_t* E16, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Affine Gp = affine_load(G16 + (size_t)i * 16);
+    bool ok = !Gp.inf && on_curve(Gp) && heg_verify(heg48 + (size_t)i * 48, Gp, affine_load(D16 + (size_t)i * 16), affine_load(E16 + (size_t)i * 16));
+    status[i] = ok ? TECDSA_ST_OK : TECDSA_ST_PROOF;
+}
+// `Sha256::new().chain_bigint(x_0)...chain_bigint(x_{k-1}).result_bigint()`: item j of element i has limbs[j] limbs at
+// data + i*stride + offset_j (offsets are the running sum of limbs)
+__global__ void k_sha256_bigints(const uint32_t* data, int stride, const int* limbs, int n_items, uint32_t* out8, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Sha256 h; h.init();
+    const uint32_t* p = data + (size_t)i * stride;
+    for (int j = 0; j < n_items; j++) { h.put_bigint(p, limbs[j]); p += limbs[j]; }
+    h.finish(out8 + (size_t)i * 8);
+}
+// HashCommitment::create_commitment_with_user_defined_randomness(from_bytes(compress(P)), blind)
+__global__ void k_hash_commit(const uint32_t* P16, const uint32_t* blind8, uint32_t* out8, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    hash_commit_point(out8 + (size_t)i * 8, affine_load(P16 + (size_t)i * 16), blind8 + (size_t)i * 8);
+}
+
 Arena key_arena(const tecdsa_keyset* ks) {
     Arena A;
     memset(&A, 0, sizeof(A));
@@ -667,6 +739,104 @@ extern "C" int tecdsa_bob_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyset*
     add_exp(L.e128, 128, n, NN, 2, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, arr(da, 128), arr(ds1, 28), 28, 2, arr(lin, 128), arr(mei, 128), v, 128);
     RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
     k_bob_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, da, dm, dz, zp, dt, v, w, de, ds1, dX, dU, bad, ok1, ok2, ok3, e2, dst, n);
+    KCHECK();
+    return S.finish();
+}
+
+
+// ------------------------------------------------------------------------------------------ curv sigma proofs / hashes
+#define SIMPLE_PROLOGUE(name)                                                        \
+    if (!c) return tecdsa_fail(TECDSA_E_ARG, name ": null ctx");                     \
+    if (count == 0) return 0;                                                        \
+    CK(cudaSetDevice(c->device));                                                    \
+    const int n = (int)count;                                                        \
+    Stage S(c, mem);
+
+extern "C" int tecdsa_dlog_prove_batch(tecdsa_ctx* c, const uint32_t* sk, const uint32_t* nonce, uint32_t* proof, size_t count, int mem) {
+    if (!sk || !nonce || !proof) return tecdsa_fail(TECDSA_E_ARG, "dlog_prove: null argument");
+    SIMPLE_PROLOGUE("dlog_prove")
+    const uint32_t *a = S.in(sk, count * 8), *b = S.in(nonce, count * 8);
+    uint32_t* o = S.out(proof, count * 40);
+    if (S.err) return S.finish();
+    k_dlog_prove<<<grid_for(count), 64, 0, c->stream>>>(o, a, b, n);
+    KCHECK();
+    return S.finish();
+}
+extern "C" int tecdsa_dlog_verify_batch(tecdsa_ctx* c, const uint32_t* proof, uint8_t* status, size_t count, int mem) {
+    if (!proof || !status) return tecdsa_fail(TECDSA_E_ARG, "dlog_verify: null argument");
+    SIMPLE_PROLOGUE("dlog_verify")
+    const uint32_t* a = S.in(proof, count * 40);
+    uint8_t* o = S.out(status, count);
+    if (S.err) return S.finish();
+    k_dlog_verify<<<grid_for(count), 64, 0, c->stream>>>(a, o, n);
+    KCHECK();
+    return S.finish();
+}
+extern "C" int tecdsa_pedersen_prove_batch(tecdsa_ctx* c, const uint32_t* m, const uint32_t* r, const uint32_t* s1, const uint32_t* s2,
+                                           uint32_t* com, uint32_t* proof, size_t count, int mem) {
+    if (!m || !r || !s1 || !s2 || !com || !proof) return tecdsa_fail(TECDSA_E_ARG, "pedersen_prove: null argument");
+    SIMPLE_PROLOGUE("pedersen_prove")
+    const uint32_t *dm = S.in(m, count * 8), *dr = S.in(r, count * 8), *d1 = S.in(s1, count * 8), *d2 = S.in(s2, count * 8);
+    uint32_t *dc = S.out(com, count * 16), *dp = S.out(proof, count * 64);
+    if (S.err) return S.finish();
+    k_pedersen_prove<<<grid_for(count), 64, 0, c->stream>>>(dc, dp, dm, dr, d1, d2, n);
+    KCHECK();
+    return S.finish();
+}
+extern "C" int tecdsa_pedersen_verify_batch(tecdsa_ctx* c, const uint32_t* com, const uint32_t* proof, uint8_t* status, size_t count, int mem) {
+    if (!com || !proof || !status) return tecdsa_fail(TECDSA_E_ARG, "pedersen_verify: null argument");
+    SIMPLE_PROLOGUE("pedersen_verify")
+    const uint32_t *dc = S.in(com, count * 16), *dp = S.in(proof, count * 64);
+    uint8_t* o = S.out(status, count);
+    if (S.err) return S.finish();
+    k_pedersen_verify<<<grid_for(count), 64, 0, c->stream>>>(dc, dp, o, n);
+    KCHECK();
+    return S.finish();
+}
+extern "C" int tecdsa_heg_prove_batch(tecdsa_ctx* c, const uint32_t* G, const uint32_t* D, const uint32_t* E, const uint32_t* x, const uint32_t* r,
+                                      const uint32_t* s1, const uint32_t* s2, uint32_t* proof, size_t count, int mem) {
+    if (!G || !D || !E || !x || !r || !s1 || !s2 || !proof) return tecdsa_fail(TECDSA_E_ARG, "heg_prove: null argument");
+    SIMPLE_PROLOGUE("heg_prove")
+    const uint32_t *dG = S.in(G, count * 16), *dD = S.in(D, count * 16), *dE = S.in(E, count * 16), *dx = S.in(x, count * 8), *dr = S.in(r, count * 8),
+                   *d1 = S.in(s1, count * 8), *d2 = S.in(s2, count * 8);
+    uint32_t* o = S.out(proof, count * 48);
+    if (S.err) return S.finish();
+    k_heg_prove<<<grid_for(count), 64, 0, c->stream>>>(o, dG, dD, dE, dx, dr, d1, d2, n);
+    KCHECK();
+    return S.finish();
+}
+extern "C" int tecdsa_heg_verify_batch(tecdsa_ctx* c, const uint32_t* G, const uint32_t* D, const uint32_t* E, const uint32_t* proof, uint8_t* status,
+                                       size_t count, int mem) {
+    if (!G || !D || !E || !proof || !status) return tecdsa_fail(TECDSA_E_ARG, "heg_verify: null argument");
+    SIMPLE_PROLOGUE("heg_verify")
+    const uint32_t *dG = S.in(G, count * 16), *dD = S.in(D, count * 16), *dE = S.in(E, count * 16), *dp = S.in(proof, count * 48);
+    uint8_t* o = S.out(status, count);
+    if (S.err) return S.finish();
+    k_heg_verify<<<grid_for(count), 64, 0, c->stream>>>(dp, dG, dD, dE, o, n);
+    KCHECK();
+    return S.finish();
+}
+extern "C" int tecdsa_sha256_bigints_batch(tecdsa_ctx* c, const uint32_t* data, const int* item_limbs, int n_items, uint32_t* digest, size_t count, int mem) {
+    if (!data || !item_limbs || !digest || n_items <= 0 || n_items > 64) return tecdsa_fail(TECDSA_E_ARG, "sha256_bigints: bad argument");
+    SIMPLE_PROLOGUE("sha256_bigints")
+    int stride = 0;
+    for (int j = 0; j < n_items; j++) { if (item_limbs[j] <= 0) { return tecdsa_fail(TECDSA_E_ARG, "sha256_bigints: bad item size"); } stride += item_limbs[j]; }
+    const uint32_t* dd = S.in(data, count * (size_t)stride);
+    int* dl = S.tmp<int>(n_items);
+    uint32_t* o = S.out(digest, count * 8);
+    if (S.err) return S.finish();
+    if (cudaMemcpyAsync(dl, item_limbs, n_items * sizeof(int), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { S.finish(); return tecdsa_fail(TECDSA_E_CUDA, "copy"); }
+    k_sha256_bigints<<<grid_for(count), 64, 0, c->stream>>>(dd, stride, dl, n_items, o, n);
+    KCHECK();
+    return S.finish();
+}
+extern "C" int tecdsa_hash_commitment_batch(tecdsa_ctx* c, const uint32_t* points, const uint32_t* blind, uint32_t* com, size_t count, int mem) {
+    if (!points || !blind || !com) return tecdsa_fail(TECDSA_E_ARG, "hash_commitment: null argument");
+    SIMPLE_PROLOGUE("hash_commitment")
+    const uint32_t *dp = S.in(points, count * 16), *db = S.in(blind, count * 8);
+    uint32_t* o = S.out(com, count * 8);
+    if (S.err) return S.finish();
+    k_hash_commit<<<grid_for(count), 64, 0, c->stream>>>(dp, db, o, n);
     KCHECK();
     return S.finish();
 }

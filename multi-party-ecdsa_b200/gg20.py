@@ -304,3 +304,87 @@ def bob_proof_verify(eng, keys, ek_row, st_row, a_enc, mta_out, pf, X=None, u=No
     status = np.full(n, 255, dtype=np.uint8)
     eng._ck(eng.lib.tecdsa_bob_proof_verify_batch(eng._ctx, keys.handle, *[_ptr(a) for a in ins], _ptr(Xa), _ptr(Ua), _ptr(status), n, HOST), "bob_proof_verify")
     return status
+
+
+# ----------------------------------------------------------------------------- curv sigma proofs / hashes, batched
+def _bind_sigma(lib):
+    if getattr(lib, "_sigma_bound", False):
+        return
+    V, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.tecdsa_dlog_prove_batch.argtypes = [V, V, V, V, S, I]
+    lib.tecdsa_dlog_verify_batch.argtypes = [V, V, V, S, I]
+    lib.tecdsa_pedersen_prove_batch.argtypes = [V] * 7 + [S, I]
+    lib.tecdsa_pedersen_verify_batch.argtypes = [V, V, V, V, S, I]
+    lib.tecdsa_heg_prove_batch.argtypes = [V] * 9 + [S, I]
+    lib.tecdsa_heg_verify_batch.argtypes = [V] * 6 + [S, I]
+    lib.tecdsa_sha256_bigints_batch.argtypes = [V, V, V, I, V, S, I]
+    lib.tecdsa_hash_commitment_batch.argtypes = [V, V, V, V, S, I]
+    lib._sigma_bound = True
+
+
+def dlog_prove(eng, sk, nonce):
+    """Batched curv `DLogProof::prove`; returns (n, 40) uint32: pk 16 | T 16 | response 8."""
+    _bind_sigma(eng.lib)
+    a, b = ints_to_limbs(sk, 8), ints_to_limbs(nonce, 8)
+    out = np.zeros((len(sk), 40), dtype=np.uint32)
+    eng._ck(eng.lib.tecdsa_dlog_prove_batch(eng._ctx, _ptr(a), _ptr(b), _ptr(out), len(sk), HOST), "dlog_prove")
+    return out
+
+
+def dlog_verify(eng, proofs: np.ndarray) -> np.ndarray:
+    _bind_sigma(eng.lib)
+    st = np.full(proofs.shape[0], 255, dtype=np.uint8)
+    p = np.ascontiguousarray(proofs, dtype=np.uint32)
+    eng._ck(eng.lib.tecdsa_dlog_verify_batch(eng._ctx, _ptr(p), _ptr(st), p.shape[0], HOST), "dlog_verify")
+    return st
+
+
+def pedersen_prove(eng, m, r, s1, s2):
+    _bind_sigma(eng.lib)
+    ins = [ints_to_limbs(x, 8) for x in (m, r, s1, s2)]
+    com, pf = np.zeros((len(m), 16), np.uint32), np.zeros((len(m), 64), np.uint32)
+    eng._ck(eng.lib.tecdsa_pedersen_prove_batch(eng._ctx, *[_ptr(a) for a in ins], _ptr(com), _ptr(pf), len(m), HOST), "pedersen_prove")
+    return com, pf
+
+
+def pedersen_verify(eng, com, pf) -> np.ndarray:
+    _bind_sigma(eng.lib)
+    st = np.full(com.shape[0], 255, dtype=np.uint8)
+    eng._ck(eng.lib.tecdsa_pedersen_verify_batch(eng._ctx, _ptr(com), _ptr(pf), _ptr(st), com.shape[0], HOST), "pedersen_verify")
+    return st
+
+
+def heg_prove(eng, G, D, E, x, r, s1, s2):
+    _bind_sigma(eng.lib)
+    ins = [_pts(G), _pts(D), _pts(E)] + [ints_to_limbs(v, 8) for v in (x, r, s1, s2)]
+    pf = np.zeros((len(x), 48), np.uint32)
+    eng._ck(eng.lib.tecdsa_heg_prove_batch(eng._ctx, *[_ptr(a) for a in ins], _ptr(pf), len(x), HOST), "heg_prove")
+    return pf
+
+
+def heg_verify(eng, G, D, E, pf) -> np.ndarray:
+    _bind_sigma(eng.lib)
+    st = np.full(pf.shape[0], 255, dtype=np.uint8)
+    ins = [_pts(G), _pts(D), _pts(E)]
+    eng._ck(eng.lib.tecdsa_heg_verify_batch(eng._ctx, *[_ptr(a) for a in ins], _ptr(pf), _ptr(st), pf.shape[0], HOST), "heg_verify")
+    return st
+
+
+def sha256_bigints(eng, rows, item_limbs):
+    """rows: list of tuples of ints (one tuple per digest), item_limbs: limbs reserved per item."""
+    _bind_sigma(eng.lib)
+    n = len(rows)
+    data = np.concatenate([ints_to_limbs([row[j] for row in rows], l) for j, l in enumerate(item_limbs)], axis=1)
+    data = np.ascontiguousarray(data)
+    il = (ctypes.c_int * len(item_limbs))(*item_limbs)
+    out = np.zeros((n, 8), dtype=np.uint32)
+    eng._ck(eng.lib.tecdsa_sha256_bigints_batch(eng._ctx, _ptr(data), il, len(item_limbs), _ptr(out), n, HOST), "sha256_bigints")
+    return limbs_to_ints(out)
+
+
+def hash_commitment(eng, points, blinds):
+    _bind_sigma(eng.lib)
+    P, B = _pts(points), ints_to_limbs(blinds, 8)
+    out = np.zeros((len(blinds), 8), dtype=np.uint32)
+    eng._ck(eng.lib.tecdsa_hash_commitment_batch(eng._ctx, _ptr(P), _ptr(B), _ptr(out), len(blinds), HOST), "hash_commitment")
+    return limbs_to_ints(out)

@@ -196,3 +196,50 @@ def test_bob_proofs_batch(engine, pkg, keyset, check):
         st2 = gg20.bob_proof_verify(engine, ks, ek_row, st_row, cols["a_enc"], cols["mta"], pf, Xbad, pf["u"])
         assert st2[2] in (pkg.ST_HASH_MISMATCH, pkg.ST_PROOF) and not st2[3:].any()
     ks.free()
+
+
+def test_sigma_proofs_and_hashes_batch(engine, pkg):
+    """curv's DLogProof / PedersenProof / HomoELGamalProof / HashCommitment / chain_bigint as stand-alone batches,
+    byte-identical to the oracle; tampered proofs rejected."""
+    from mpecdsa_b200 import gg20
+    rng = Drbg(21, "sigma-batch")
+    n = 20
+    sk, nonce = [rng.scalar() for _ in range(n)], [rng.scalar() for _ in range(n)]
+    pf = gg20.dlog_prove(engine, sk, nonce)
+    for i in range(n):
+        w = o.dlog_prove(sk[i], nonce[i])
+        got = pkg.limbs_to_ints(pf[i:i + 1, :16])[0], pkg.limbs_to_ints(pf[i:i + 1, 16:32])[0], pkg.limbs_to_ints(pf[i:i + 1, 32:])[0]
+        assert got == (gg20.pack_point(w.pk), gg20.pack_point(w.pk_t_rand_commitment), w.challenge_response)
+    assert not gg20.dlog_verify(engine, pf).any()
+    bad = pf.copy(); bad[0, 32] ^= 1; bad[1, 0] ^= 1
+    st = gg20.dlog_verify(engine, bad)
+    assert st[0] == pkg.ST_PROOF and st[1] == pkg.ST_PROOF and not st[2:].any()
+    # Pedersen
+    m, r, s1, s2 = ([rng.scalar() for _ in range(n)] for _ in range(4))
+    com, ped = gg20.pedersen_prove(engine, m, r, s1, s2)
+    for i in range(n):
+        w = o.pedersen_prove(m[i], r[i], s1[i], s2[i])
+        assert gg20.unpack_point(pkg.limbs_to_ints(com[i:i + 1])[0]) == w.com
+        assert pkg.limbs_to_ints(ped[i:i + 1, :8])[0] == w.e and pkg.limbs_to_ints(ped[i:i + 1, 40:48])[0] == w.z1 and pkg.limbs_to_ints(ped[i:i + 1, 48:56])[0] == w.z2
+    assert not gg20.pedersen_verify(engine, com, ped).any()
+    ped_bad = ped.copy(); ped_bad[2, 40] ^= 1
+    assert gg20.pedersen_verify(engine, com, ped_bad)[2] == pkg.ST_PROOF
+    # HomoElGamal on the statement shape of phase 6 (party_i.rs:778-799)
+    R = [o.pt_mul(o.G, rng.scalar()) for _ in range(n)]
+    l, sigma = [rng.scalar() for _ in range(n)], [rng.scalar() for _ in range(n)]
+    T = [o.pt_add(o.pt_mul(o.G, s), o.pt_mul(o.H2, x)) for s, x in zip(sigma, l)]
+    S = [o.pt_mul(Rp, s) for Rp, s in zip(R, sigma)]
+    a, b = [rng.scalar() for _ in range(n)], [rng.scalar() for _ in range(n)]
+    heg = gg20.heg_prove(engine, R, T, S, l, sigma, a, b)
+    for i in range(n):
+        w = o.heg_prove(l[i], sigma[i], R[i], o.H2, o.G, T[i], S[i], a[i], b[i])
+        assert (gg20.unpack_point(pkg.limbs_to_ints(heg[i:i + 1, :16])[0]), gg20.unpack_point(pkg.limbs_to_ints(heg[i:i + 1, 16:32])[0]),
+                pkg.limbs_to_ints(heg[i:i + 1, 32:40])[0], pkg.limbs_to_ints(heg[i:i + 1, 40:48])[0]) == (w.T, w.A3, w.z1, w.z2)
+    assert not gg20.heg_verify(engine, R, T, S, heg).any()
+    S_bad = list(S); S_bad[3] = o.pt_add(S[3], o.G)
+    assert gg20.heg_verify(engine, R, T, S_bad, heg)[3] == pkg.ST_PROOF
+    # hashes
+    rows = [(rng.bits(2048), rng.bits(4096) >> (8 * (i % 5)), rng.bits(250), 0 if i == 0 else rng.bits(64)) for i in range(n)]
+    assert gg20.sha256_bigints(engine, rows, [64, 128, 8, 4]) == [o.sha256_bigints(list(row)) for row in rows]
+    blinds = [rng.bits(256) >> (i * 7) for i in range(n)]
+    assert gg20.hash_commitment(engine, R, blinds) == [o.hash_commitment(o.bn_from_bytes(o.pt_compress(p)), bl) for p, bl in zip(R, blinds)]
