@@ -311,11 +311,12 @@ static int job_prepare(tecdsa_ctx* c, size_t table_bytes, const void* desc, size
 }
 
 int tecdsa_ctx::launch_exp(const ExpLaunch& l, int K) {
-    JobGeom g = K == 64 ? job_geom<64, TPI_2048>(sm_count) : job_geom<128, TPI_4096>(sm_count);
+    JobGeom g = K == 32 ? job_geom<32, TPI_1024>(sm_count) : K == 64 ? job_geom<64, TPI_2048>(sm_count) : job_geom<128, TPI_4096>(sm_count);
     char* d_desc; unsigned int* d_counter; uint32_t* d_tables;
     int rc = job_prepare(this, g.table_bytes, &l, sizeof(ExpLaunch), &d_desc, &d_counter, &d_tables);
     if (rc) return rc;
-    if (K == 64) exp_jobs_kernel<64, TPI_2048><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
+    if (K == 32) exp_jobs_kernel<32, TPI_1024><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
+    else if (K == 64) exp_jobs_kernel<64, TPI_2048><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
     else exp_jobs_kernel<128, TPI_4096><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
     count_launch();
     CK(cudaGetLastError());

@@ -11,6 +11,7 @@ namespace tecdsa {
 struct ExpLaunch;
 struct InvLaunch;
 // lane-group widths of the job-list kernels (16 limbs per lane for both modulus widths)
+constexpr int TPI_1024 = 4;     // 8 limbs per lane
 constexpr int TPI_2048 = 4;
 constexpr int TPI_4096 = 8;
 }  // namespace tecdsa

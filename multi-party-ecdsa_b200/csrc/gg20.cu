@@ -20,7 +20,7 @@ struct Builder {
     const tecdsa_keyset* ks;
     Arena A;
     int U;
-    ExpLaunch L64, L128;
+    ExpLaunch L32, L64, L128;
     InvLaunch I64, I128;
 
     Operand fld(int f, int limbs = 0) const {
@@ -54,12 +54,20 @@ struct Builder {
         ExpClass& k = l.cls[l.n_classes - 1];
         k.fb = ks->fb; k.fb_row = Operand{nullptr, rows, 0, 1, 0}; k.fb_sel[0] = 1; k.fb_sel[1] = 0;
     }
-    // own-key power base^N mod N^2 through its CRT halves mod p^2 and q^2 (the unit knows its own p, q); slot s
-    // writes YP[s], YQ[s]; gg20_crt recombines them into XC[s]  (declared shortcut: identical value)
-    void crt_halves(ExpLaunch& l, int gpw, const uint32_t* rows, int slot, Operand base) {
+    // own-key power base^N mod N^2 (the unit knows its own p, q), slot s, in three stages (declared shortcut: identical
+    // value): b^(pq) mod p^2 == ((b mod p)^(q mod (p-1)) mod p)^p mod p^2 because x^p mod p^2 depends only on x mod p.
+    //   1. 1024-bit job list:  TP[s] = (b mod p)^(q mod (p-1)) mod p,   TQ[s] likewise          (crt_stage1)
+    //   2. 2048-bit job list:  YP[s] = TP[s]^p mod p^2,  YQ[s] = TQ[s]^q mod q^2                (crt_stage2)
+    //   3. gg20_crt recombines YP, YQ into XC[s] in [0, N^2)
+    void crt_stage1(ExpLaunch& l32, int gpw32, const uint32_t* rows, int slot, Operand base64) {
         const Operand none = {nullptr, nullptr, 0, 0, 0};
-        exp_class(l, gpw, key(KT_PP, rows), 1, base, key(KT_N, rows), 64, none, none, 0, 0, none, none, F_YP0 + slot);
-        exp_class(l, gpw, key(KT_QQ, rows), 1, base, key(KT_N, rows), 64, none, none, 0, 0, none, none, F_YQ0 + slot);
+        exp_class(l32, gpw32, key(KT_P, rows), 1, base64, key(KT_QMODPM1, rows), 32, none, none, 0, 0, none, none, F_TP0 + slot, 1);
+        exp_class(l32, gpw32, key(KT_Q, rows), 1, base64, key(KT_PMODQM1, rows), 32, none, none, 0, 0, none, none, F_TQ0 + slot, 1);
+    }
+    void crt_stage2(ExpLaunch& l64, int gpw64, const uint32_t* rows, int slot) {
+        const Operand none = {nullptr, nullptr, 0, 0, 0};
+        exp_class(l64, gpw64, key(KT_PP, rows), 1, fld(F_TP0 + slot, 32), key(KT_P, rows), 32, none, none, 0, 0, none, none, F_YP0 + slot);
+        exp_class(l64, gpw64, key(KT_QQ, rows), 1, fld(F_TQ0 + slot, 32), key(KT_Q, rows), 32, none, none, 0, 0, none, none, F_YQ0 + slot);
     }
     void inv_class(InvLaunch& l, int gpw, Operand mod, Operand in, int out_field, int flag_byte) {
         InvClass& k = l.cls[l.n_classes++];
@@ -71,7 +79,7 @@ struct Builder {
 };
 
 const Operand NONE = {nullptr, nullptr, 0, 0, 0};
-constexpr int GPW64 = 32 / TPI_2048, GPW128 = 32 / TPI_4096;
+constexpr int GPW32 = 32 / TPI_1024, GPW64 = 32 / TPI_2048, GPW128 = 32 / TPI_4096;
 
 template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A, int per_unit = 1) {
     int grid = (A.U * per_unit + 63) / 64;
@@ -236,9 +244,9 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     const int launches0 = (int)c->launches;
     CK(cudaEventRecord(c->ev0, c->stream));
 
-    ExpLaunch &L64 = B.L64, &L128 = B.L128;
+    ExpLaunch &L32 = B.L32, &L64 = B.L64, &L128 = B.L128;
     InvLaunch &I64 = B.I64, &I128 = B.I128;
-    Builder::reset(L64); Builder::reset(L128); Builder::reset(I64); Builder::reset(I128);
+    Builder::reset(L32); Builder::reset(L64); Builder::reset(L128); Builder::reset(I64); Builder::reset(I128);
     const uint32_t *ro = A.row_own, *rp = A.row_peer;
     auto st_rows = [&](int x) { return A.row_st + (size_t)x * U; };
 #define RUN(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
@@ -247,10 +255,13 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     RUN(glue(c, gg20_r0_pre, A));
     // c_k = (1 + k N) * r_k^N mod N^2 (mta/mod.rs:68-75) and u = (alpha N + 1) * beta^N mod N^2 (range_proofs.rs:53-55):
     // the N-th powers are under the unit's OWN key, so they run as CRT halves mod p^2 / q^2 (2048-bit)
-    B.crt_halves(L64, GPW64, ro, 0, B.rnd(RND_RK, 64));
+    B.crt_stage1(L32, GPW32, ro, 0, B.rnd(RND_RK, 64));
+    for (int x = 0; x < 3; x++) B.crt_stage1(L32, GPW32, ro, 1 + x, B.rnd(RND_AL + x * RND_AL_STRIDE + RND_AL_BETA, 64));
+    RUN(run_exp(c, L32, 32));
+    B.crt_stage2(L64, GPW64, ro, 0);
     for (int x = 0; x < 3; x++) {
         const int al = RND_AL + x * RND_AL_STRIDE;
-        B.crt_halves(L64, GPW64, ro, 1 + x, B.rnd(al + RND_AL_BETA, 64));
+        B.crt_stage2(L64, GPW64, ro, 1 + x);
         // w = h1^alpha * h2^gamma mod N_tilde                           (range_proofs.rs:56-57)
         B.fb_class(L64, GPW64, st_rows(x), B.rnd(al + RND_AL_GAMMA, 88), 88, B.rnd(al + RND_AL_ALPHA, 24), 24, 0, NONE, F_WP0 + x);
         // z = h1^a * h2^ro mod N_tilde                                  (range_proofs.rs:52)
@@ -311,7 +322,9 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     B.fb_class(L64, GPW64, rp, B.rnd(RND_PDL_GAMMA, 88), 88, B.rnd(RND_PDL_ALPHA, 24), 24, 0, NONE, F_PU3);     // u3 (:93-99)
     // u2 = (N+1)^alpha * beta^N mod N^2, with (N+1)^alpha == 1 + alpha N (declared shortcut, identical value) (:86-92);
     // beta^N under the own key through CRT halves
-    B.crt_halves(L64, GPW64, ro, 4, B.rnd(RND_PDL_BETA, 64));
+    B.crt_stage1(L32, GPW32, ro, 4, B.rnd(RND_PDL_BETA, 64));
+    RUN(run_exp(c, L32, 32));
+    B.crt_stage2(L64, GPW64, ro, 4);
     RUN(run_exp(c, L64, 64));
     RUN(glue_crt(c, A, 4, 1));
     B.exp_class(L128, GPW128, B.key(KT_NN, ro), 0, NONE, NONE, 0, NONE, NONE, 0, 2, B.fld(F_PLIN), B.fld(F_XC4), F_PU2);
@@ -329,7 +342,9 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         B.exp_class(L64, GPW64, B.key(KT_NT, stmt), 1, z, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VZE0 + j);       // z^e; (z^-1)^e == (z^e)^-1 (:166-172)
         B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, ck, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VCE0 + j);  // c^e (:151-157)
     }
-    B.crt_halves(L64, GPW64, ro, 5, B.fld(F_PS2, 64));       // own proof's s2^N mod N^2_own through CRT halves
+    B.crt_stage1(L32, GPW32, ro, 5, B.fld(F_PS2, 64));       // own proof's s2^N mod N^2_own through the CRT stages
+    RUN(run_exp(c, L32, 32));
+    B.crt_stage2(L64, GPW64, ro, 5);
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
     RUN(glue_crt(c, A, 5, 1));
     for (int j = 0; j < 2; j++) {

@@ -56,7 +56,10 @@ enum : int {
     /* own-key powers b^N mod N^2 through CRT: halves mod p^2 / q^2 and the recombined value */      \
     X(YP0, 64) X(YP1, 64) X(YP2, 64) X(YP3, 64) X(YP4, 64) X(YP5, 64)                              \
     X(YQ0, 64) X(YQ1, 64) X(YQ2, 64) X(YQ3, 64) X(YQ4, 64) X(YQ5, 64)                              \
-    X(XC0, 128) X(XC1, 128) X(XC2, 128) X(XC3, 128) X(XC4, 128) X(XC5, 128)
+    X(XC0, 128) X(XC1, 128) X(XC2, 128) X(XC3, 128) X(XC4, 128) X(XC5, 128)                          \
+    /* 1024-bit stage: (b mod p)^(q mod (p-1)) mod p and the q-side twin */                          \
+    X(TP0, 32) X(TP1, 32) X(TP2, 32) X(TP3, 32) X(TP4, 32) X(TP5, 32)                              \
+    X(TQ0, 32) X(TQ1, 32) X(TQ2, 32) X(TQ3, 32) X(TQ4, 32) X(TQ5, 32)
 
 enum Field : int {
 #define X(name, size) F_##name,
@@ -89,10 +92,11 @@ enum KeyTable : int {
     KT_HPR, KT_HQR,  // 32   hp*R mod p, hq*R mod q  (R = 2^1024; hp = L_p((1-N) mod p^2)^-1 mod p)
     KT_PINVQR,       // 32   (p^-1 mod q) * R mod q
     KT_PPINVQQR,     // 64   ((p^2)^-1 mod q^2) * 2^2048 mod q^2  (CRT recombination of own-key N^2 powers)
+    KT_QMODPM1, KT_PMODQM1,   // 32   q mod (p-1), p mod (q-1): exponents of the 1024-bit stage of an own-key N-th power
     KT_XI,           // 8    x_i
     KT_PK,           // 16   X_i affine
     KT_COUNT
 };
-static const int KEY_SIZE[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 8, 16};
+static const int KEY_SIZE[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 32, 32, 8, 16};
 
 }  // namespace tecdsa

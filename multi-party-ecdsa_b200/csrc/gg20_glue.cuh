@@ -14,7 +14,7 @@ namespace tecdsa {
 
 using namespace secp;
 
-__device__ __constant__ const int KEY_SIZE_D[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 8, 16};
+__device__ __constant__ const int KEY_SIZE_D[KT_COUNT] = {64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 32, 32, 8, 16};
 // q^3 (24 limbs): the verifier's range bound `s1 > q^3 => reject` (utilities/mta/range_proofs.rs:118)
 __device__ __constant__ const uint32_t Q3_LIMBS[24] = {
     0x857B73C1u, 0xEB6926B7u, 0xE1E11B11u, 0x3552090Fu, 0x7A1CF066u, 0xD9EF0F38u, 0x02D99574u, 0x46385C85u,
@@ -506,6 +506,8 @@ static __global__ void gg20_key_setup(uint32_t* const* tables, int rows) {
     uint32_t one[32]; st::zero(one, 32); one[0] = 1;
     st::sub(T(KT_PM1), p, one, 32);
     st::sub(T(KT_QM1), q, one, 32);
+    st::mod_slow(T(KT_QMODPM1), q, 32, T(KT_PM1), 32);
+    st::mod_slow(T(KT_PMODQM1), p, 32, T(KT_QM1), 32);
     uint32_t scratch[65], t1[32], t2[32], rr[32], x[32], acc[32];
     for (int half = 0; half < 2; half++) {
         const uint32_t* m = half ? q : p;        // modulus

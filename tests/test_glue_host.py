@@ -15,7 +15,7 @@ from oracle import gg20_oracle as o
 from oracle.sampling import Drbg
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness")
-KEY_SIZE = [64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 8, 16]
+KEY_SIZE = [64, 128, 64, 64, 64, 64, 64, 32, 32, 32, 32, 32, 32, 32, 32, 32, 64, 32, 32, 8, 16]
 
 
 @pytest.fixture(scope="module")
@@ -146,6 +146,9 @@ def test_key_setup_and_decrypt_tail(h, keyset):
         assert I(tabs[15][r]) == pow(p, -1, q) * R % q
         R64 = 1 << 2048
         assert I(tabs[16][r]) == pow(p * p, -1, q * q) * R64 % (q * q)
+        assert I(tabs[17][r]) == q % (p - 1) and I(tabs[18][r]) == p % (q - 1)
+        b = rng.randrange(1, p * q)          # the identity behind the 1024-bit stage
+        assert pow(pow(b % p, q % (p - 1), p), p, p * p) == pow(b, p * q, p * p)
         for _ in range(2):          # CRT recombination of an own-key power b^N mod N^2
             b = rng.randrange(1, p * q)
             yp, yq = pow(b, p * q, p * p), pow(b, p * q, q * q)
