@@ -282,16 +282,18 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     // ================= Round 1 (rounds.rs:122-206): 2 x MessageB::b — the three AliceProof::verify
     // of the peer's MessageA are computed ONCE and used for both calls (declared de-duplication).
     RUN(glue(c, gg20_r1_pre, A));
+    // (c^e)^-1 mod N^2 is evaluated as (c^-1)^e (the reference does the same in commitment_unknown_order,
+    // zk_pdl_with_slack/mod.rs:191-193): ONE inversion of the peer's ciphertext serves the three proofs here and the
+    // peer's PDL proof in round 5 (declared shortcut, identical value)
+    B.inv_class(I128, GPW128, B.key(KT_NN, rp), B.peer(F_CK), F_CINVP, 3);
+    RUN(run_inv(c, I128, 128));
     for (int x = 0; x < 3; x++) {
         B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 1, B.peer(F_Z0 + x), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_ZE0 + x);   // z^e (:122)
-        B.exp_class(L128, GPW128, B.key(KT_NN, rp), 1, B.peer(F_CK), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_CE0 + x);              // c^e (:135)
+        B.exp_class(L128, GPW128, B.key(KT_NN, rp), 1, B.fld(F_CINVP), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_CEI0 + x);           // (c^-1)^e (:135)
     }
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
-    for (int x = 0; x < 3; x++) {
-        B.inv_class(I64, GPW64, B.key(KT_NT, st_rows(x)), B.fld(F_ZE0 + x), F_ZEI0 + x, x);
-        B.inv_class(I128, GPW128, B.key(KT_NN, rp), B.fld(F_CE0 + x), F_CEI0 + x, 3 + x);
-    }
-    RUN(run_inv(c, I128, 128)); RUN(run_inv(c, I64, 64));
+    for (int x = 0; x < 3; x++) B.inv_class(I64, GPW64, B.key(KT_NT, st_rows(x)), B.fld(F_ZE0 + x), F_ZEI0 + x, x);
+    RUN(run_inv(c, I64, 64));
     for (int x = 0; x < 3; x++) {
         // w' = h1^s1 * h2^s2 * (z^e)^-1 mod N_tilde                     (range_proofs.rs:129-132)
         B.fb_class(L64, GPW64, st_rows(x), B.peer(F_S20 + x), 92, B.peer(F_S10 + x), 28, 1, B.fld(F_ZEI0 + x), F_WV0 + x);
@@ -335,23 +337,22 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
 
     // ================= Round 5 (rounds.rs:525-592): verify both signers' PDL proofs (own one included)
     RUN(glue(c, gg20_r5_pre, A));
+    B.inv_class(I128, GPW128, B.key(KT_NN, ro), B.fld(F_CK), F_CINVO, 8);          // own ciphertext (proof j = 0); the peer's inverse is CINVP
+    RUN(run_inv(c, I128, 128));
     for (int j = 0; j < 2; j++) {
         const uint32_t* prover = j ? rp : ro;            // key row of the prover
         const uint32_t* stmt = j ? ro : rp;              // whose (N_tilde, h1, h2) the proof was made against
-        Operand z = j ? B.peer(F_PZ) : B.fld(F_PZ), ck = j ? B.peer(F_CK) : B.fld(F_CK);
+        Operand z = j ? B.peer(F_PZ) : B.fld(F_PZ);
         B.exp_class(L64, GPW64, B.key(KT_NT, stmt), 1, z, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VZE0 + j);       // z^e; (z^-1)^e == (z^e)^-1 (:166-172)
-        B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, ck, B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VCE0 + j);  // c^e (:151-157)
+        B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, B.fld(j ? F_CINVP : F_CINVO), B.fld(F_VE0 + j), 8, NONE, NONE, 0, 0, NONE, NONE, F_VCEI0 + j);  // (c^-1)^e (:151-157)
     }
     B.crt_stage1(L32, GPW32, ro, 5, B.fld(F_PS2, 64));       // own proof's s2^N mod N^2_own through the CRT stages
     RUN(run_exp(c, L32, 32));
     B.crt_stage2(L64, GPW64, ro, 5);
     RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
     RUN(glue_crt(c, A, 5, 1));
-    for (int j = 0; j < 2; j++) {
-        B.inv_class(I64, GPW64, B.key(KT_NT, j ? ro : rp), B.fld(F_VZE0 + j), F_VZEI0 + j, 6 + j);
-        B.inv_class(I128, GPW128, B.key(KT_NN, j ? rp : ro), B.fld(F_VCE0 + j), F_VCEI0 + j, 8 + j);
-    }
-    RUN(run_inv(c, I128, 128)); RUN(run_inv(c, I64, 64));
+    for (int j = 0; j < 2; j++) B.inv_class(I64, GPW64, B.key(KT_NT, j ? ro : rp), B.fld(F_VZE0 + j), F_VZEI0 + j, 6 + j);
+    RUN(run_inv(c, I64, 64));
     for (int j = 0; j < 2; j++) {
         const uint32_t* prover = j ? rp : ro;
         const uint32_t* stmt = j ? ro : rp;

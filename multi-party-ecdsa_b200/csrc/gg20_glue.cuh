@@ -39,7 +39,7 @@ struct Arena {
     __device__ __forceinline__ uint8_t* flags(int u) const { return reinterpret_cast<uint8_t*>(p(F_FLAGS, u)); }
     __device__ __forceinline__ void fail(int u, uint8_t code) const { if (status[u] == 0) status[u] = code; }
 };
-// FLAGS bytes: 0..2 ZEI ok, 3..5 CEI ok, 6..7 VZEI ok, 8..9 VCEI ok, 10 range bits, 11..12 MessageB checks ok,
+// FLAGS bytes: 0..2 ZEI ok, 3 peer ciphertext invertible, 6..7 VZEI ok, 8 own ciphertext invertible, 10 range bits, 11..12 MessageB checks ok,
 // 13 g_w_vec ok, 14..15 Pedersen ok, 16..17 PDL ok, 18..19 HomoElGamal ok, 20..22 AliceProof challenge ok
 
 // ------------------------------------------------------------------------------ small helpers
@@ -265,7 +265,7 @@ static __global__ void gg20_r2_finish(Arena A) {
     const uint32_t* rnd = A.p(F_RND, u);
     const uint8_t* fl = A.flags(u);
     bool ok1 = fl[10] == 0;
-    for (int x = 0; x < 3; x++) ok1 = ok1 && fl[x] && fl[3 + x] && fl[20 + x];
+    for (int x = 0; x < 3; x++) ok1 = ok1 && fl[x] && fl[3] && fl[20 + x];      // fl[3]: the peer's ciphertext is invertible mod N^2
     if (!ok1) A.fail(u, TECDSA_ST_INVALID_KEY);                    // MessageB::b -> Err(InvalidKey) (mta/mod.rs:123-131)
     if (!(fl[11] && fl[12] && fl[13])) A.fail(u, TECDSA_ST_INVALID_KEY);
     const U256 k = load_scalar(rnd + RND_K), gamma = load_scalar(rnd + RND_GAMMA), w = u256_load(A.p(F_W, u));
@@ -391,7 +391,7 @@ static __global__ void gg20_r5_check(Arena A) {
     U256 e = sc_from_limbs(A.p(F_VE0 + j, u), 8);
     U256 s1 = sc_from_limbs(A.p(F_PS1, src), 28);
     Affine u1t = lin2(R, s1, affine_load(A.p(F_RD, src)), sc_neg(e));
-    bool ok = fl[6 + j] && fl[8 + j];
+    bool ok = fl[6 + j] && (j ? fl[3] : fl[8]);       // z and the prover's ciphertext invertible
     ok = ok && affine_eq(u1t, affine_load(A.p(F_PU1, src)));
     ok = ok && st::cmp(A.p(F_VU20 + j, u), A.p(F_PU2, src), 128) == 0;
     ok = ok && st::cmp(A.p(F_VU30 + j, u), A.p(F_PU3, src), 64) == 0;

@@ -9,6 +9,9 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#ifdef __CUDACC__
+#include "bigint.cuh"      // IMAD.WIDE carry-chain helpers (mad_even / madc_odd_rshift)
+#endif
 
 namespace tecdsa {
 namespace secp {
@@ -54,12 +57,35 @@ __device__ __forceinline__ uint32_t u256_sub(U256& r, const U256& a, const uint3
     for (int i = 0; i < 8; i++) { c += (int64_t)a.v[i] - b[i]; r.v[i] = (uint32_t)c; c >>= 32; }
     return (uint32_t)(c & 1);
 }
-// 8x8 -> 16 limbs, product scanning with a 96-bit column accumulator
+// 8x8 -> 16 limbs.  Device: operand scanning on the even/odd accumulator sets of bigint.cuh, one
+// IMAD.WIDE.U32(.X) per 32x32 product (64 per call).  Host (tests/host_harness only): portable
+// product scanning with a 96-bit column accumulator.
 __device__ __forceinline__ void mul_256(uint32_t (&t)[16], const U256& a, const U256& b) {
+#ifdef __CUDA_ARCH__
+    uint32_t E[10], O[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) { E[j] = 0; O[j] = 0; }
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        // row i: E is the even set, O the previous even set turning into the odd set
+        E[0] = tecdsa::add_cc(E[0], O[1]);
+        tecdsa::madc_odd_rshift<8>(O, a.v, b.v[i]);
+        tecdsa::mad_even<8>(E, a.v, b.v[i]);
+        t[i] = E[0];
+        // row i+1: roles swapped
+        O[0] = tecdsa::add_cc(O[0], E[1]);
+        tecdsa::madc_odd_rshift<8>(E, a.v, b.v[i + 1]);
+        tecdsa::mad_even<8>(O, a.v, b.v[i + 1]);
+        t[i + 1] = O[0];
+    }
+    // O: even set with column 0 consumed; E: odd set
+    t[8] = tecdsa::add_cc(O[1], E[0]);
+#pragma unroll
+    for (int j = 1; j < 8; j++) t[8 + j] = tecdsa::addc_cc(O[j + 1], E[j]);
+    (void)tecdsa::addc(0, 0);
+#else
     uint64_t acc = 0; uint32_t hi = 0;
-#pragma unroll
     for (int k = 0; k < 15; k++) {
-#pragma unroll
         for (int i = 0; i < 8; i++) {
             int j = k - i;
             if (j < 0 || j > 7) continue;
@@ -72,6 +98,7 @@ __device__ __forceinline__ void mul_256(uint32_t (&t)[16], const U256& a, const 
         hi = 0;
     }
     t[15] = (uint32_t)acc;
+#endif
 }
 
 // ------------------------------------------------------------------------------- field Fp

@@ -84,7 +84,7 @@ for p in range(2):
     exp[p]["R"] = pt(want[p].R); exp[p]["SIGMA"] = want[p].sigma_i
     exp[p]["DIGEST"] = int.from_bytes(want[p].transcript, "big")
 order = ["W", "GG", "COM", "MK", "ALIN0", "CK", "U0", "U1", "U2", "Z0", "Z1", "Z2", "WP0", "WP1", "WP2", "E0", "E1", "E2",
-         "S10", "S20", "S0", "S1", "S2", "GS10", "ZE0", "CE0", "ZEI0", "CEI0", "ZEI1", "CEI1", "ZEI2", "CEI2", "WV0", "UV0", "WV1", "UV1", "WV2", "UV2",
+         "S10", "S20", "S0", "S1", "S2", "GS10", "ZE0", "ZEI0", "CEI0", "ZEI1", "CEI1", "ZEI2", "CEI2", "WV0", "UV0", "WV1", "UV1", "WV2", "UV2",
          "LBG", "CBG", "CBW", "BETA_G", "NU", "DL0", "DL1", "DL2", "DL3", "DPG", "DQG", "DPW", "DQW", "ALPHA", "MU", "DELTA", "SIGMA", "T", "R", "DIGEST"]
 bad = 0
 for name in order:
