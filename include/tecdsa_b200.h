@@ -153,6 +153,28 @@ int tecdsa_bob_proof_verify_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, cons
                                   const uint32_t* s1, const uint32_t* s2, const uint32_t* t1, const uint32_t* t2, const uint32_t* X,
                                   const uint32_t* u, uint8_t* status, size_t count, int mem);
 
+/* ---- L2: the MtA share conversion messages (src/utilities/mta/mod.rs:52-179) ----------------------------------
+ * message_a = `MessageA::a_with_predefined_randomness`: c = Enc(ek_row; a, r) and one AliceProof per statement;
+ *   per-proof arrays are indexed [instance][statement] (n_st statements per instance, st_rows gives their key rows;
+ *   n_st = 0 is the "no range proofs" form used by GG18 / blame).
+ * message_b = `MessageB::b_with_predefined_randomness`: verifies every range proof of MessageA (any failure ->
+ *   status TECDSA_ST_INVALID_KEY, like Err(InvalidKey)), c_b = c_a^b * Enc(beta'; r') mod N^2, beta = -beta' mod q,
+ *   and the DLogProofs of b and beta' (40 limbs each, layout as tecdsa_dlog_prove_batch).
+ * get_alpha = `MessageB::verify_proofs_get_alpha`: alpha' = Dec(dk_row; c_b) (64 limbs, optional output),
+ *   alpha = alpha' mod q, status OK iff both DLogProofs verify and G*alpha == B*a + B'.                            */
+int tecdsa_mta_message_a_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_rows, int n_st,
+                               const uint32_t* a, const uint32_t* r, const uint32_t* alpha, const uint32_t* beta, const uint32_t* gamma,
+                               const uint32_t* rho, uint32_t* c, uint32_t* z, uint32_t* e, uint32_t* s, uint32_t* s1, uint32_t* s2,
+                               size_t count, int mem);
+int tecdsa_mta_message_b_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_rows, int n_st,
+                               const uint32_t* b, const uint32_t* c_a, const uint32_t* z, const uint32_t* e, const uint32_t* s,
+                               const uint32_t* s1, const uint32_t* s2, const uint32_t* randomness, const uint32_t* beta_tag,
+                               const uint32_t* nonce_b, const uint32_t* nonce_beta, uint32_t* c_b, uint32_t* b_proof,
+                               uint32_t* beta_tag_proof, uint32_t* beta, uint8_t* status, size_t count, int mem);
+int tecdsa_mta_get_alpha_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* dk_row, const uint32_t* a, const uint32_t* c_b,
+                               const uint32_t* b_proof, const uint32_t* beta_tag_proof, uint32_t* alpha, uint32_t* alpha_plain,
+                               uint8_t* status, size_t count, int mem);
+
 /* ---- curv-kzen sigma proofs and hashes used by the protocol (out-of-tree crate; call sites cited) ----------------
  * Scalars are 8 limbs (reduced mod q on entry), points affine x||y 16 limbs.  Verifiers write TECDSA_ST_OK or
  * TECDSA_ST_PROOF.  Encodings [R]: challenges hash 65-byte uncompressed points and reduce the digest mod q.

@@ -367,6 +367,45 @@ __global__ void k_hash_commit(const uint32_t* P16, const uint32_t* blind8, uint3
     hash_commit_point(out8 + (size_t)i * 8, affine_load(P16 + (size_t)i * 16), blind8 + (size_t)i * 8);
 }
 
+
+// ---- MtA messages (utilities/mta/mod.rs:52-179) --------------------------------------------------------
+// replicate per-instance rows for a flat (instance, statement) proof batch: dst[i*n_st + x] = src[i]
+__global__ void k_expand(uint32_t* dst, const uint32_t* src, int limbs, int n_st, int count) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * n_st) return;
+    const uint32_t* p = src + (size_t)(t / n_st) * limbs;
+    uint32_t* d = dst + (size_t)t * limbs;
+    for (int j = 0; j < limbs; j++) d[j] = p[j];
+}
+// MessageB::b tail: any rejected proof -> InvalidKey; beta = -beta' mod q; the two DLogProofs (mod.rs:123-148)
+__global__ void k_mta_b_post(const uint8_t* proof_status, int n_st, const uint32_t* b, const uint32_t* beta_tag, const uint32_t* nonce_b,
+                             const uint32_t* nonce_beta, uint32_t* beta_out, uint32_t* b_proof, uint32_t* bt_proof, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    bool ok = true;
+    for (int x = 0; x < n_st; x++) ok = ok && proof_status[(size_t)i * n_st + x] == TECDSA_ST_OK;
+    status[i] = ok ? TECDSA_ST_OK : TECDSA_ST_INVALID_KEY;
+    U256 bt = sc_from_limbs(beta_tag + (size_t)i * 64, 64);
+    u256_store(beta_out + (size_t)i * 8, sc_neg(bt));
+    dlog_prove(b_proof + (size_t)i * 40, sc_from_limbs(b + (size_t)i * 8, 8), sc_from_limbs(nonce_b + (size_t)i * 8, 8));
+    dlog_prove(bt_proof + (size_t)i * 40, bt, sc_from_limbs(nonce_beta + (size_t)i * 8, 8));
+}
+// MessageB::verify_proofs_get_alpha tail (mod.rs:165-178)
+__global__ void k_mta_alpha(Arena A, const uint32_t* rows, const uint32_t* dp, const uint32_t* dq, const uint32_t* a, const uint32_t* b_proof,
+                            const uint32_t* bt_proof, uint32_t* plain, uint32_t* alpha_out, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t* pl = plain + (size_t)i * 64;
+    decrypt_finish(pl, A, rows[i], dp + (size_t)i * 64, dq + (size_t)i * 64);
+    U256 alpha = sc_from_limbs(pl, 64);
+    u256_store(alpha_out + (size_t)i * 8, alpha);
+    const uint32_t *bp = b_proof + (size_t)i * 40, *btp = bt_proof + (size_t)i * 40;
+    Affine g_alpha = mul_G(alpha);
+    Affine ba_btag = jac_to_affine(jac_add(jac_mul(jac_from_affine(affine_load(bp)), sc_from_limbs(a + (size_t)i * 8, 8)), jac_from_affine(affine_load(btp))));
+    const bool v1 = dlog_verify(bp), v2 = dlog_verify(btp);
+    status[i] = (v1 && v2 && affine_eq(ba_btag, g_alpha)) ? TECDSA_ST_OK : TECDSA_ST_INVALID_KEY;
+}
+
 Arena key_arena(const tecdsa_keyset* ks) {
     Arena A;
     memset(&A, 0, sizeof(A));
@@ -522,6 +561,30 @@ extern "C" int tecdsa_paillier_decrypt_batch(tecdsa_ctx* c, const tecdsa_keyset*
 }
 
 // ------------------------------------------------------------------------------------------ L2: MtA range proof (Alice)
+// AliceProof::generate on device-resident arrays (shared by the L2 entry point and tecdsa_mta_message_a_batch)
+static int alice_generate_dev(tecdsa_ctx* c, Stage& S, const tecdsa_keyset* ks, int n, const uint32_t* er, const uint32_t* sr, const uint32_t* da,
+                              const uint32_t* dc, const uint32_t* dr, const uint32_t* dal, const uint32_t* dbe, const uint32_t* dga, const uint32_t* dro,
+                              uint32_t* dz, uint32_t* de, uint32_t* ds, uint32_t* ds1, uint32_t* ds2) {
+    const size_t count = (size_t)n;
+    uint32_t *lin = S.tmp<uint32_t>(count * 128), *u = S.tmp<uint32_t>(count * 128), *w = S.tmp<uint32_t>(count * 64);
+    if (S.err) return S.err;
+    Arena A = key_arena(ks);
+    k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dal, 24, ks->tab[KT_N], er, n);
+    c->count_launch();
+    Launches L;
+    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, u, 128);  // u (:53-55)
+    add_fb(L.e64, n, ks, sr, arr(dga, 88), 88, arr(dal, 24), 24, 0, NONE, w);       // w = h1^alpha h2^gamma (:56-57)
+    add_fb(L.e64, n, ks, sr, arr(dro, 72), 72, arr(da, 8), 8, 0, NONE, dz);         // z = h1^a h2^ro       (:52)
+    int rc = run(c, L.e128, 128); if (rc) return rc;
+    rc = run(c, L.e64, 64); if (rc) return rc;
+    k_alice_mid<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, da, dal, dga, dro, de, ds1, ds2, n);
+    c->count_launch();
+    add_exp(L.e64, 64, n, tab(ks->tab[KT_N], er, 64), 1, arr(dr, 64), arr(de, 8), 8, NONE, NONE, 0, 1, arr(dbe, 64), NONE, ds, 64);   // s = r^e beta mod N (:86)
+    rc = run(c, L.e64, 64); if (rc) return rc;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "alice_generate", e);
+}
+
 extern "C" int tecdsa_alice_proof_generate_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row,
                                                  const uint32_t* a, const uint32_t* cipher, const uint32_t* r, const uint32_t* alpha,
                                                  const uint32_t* beta, const uint32_t* gamma, const uint32_t* rho, uint32_t* z, uint32_t* e,
@@ -530,27 +593,46 @@ extern "C" int tecdsa_alice_proof_generate_batch(tecdsa_ctx* c, const tecdsa_key
         return tecdsa_fail(TECDSA_E_ARG, "alice_proof_generate: null argument");
     if (count == 0) return 0;
     CK(cudaSetDevice(c->device));
-    const int n = (int)count;
     Stage S(c, mem);
     const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *da = S.in(a, count * 8), *dc = S.in(cipher, count * 128),
                    *dr = S.in(r, count * 64), *dal = S.in(alpha, count * 24), *dbe = S.in(beta, count * 64), *dga = S.in(gamma, count * 88),
                    *dro = S.in(rho, count * 72);
     uint32_t *dz = S.out(z, count * 64), *de = S.out(e, count * 8), *ds = S.out(s, count * 64), *ds1 = S.out(s1, count * 28), *ds2 = S.out(s2, count * 92);
-    uint32_t *lin = S.tmp<uint32_t>(count * 128), *u = S.tmp<uint32_t>(count * 128), *w = S.tmp<uint32_t>(count * 64);
     if (S.err) return S.finish();
-    Arena A = key_arena(ks);
-    k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dal, 24, ks->tab[KT_N], er, n);
-    KCHECK();
-    Launches L;
-    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, u, 128);  // u (:53-55)
-    add_fb(L.e64, n, ks, sr, arr(dga, 88), 88, arr(dal, 24), 24, 0, NONE, w);       // w = h1^alpha h2^gamma (:56-57)
-    add_fb(L.e64, n, ks, sr, arr(dro, 72), 72, arr(da, 8), 8, 0, NONE, dz);         // z = h1^a h2^ro       (:52)
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
-    k_alice_mid<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, da, dal, dga, dro, de, ds1, ds2, n);
-    KCHECK();
-    add_exp(L.e64, 64, n, tab(ks->tab[KT_N], er, 64), 1, arr(dr, 64), arr(de, 8), 8, NONE, NONE, 0, 1, arr(dbe, 64), NONE, ds, 64);   // s = r^e beta mod N (:86)
-    RUN(run(c, L.e64, 64));
+    RUN(alice_generate_dev(c, S, ks, (int)count, er, sr, da, dc, dr, dal, dbe, dga, dro, dz, de, ds, ds1, ds2));
     return S.finish();
+}
+
+// AliceProof::verify on device-resident arrays (shared by the L2 entry point and tecdsa_mta_message_b_batch)
+static int alice_verify_dev(tecdsa_ctx* c, Stage& S, const tecdsa_keyset* ks, int n, const uint32_t* er, const uint32_t* sr, const uint32_t* dc,
+                            const uint32_t* dz, const uint32_t* de, const uint32_t* ds, const uint32_t* ds1, const uint32_t* ds2, uint8_t* dst) {
+    const size_t count = (size_t)n;
+    uint32_t *gs1 = S.tmp<uint32_t>(count * 128), *ze = S.tmp<uint32_t>(count * 64), *ce = S.tmp<uint32_t>(count * 128),
+             *zei = S.tmp<uint32_t>(count * 64), *cei = S.tmp<uint32_t>(count * 128), *w = S.tmp<uint32_t>(count * 64),
+             *u = S.tmp<uint32_t>(count * 128), *e2 = S.tmp<uint32_t>(count * 8);
+    uint8_t *bad = S.tmp<uint8_t>(count), *okz = S.tmp<uint8_t>(count), *okc = S.tmp<uint8_t>(count);
+    if (S.err) return S.err;
+    Arena A = key_arena(ks);
+    k_alice_vpre<<<grid_for(count), 64, 0, c->stream>>>(A, er, ds1, gs1, bad, n);
+    c->count_launch();
+    Launches L;
+    Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
+    add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);            // z^e (:122)
+    add_exp(L.e128, 128, n, NN, 1, arr(dc, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);        // c^e (:135)
+    int rc = run(c, L.e128, 128); if (rc) return rc;
+    rc = run(c, L.e64, 64); if (rc) return rc;
+    add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, okz);
+    add_inv(L.i128, 128, n, NN, arr(ce, 128), cei, okc);
+    rc = run(c, L.i128, 128); if (rc) return rc;
+    rc = run(c, L.i64, 64); if (rc) return rc;
+    add_fb(L.e64, n, ks, sr, arr(ds2, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), w);                             // w' (:129-132)
+    add_exp(L.e128, 128, n, NN, 1, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(gs1, 128), arr(cei, 128), u, 128);   // u' (:141)
+    rc = run(c, L.e128, 128); if (rc) return rc;
+    rc = run(c, L.e64, 64); if (rc) return rc;
+    k_alice_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, de, bad, okz, okc, e2, dst, n);
+    c->count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "alice_verify", e);
 }
 
 extern "C" int tecdsa_alice_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row,
@@ -560,35 +642,14 @@ extern "C" int tecdsa_alice_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyse
         return tecdsa_fail(TECDSA_E_ARG, "alice_proof_verify: null argument");
     if (count == 0) return 0;
     CK(cudaSetDevice(c->device));
-    const int n = (int)count;
     Stage S(c, mem);
     const uint32_t *er = S.in(ek_row, count), *sr = S.in(st_row, count), *dc = S.in(cipher, count * 128), *dz = S.in(z, count * 64),
                    *de = S.in(e, count * 8), *ds = S.in(s, count * 64), *ds1 = S.in(s1, count * 28), *ds2 = S.in(s2, count * 92);
     uint8_t* dst = S.out(status, count);
-    uint32_t *gs1 = S.tmp<uint32_t>(count * 128), *ze = S.tmp<uint32_t>(count * 64), *ce = S.tmp<uint32_t>(count * 128),
-             *zei = S.tmp<uint32_t>(count * 64), *cei = S.tmp<uint32_t>(count * 128), *w = S.tmp<uint32_t>(count * 64),
-             *u = S.tmp<uint32_t>(count * 128), *e2 = S.tmp<uint32_t>(count * 8);
-    uint8_t *bad = S.tmp<uint8_t>(count), *okz = S.tmp<uint8_t>(count), *okc = S.tmp<uint8_t>(count);
     if (S.err) return S.finish();
-    Arena A = key_arena(ks);
-    k_alice_vpre<<<grid_for(count), 64, 0, c->stream>>>(A, er, ds1, gs1, bad, n);
-    KCHECK();
-    Launches L;
-    Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
-    add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);            // z^e (:122)
-    add_exp(L.e128, 128, n, NN, 1, arr(dc, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);        // c^e (:135)
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
-    add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, okz);
-    add_inv(L.i128, 128, n, NN, arr(ce, 128), cei, okc);
-    RUN(run(c, L.i128, 128)); RUN(run(c, L.i64, 64));
-    add_fb(L.e64, n, ks, sr, arr(ds2, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), w);                             // w' (:129-132)
-    add_exp(L.e128, 128, n, NN, 1, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(gs1, 128), arr(cei, 128), u, 128);   // u' (:141)
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
-    k_alice_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, de, bad, okz, okc, e2, dst, n);
-    KCHECK();
+    RUN(alice_verify_dev(c, S, ks, (int)count, er, sr, dc, dz, de, ds, ds1, ds2, dst));
     return S.finish();
 }
-
 
 // ------------------------------------------------------------------------------------------ L2: PDL with slack
 extern "C" int tecdsa_pdl_prove_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_row, const uint32_t* x,
@@ -837,6 +898,114 @@ extern "C" int tecdsa_hash_commitment_batch(tecdsa_ctx* c, const uint32_t* point
     uint32_t* o = S.out(com, count * 8);
     if (S.err) return S.finish();
     k_hash_commit<<<grid_for(count), 64, 0, c->stream>>>(dp, db, o, n);
+    KCHECK();
+    return S.finish();
+}
+
+
+// ------------------------------------------------------------------------------------------ L2: MtA messages
+extern "C" int tecdsa_mta_message_a_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_rows, int n_st,
+                                          const uint32_t* a, const uint32_t* r, const uint32_t* alpha, const uint32_t* beta, const uint32_t* gamma,
+                                          const uint32_t* rho, uint32_t* c_out, uint32_t* z, uint32_t* e, uint32_t* s, uint32_t* s1, uint32_t* s2,
+                                          size_t count, int mem) {
+    if (!c || !ks || !ek_row || !a || !r || !c_out || n_st < 0 || n_st > 16) return tecdsa_fail(TECDSA_E_ARG, "mta_message_a: bad argument");
+    if (n_st > 0 && (!st_rows || !alpha || !beta || !gamma || !rho || !z || !e || !s || !s1 || !s2)) return tecdsa_fail(TECDSA_E_ARG, "mta_message_a: null proof buffer");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    const size_t np = count * (size_t)n_st;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *da = S.in(a, count * 8), *dr = S.in(r, count * 64);
+    uint32_t* dc = S.out(c_out, count * 128);
+    uint32_t *a64 = S.tmp<uint32_t>(count * 64), *lin = S.tmp<uint32_t>(count * 128);
+    if (S.err) return S.finish();
+    // c = (1 + a N) r^N mod N^2   (mod.rs:68-75)
+    CK(cudaMemsetAsync(a64, 0, count * 64 * 4, c->stream));
+    CK(cudaMemcpy2DAsync(a64, 64 * 4, da, 8 * 4, 8 * 4, count, cudaMemcpyDeviceToDevice, c->stream));
+    k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, a64, 64, ks->tab[KT_N], er, n);
+    KCHECK();
+    Launches L;
+    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dr, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, dc, 128);
+    RUN(run(c, L.e128, 128));
+    if (n_st > 0) {
+        const uint32_t *sr = S.in(st_rows, np), *dal = S.in(alpha, np * 24), *dbe = S.in(beta, np * 64), *dga = S.in(gamma, np * 88), *dro = S.in(rho, np * 72);
+        uint32_t *dz = S.out(z, np * 64), *de = S.out(e, np * 8), *ds = S.out(s, np * 64), *ds1 = S.out(s1, np * 28), *ds2 = S.out(s2, np * 92);
+        uint32_t *er_f = S.tmp<uint32_t>(np), *a_f = S.tmp<uint32_t>(np * 8), *r_f = S.tmp<uint32_t>(np * 64), *c_f = S.tmp<uint32_t>(np * 128);
+        if (S.err) return S.finish();
+        const int g = grid_for(np);
+        k_expand<<<g, 64, 0, c->stream>>>(er_f, er, 1, n_st, n);
+        k_expand<<<g, 64, 0, c->stream>>>(a_f, da, 8, n_st, n);
+        k_expand<<<g, 64, 0, c->stream>>>(r_f, dr, 64, n_st, n);
+        k_expand<<<g, 64, 0, c->stream>>>(c_f, dc, 128, n_st, n);
+        KCHECK();
+        RUN(alice_generate_dev(c, S, ks, (int)np, er_f, sr, a_f, c_f, r_f, dal, dbe, dga, dro, dz, de, ds, ds1, ds2));
+    }
+    return S.finish();
+}
+
+extern "C" int tecdsa_mta_message_b_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* ek_row, const uint32_t* st_rows, int n_st,
+                                          const uint32_t* b, const uint32_t* c_a, const uint32_t* z, const uint32_t* e, const uint32_t* s,
+                                          const uint32_t* s1, const uint32_t* s2, const uint32_t* randomness, const uint32_t* beta_tag,
+                                          const uint32_t* nonce_b, const uint32_t* nonce_beta, uint32_t* c_b, uint32_t* b_proof,
+                                          uint32_t* beta_tag_proof, uint32_t* beta, uint8_t* status, size_t count, int mem) {
+    if (!c || !ks || !ek_row || !b || !c_a || !randomness || !beta_tag || !nonce_b || !nonce_beta || !c_b || !b_proof || !beta_tag_proof || !beta || !status ||
+        n_st < 0 || n_st > 16)
+        return tecdsa_fail(TECDSA_E_ARG, "mta_message_b: bad argument");
+    if (n_st > 0 && (!st_rows || !z || !e || !s || !s1 || !s2)) return tecdsa_fail(TECDSA_E_ARG, "mta_message_b: null proof buffer");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    const size_t np = count * (size_t)n_st;
+    Stage S(c, mem);
+    const uint32_t *er = S.in(ek_row, count), *db = S.in(b, count * 8), *dca = S.in(c_a, count * 128), *dr = S.in(randomness, count * 64),
+                   *dbt = S.in(beta_tag, count * 64), *dnb = S.in(nonce_b, count * 8), *dnt = S.in(nonce_beta, count * 8);
+    uint32_t *dcb = S.out(c_b, count * 128), *dbp = S.out(b_proof, count * 40), *dtp = S.out(beta_tag_proof, count * 40), *dbeta = S.out(beta, count * 8);
+    uint8_t* dst = S.out(status, count);
+    uint8_t* pst = S.tmp<uint8_t>(np ? np : 1);
+    uint32_t* lin = S.tmp<uint32_t>(count * 128);
+    if (S.err) return S.finish();
+    if (n_st > 0) {     // verify every range proof of MessageA (mod.rs:123-131)
+        const uint32_t *sr = S.in(st_rows, np), *dz = S.in(z, np * 64), *de = S.in(e, np * 8), *ds = S.in(s, np * 64), *ds1 = S.in(s1, np * 28), *ds2 = S.in(s2, np * 92);
+        uint32_t *er_f = S.tmp<uint32_t>(np), *c_f = S.tmp<uint32_t>(np * 128);
+        if (S.err) return S.finish();
+        k_expand<<<grid_for(np), 64, 0, c->stream>>>(er_f, er, 1, n_st, n);
+        k_expand<<<grid_for(np), 64, 0, c->stream>>>(c_f, dca, 128, n_st, n);
+        KCHECK();
+        RUN(alice_verify_dev(c, S, ks, (int)np, er_f, sr, c_f, dz, de, ds, ds1, ds2, pst));
+    }
+    // c_b = c_a^b * Enc(beta'; r') mod N^2   (mod.rs:133-145)
+    k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dbt, 64, ks->tab[KT_N], er, n);
+    KCHECK();
+    Launches L;
+    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 2, arr(dr, 64), tab(ks->tab[KT_N], er, 64), 64, arr(dca, 128), arr(db, 8), 8, 1, arr(lin, 128), NONE, dcb, 128);
+    RUN(run(c, L.e128, 128));
+    k_mta_b_post<<<grid_for(count), 64, 0, c->stream>>>(pst, n_st, db, dbt, dnb, dnt, dbeta, dbp, dtp, dst, n);
+    KCHECK();
+    return S.finish();
+}
+
+extern "C" int tecdsa_mta_get_alpha_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* dk_row, const uint32_t* a, const uint32_t* c_b,
+                                          const uint32_t* b_proof, const uint32_t* beta_tag_proof, uint32_t* alpha, uint32_t* alpha_plain,
+                                          uint8_t* status, size_t count, int mem) {
+    if (!c || !ks || !dk_row || !a || !c_b || !b_proof || !beta_tag_proof || !alpha || !status) return tecdsa_fail(TECDSA_E_ARG, "mta_get_alpha: null argument");
+    if (count == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int n = (int)count;
+    Stage S(c, mem);
+    const uint32_t *dr = S.in(dk_row, count), *da = S.in(a, count * 8), *dcb = S.in(c_b, count * 128), *dbp = S.in(b_proof, count * 40), *dtp = S.in(beta_tag_proof, count * 40);
+    uint32_t* dal = S.out(alpha, count * 8);
+    uint32_t* dpl = alpha_plain ? S.out(alpha_plain, count * 64) : S.tmp<uint32_t>(count * 64);
+    uint8_t* dst = S.out(status, count);
+    uint32_t *dp = S.tmp<uint32_t>(count * 64), *dq = S.tmp<uint32_t>(count * 64);
+    if (S.err) return S.finish();
+    Launches L;
+    Operand cw = arr(dcb, 128);
+    add_exp(L.e64, 64, n, tab(ks->tab[KT_PP], dr, 64), 1, cw, tab(ks->tab[KT_PM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dp, 64);
+    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
+    add_exp(L.e64, 64, n, tab(ks->tab[KT_QQ], dr, 64), 1, cw, tab(ks->tab[KT_QM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dq, 64);
+    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
+    RUN(run(c, L.e64, 64));
+    k_mta_alpha<<<grid_for(count), 64, 0, c->stream>>>(key_arena(ks), dr, dp, dq, da, dbp, dtp, dpl, dal, dst, n);
     KCHECK();
     return S.finish();
 }

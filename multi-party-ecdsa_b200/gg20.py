@@ -388,3 +388,59 @@ def hash_commitment(eng, points, blinds):
     out = np.zeros((len(blinds), 8), dtype=np.uint32)
     eng._ck(eng.lib.tecdsa_hash_commitment_batch(eng._ctx, _ptr(P), _ptr(B), _ptr(out), len(blinds), HOST), "hash_commitment")
     return limbs_to_ints(out)
+
+
+# ----------------------------------------------------------------------------- L2: MtA messages, batched
+def _bind_mta(lib):
+    if getattr(lib, "_mta_bound", False):
+        return
+    V, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.tecdsa_mta_message_a_batch.argtypes = [V, V, V, V, I] + [V] * 12 + [S, I]
+    lib.tecdsa_mta_message_b_batch.argtypes = [V, V, V, V, I] + [V] * 16 + [S, I]
+    lib.tecdsa_mta_get_alpha_batch.argtypes = [V] * 10 + [S, I]
+    lib._mta_bound = True
+
+
+def mta_message_a(eng, keys, ek_row, st_rows, a, r, proof_rand):
+    """Batched `MessageA::a_with_predefined_randomness`.  st_rows: [n][n_st] key rows; proof_rand[i][x] =
+    (alpha, beta, gamma, rho).  Returns (c list, dict of [n][n_st] int lists)."""
+    _bind_mta(eng.lib)
+    n = len(a)
+    n_st = len(st_rows[0]) if n else 0
+    flat = [pr for inst in proof_rand for pr in inst]
+    ins = [ints_to_limbs(a, 8), ints_to_limbs(r, 64)] + [ints_to_limbs([p[j] for p in flat], l) for j, l in enumerate((24, 64, 88, 72))]
+    c = np.zeros((n, 128), np.uint32)
+    outs = {k: np.zeros((n * n_st, l), np.uint32) for k, l in (("z", 64), ("e", 8), ("s", 64), ("s1", 28), ("s2", 92))}
+    er, sr = _rows(ek_row), np.ascontiguousarray(np.asarray(st_rows, dtype=np.uint32).reshape(-1))
+    eng._ck(eng.lib.tecdsa_mta_message_a_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), n_st, *[_ptr(x) for x in ins], _ptr(c),
+                                               *[_ptr(outs[k]) for k in ("z", "e", "s", "s1", "s2")], n, HOST), "mta_message_a")
+    proofs = {k: [limbs_to_ints(v)[i * n_st:(i + 1) * n_st] for i in range(n)] for k, v in outs.items()}
+    return limbs_to_ints(c), proofs
+
+
+def mta_message_b(eng, keys, ek_row, st_rows, b, c_a, proofs, randomness, beta_tag, nonce_b, nonce_beta):
+    """Batched `MessageB::b_with_predefined_randomness`; proofs as returned by mta_message_a."""
+    _bind_mta(eng.lib)
+    n = len(b)
+    n_st = len(st_rows[0]) if n else 0
+    flat = {k: [v for inst in proofs[k] for v in inst] for k in ("z", "e", "s", "s1", "s2")}
+    er, sr = _rows(ek_row), np.ascontiguousarray(np.asarray(st_rows, dtype=np.uint32).reshape(-1))
+    ins = [ints_to_limbs(b, 8), ints_to_limbs(c_a, 128), ints_to_limbs(flat["z"], 64), ints_to_limbs(flat["e"], 8), ints_to_limbs(flat["s"], 64),
+           ints_to_limbs(flat["s1"], 28), ints_to_limbs(flat["s2"], 92), ints_to_limbs(randomness, 64), ints_to_limbs(beta_tag, 64),
+           ints_to_limbs(nonce_b, 8), ints_to_limbs(nonce_beta, 8)]
+    c_b, bp, btp, beta = np.zeros((n, 128), np.uint32), np.zeros((n, 40), np.uint32), np.zeros((n, 40), np.uint32), np.zeros((n, 8), np.uint32)
+    status = np.full(n, 255, np.uint8)
+    eng._ck(eng.lib.tecdsa_mta_message_b_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), n_st, *[_ptr(x) for x in ins], _ptr(c_b), _ptr(bp), _ptr(btp),
+                                               _ptr(beta), _ptr(status), n, HOST), "mta_message_b")
+    return limbs_to_ints(c_b), bp, btp, limbs_to_ints(beta), status
+
+
+def mta_get_alpha(eng, keys, dk_row, a, c_b, b_proof, beta_tag_proof):
+    """Batched `MessageB::verify_proofs_get_alpha` -> (alpha list, alpha' list, status)."""
+    _bind_mta(eng.lib)
+    n = len(a)
+    ins = [_rows(dk_row), ints_to_limbs(a, 8), ints_to_limbs(c_b, 128), np.ascontiguousarray(b_proof), np.ascontiguousarray(beta_tag_proof)]
+    alpha, plain = np.zeros((n, 8), np.uint32), np.zeros((n, 64), np.uint32)
+    status = np.full(n, 255, np.uint8)
+    eng._ck(eng.lib.tecdsa_mta_get_alpha_batch(eng._ctx, keys.handle, *[_ptr(x) for x in ins], _ptr(alpha), _ptr(plain), _ptr(status), n, HOST), "mta_get_alpha")
+    return limbs_to_ints(alpha), limbs_to_ints(plain), status

@@ -243,3 +243,58 @@ def test_sigma_proofs_and_hashes_batch(engine, pkg):
     assert gg20.sha256_bigints(engine, rows, [64, 128, 8, 4]) == [o.sha256_bigints(list(row)) for row in rows]
     blinds = [rng.bits(256) >> (i * 7) for i in range(n)]
     assert gg20.hash_commitment(engine, R, blinds) == [o.hash_commitment(o.bn_from_bytes(o.pt_compress(p)), bl) for p, bl in zip(R, blinds)]
+
+
+def test_mta_messages_batch(engine, pkg, keyset):
+    """mirrors mta/test.rs:5-18 batched and at message level: MessageA / MessageB bytes identical to the oracle,
+    alpha + beta == a*b (mod q); a tampered range proof makes MessageB::b fail with InvalidKey (mta/mod.rs:123-131)."""
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    rng = Drbg(31, "mta-batch")
+    n = 6
+    q3 = o.Q ** 3
+    ek_row = [i % 3 for i in range(n)]                      # Alice's key row
+    st_rows = [[0, 1, 2]] * n                               # the full h1_h2_n_tilde_vec, as Round0 passes it (sign/rounds.rs:85)
+    stmts = keyset[0].h1_h2_n_tilde_vec
+    a, r, pr = [], [], []
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]
+        a.append(rng.scalar()); r.append(rng.below(ek.n))
+        pr.append([(rng.below(q3), rng.unit_mod(ek.n), rng.below(q3 * st.N), rng.below(o.Q * st.N)) for st in stmts])
+    c, proofs = gg20.mta_message_a(engine, ks, ek_row, st_rows, a, r, pr)
+    m_as = []
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]
+        m_a = o.message_a(a[i], ek, r[i], stmts, pr[i])
+        m_as.append(m_a)
+        assert c[i] == m_a.c
+        for x, pf in enumerate(m_a.range_proofs):
+            assert tuple(proofs[k][i][x] for k in ("z", "e", "s", "s1", "s2")) == (pf.z, pf.e, pf.s, pf.s1, pf.s2)
+    b = [rng.scalar() for _ in range(n)]
+    rand_b, beta_tag = [], []
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]
+        rand_b.append(rng.below(ek.n)); beta_tag.append(rng.below(ek.n))
+    nb, nbt = [rng.scalar() for _ in range(n)], [rng.scalar() for _ in range(n)]
+    c_b, bp, btp, beta, st = gg20.mta_message_b(engine, ks, ek_row, st_rows, b, c, proofs, rand_b, beta_tag, nb, nbt)
+    assert not st.any()
+    for i in range(n):
+        ek = keyset[0].paillier_key_vec[ek_row[i]]
+        m_b, beta_w = o.message_b(b[i], ek, m_as[i], rand_b[i], beta_tag[i], stmts, nb[i], nbt[i])
+        assert c_b[i] == m_b.c and beta[i] == beta_w
+        assert pkg.limbs_to_ints(bp[i:i + 1, 32:])[0] == m_b.b_proof.challenge_response
+        assert gg20.unpack_point(pkg.limbs_to_ints(btp[i:i + 1, :16])[0]) == m_b.beta_tag_proof.pk
+    alpha, plain, st2 = gg20.mta_get_alpha(engine, ks, ek_row, a, c_b, bp, btp)
+    assert not st2.any()
+    for i in range(n):
+        assert (alpha[i] + beta[i]) % o.Q == a[i] * b[i] % o.Q
+        assert plain[i] == o.paillier_decrypt(keyset[ek_row[i]].dk, c_b[i])
+    # tampered proof of instance 1 (statement 2): Bob refuses; wrong `a` at Alice's check: InvalidKey
+    bad = {k: [list(v) for v in proofs[k]] for k in proofs}
+    bad["s"][1][2] += 1
+    _, _, _, _, st3 = gg20.mta_message_b(engine, ks, ek_row, st_rows, b, c, bad, rand_b, beta_tag, nb, nbt)
+    assert st3[1] == pkg.ST_INVALID_KEY and not np.delete(st3, 1).any()
+    a_bad = list(a); a_bad[0] = (a[0] + 1) % o.Q
+    _, _, st4 = gg20.mta_get_alpha(engine, ks, ek_row, a_bad, c_b, bp, btp)
+    assert st4[0] == pkg.ST_INVALID_KEY and not st4[1:].any()
+    ks.free()
