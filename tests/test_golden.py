@@ -1,0 +1,79 @@
+"""Known-answer tests against tests/golden/vectors_r01.json (frozen oracle outputs over the committed key fixtures;
+the reference has no vectors of its own).  CPU: the oracle still reproduces them.  GPU: the CUDA path, through the C ABI,
+reproduces the same bytes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gg20_oracle as o
+from oracle.sampling import Drbg, sample_unit
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+V = json.load(open(os.path.join(HERE, "vectors_r01.json")))
+X = lambda s: int(s, 16)
+PT = lambda p: (X(p[0]), X(p[1]))
+
+
+def test_oracle_reproduces_vectors(keyset):
+    from tests.golden import make_vectors
+    assert make_vectors.build() == V
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_vectors(engine, pkg, keyset):
+    from mpecdsa_b200 import gg20
+    ks = gg20.KeySets(engine, [keyset])
+    for bits in (1024, 2048, 4096):
+        cs = [c for c in V["modexp"] if c["bits"] == bits]
+        got, st = engine.mod_pow([X(c["base"]) for c in cs], [X(c["exp"]) for c in cs], [X(c["mod"]) for c in cs], mod_bits=bits, exp_bits=bits)
+        assert got == [X(c["out"]) for c in cs] and not st.any()
+    ns = [k.dk.p * k.dk.q for k in keyset]
+    P = V["paillier"]
+    rows = [c["row"] for c in P]
+    c = engine.paillier_encrypt(ns, rows, [X(x["m"]) for x in P], [X(x["r"]) for x in P])
+    assert c == [X(x["c"]) for x in P]
+    ck = engine.paillier_mul(ns, rows, c, [X(x["k"]) for x in P])
+    assert ck == [X(x["c_mul_k"]) for x in P]
+    ca = engine.paillier_add(ns, rows, c, ck)
+    assert ca == [X(x["c_add"]) for x in P]
+    assert engine.paillier_decrypt(ks.handle, rows, ca) == [X(x["dec_c_add"]) for x in P]
+    A = V["alice"]
+    rr = list(zip(*[[X(t) for t in x["rand"]] for x in A]))
+    pf = gg20.alice_proof_generate(engine, ks, [x["ek_row"] for x in A], [x["st_row"] for x in A], [X(x["a"]) for x in A], [X(x["cipher"]) for x in A],
+                                   [X(x["r"]) for x in A], *[list(t) for t in rr])
+    for k in ("z", "e", "s", "s1", "s2"):
+        assert pf[k] == [X(x[k]) for x in A], k
+    D = V["pdl"]
+    rr = list(zip(*[[X(t) for t in x["rand"]] for x in D]))
+    pp = gg20.pdl_prove(engine, ks, [x["ek_row"] for x in D], [x["st_row"] for x in D], [X(x["x"]) for x in D], [X(x["r"]) for x in D],
+                        [X(x["cipher"]) for x in D], [PT(x["Q"]) for x in D], [PT(x["G"]) for x in D], *[list(t) for t in rr])
+    for k in ("z", "u2", "u3", "s1", "s2", "s3"):
+        assert pp[k] == [X(x[k]) for x in D], k
+    assert pp["u1"] == [PT(x["u1"]) for x in D]
+    B = V["bob"]
+    rr = list(zip(*[[X(t) for t in x["rand"]] for x in B]))
+    bp = gg20.bob_proof_generate(engine, ks, [x["ek_row"] for x in B], [x["st_row"] for x in B], True, [X(x["a_enc"]) for x in B], [X(x["mta"]) for x in B],
+                                 [X(x["b"]) for x in B], [X(x["beta_prim"]) for x in B], [X(x["r"]) for x in B], *[list(t) for t in rr])
+    for k in ("t", "z", "e", "s", "s1", "s2", "t1", "t2"):
+        assert bp[k] == [X(x[k]) for x in B], k
+    assert bp["u"] == [PT(x["u"]) for x in B]
+    d = V["sigma"]["dlog"]
+    out = gg20.dlog_prove(engine, [X(d["sk"])], [X(d["nonce"])])
+    assert pkg.limbs_to_ints(out[:, 32:])[0] == X(d["response"]) and gg20.unpack_point(pkg.limbs_to_ints(out[:, :16])[0]) == PT(d["pk"])
+    sess, rnds = [], []
+    for s in V["offline"]:
+        s_l = s["s_l"]
+        keys = [keyset[i - 1] for i in s_l]
+        drbg = Drbg(0xB2000005, f"vector-session{s_l}")
+        rnds += [sample_unit(drbg, keys, s_l, p) for p in range(2)]
+        sess.append((0, s_l[0] - 1, s_l[1] - 1))
+    res = gg20.offline_batch(engine, ks, sess, gg20.pack_randomness(rnds))
+    assert not res.status.any()
+    for i, s in enumerate(V["offline"]):
+        for p in range(2):
+            assert int.from_bytes(res.digest[2 * i + p].tobytes(), "little").to_bytes(32, "big").hex() == s["digest"][p]
+            assert pkg.limbs_to_ints(res.sigma[2 * i + p:2 * i + p + 1])[0] == X(s["sigma"][p])
+        assert gg20.unpack_point(pkg.limbs_to_ints(res.R[2 * i:2 * i + 1])[0]) == PT(s["R"])
+    ks.free()
