@@ -14,6 +14,10 @@ struct InvLaunch;
 constexpr int TPI_1024 = 4;     // 8 limbs per lane
 constexpr int TPI_2048 = 4;
 constexpr int TPI_4096 = 8;
+// N-adic jobs modulo N^2: lane groups are N wide (64 limbs).  Shape of the kernel (lanes per group, min blocks per SM) is a
+// process-wide tuning choice; TECDSA_NADIC_SHAPE="<tpi>,<minb>" overrides the default for measurements.
+int tecdsa_nadic_tpi();
+int tecdsa_nadic_minb();
 }  // namespace tecdsa
 
 int tecdsa_fail(int code, const char* what, cudaError_t e = cudaSuccess);
@@ -32,6 +36,7 @@ struct tecdsa_keyset {
     uint32_t* tab[tecdsa::KT_COUNT] = {};
     uint32_t* ypk = nullptr;
     uint32_t* fb = nullptr;      // fixed-base tables of (h1, h2) per key row, see jobs.cuh
+    uint32_t* nadic = nullptr;   // [rows][6*64] N-adic constants of the Paillier moduli, see nadic.cuh
     int n_keysets = 0;
 };
 
@@ -58,4 +63,6 @@ struct tecdsa_ctx {
     int reserve_arena(size_t bytes);
     int launch_exp(const tecdsa::ExpLaunch& l, int K);
     int launch_inv(const tecdsa::InvLaunch& l, int K);
+    int launch_nadic(const tecdsa::ExpLaunch& l);                               // every class modulo N^2 (ExpClass::nadic set)
+    int nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows);           // device pointers; out = [rows][6*64]
 };

@@ -44,6 +44,11 @@ struct Builder {
         k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
         k.mul[0] = m0; k.mul[1] = m1; k.mul[2] = m2; k.nbases = nb; k.nmul = nm; k.wide0 = wide0;
         k.fb = nullptr; k.fb_row = Operand{nullptr, nullptr, 0, 0, 0}; k.fb_sel[0] = k.fb_sel[1] = 0;
+        k.nadic = Operand{nullptr, nullptr, 0, 0, 0};
+        if (mod.ptr == A.key[KT_NN]) {      // every job modulo a Paillier N^2 runs in N-adic form (nadic.cuh): same value, ~2/3 of the MACs
+            k.mod = key(KT_N, mod.idx);
+            k.nadic = Operand{ks->nadic, mod.idx, 6 * 64, 1, 6 * 64};
+        }
         k.out = out(out_field); k.out_stride = A.size[out_field]; k.count = U; k.item_begin = l.total_items;
         l.total_items += (U + gpw - 1) / gpw;
     }
@@ -79,7 +84,7 @@ struct Builder {
 };
 
 const Operand NONE = {nullptr, nullptr, 0, 0, 0};
-constexpr int GPW32 = 32 / TPI_1024, GPW64 = 32 / TPI_2048, GPW128 = 32 / TPI_4096;
+constexpr int GPW32 = 32 / TPI_1024, GPW64 = 32 / TPI_2048, GPWI128 = 32 / TPI_4096;
 
 template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A, int per_unit = 1) {
     int grid = (A.U * per_unit + 63) / 64;
@@ -152,11 +157,16 @@ extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_ke
         c->count_launch();
         CK(cudaGetLastError());
     }
+    {   // N-adic constants of every Paillier modulus (KT_N was derived by gg20_key_setup above)
+        CK(cudaMalloc(&ks->nadic, (size_t)rows * 6 * 64 * 4));
+        int rc = c->nadic_setup(ks->tab[KT_N], ks->nadic, rows);
+        if (rc) return rc;
+    }
     CK(cudaStreamSynchronize(c->stream));
     // parity bits of the uploaded moduli are validated on the host copy of the inputs only
     for (int r = 0; r < rows; r++) {
         if (!(k->paillier_p[(size_t)r * 32] & 1) || !(k->paillier_q[(size_t)r * 32] & 1) || !(k->n_tilde[(size_t)r * 64] & 1)) {
-            cudaFree(ks->mem); cudaFree(ks->fb); delete ks;
+            cudaFree(ks->mem); cudaFree(ks->fb); cudaFree(ks->nadic); delete ks;
             return tecdsa_fail(TECDSA_E_ARG, "keys_upload: even modulus");
         }
     }
@@ -168,6 +178,7 @@ extern "C" int tecdsa_keys_free(tecdsa_ctx* c, tecdsa_keyset* ks) {
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
     if (ks->mem) cudaFree(ks->mem);
     if (ks->fb) cudaFree(ks->fb);
+    if (ks->nadic) cudaFree(ks->nadic);
     delete ks;
     return 0;
 }
@@ -181,7 +192,7 @@ extern "C" int tecdsa_keys_table(tecdsa_ctx* c, const tecdsa_keyset* ks, int tab
 // ------------------------------------------------------------------------------------------ job launches
 static int run_exp(tecdsa_ctx* c, ExpLaunch& l, int K) {
     if (l.n_classes == 0) return 0;
-    int rc = c->launch_exp(l, K);
+    int rc = K == 128 ? c->launch_nadic(l) : c->launch_exp(l, K);       // the 4096-bit list is all modulo N^2
     l.n_classes = 0; l.total_items = 0;
     return rc;
 }
@@ -247,6 +258,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     ExpLaunch &L32 = B.L32, &L64 = B.L64, &L128 = B.L128;
     InvLaunch &I64 = B.I64, &I128 = B.I128;
     Builder::reset(L32); Builder::reset(L64); Builder::reset(L128); Builder::reset(I64); Builder::reset(I128);
+    const int GPW128 = 32 / tecdsa_nadic_tpi();
     const uint32_t *ro = A.row_own, *rp = A.row_peer;
     auto st_rows = [&](int x) { return A.row_st + (size_t)x * U; };
 #define RUN(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
@@ -285,7 +297,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     // (c^e)^-1 mod N^2 is evaluated as (c^-1)^e (the reference does the same in commitment_unknown_order,
     // zk_pdl_with_slack/mod.rs:191-193): ONE inversion of the peer's ciphertext serves the three proofs here and the
     // peer's PDL proof in round 5 (declared shortcut, identical value)
-    B.inv_class(I128, GPW128, B.key(KT_NN, rp), B.peer(F_CK), F_CINVP, 3);
+    B.inv_class(I128, GPWI128, B.key(KT_NN, rp), B.peer(F_CK), F_CINVP, 3);
     RUN(run_inv(c, I128, 128));
     for (int x = 0; x < 3; x++) {
         B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 1, B.peer(F_Z0 + x), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_ZE0 + x);   // z^e (:122)
@@ -337,7 +349,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
 
     // ================= Round 5 (rounds.rs:525-592): verify both signers' PDL proofs (own one included)
     RUN(glue(c, gg20_r5_pre, A));
-    B.inv_class(I128, GPW128, B.key(KT_NN, ro), B.fld(F_CK), F_CINVO, 8);          // own ciphertext (proof j = 0); the peer's inverse is CINVP
+    B.inv_class(I128, GPWI128, B.key(KT_NN, ro), B.fld(F_CK), F_CINVO, 8);          // own ciphertext (proof j = 0); the peer's inverse is CINVP
     RUN(run_inv(c, I128, 128));
     for (int j = 0; j < 2; j++) {
         const uint32_t* prover = j ? rp : ro;            // key row of the prover

@@ -59,6 +59,9 @@ struct ExpClass {
     const uint32_t* fb;     // nullptr = off; else tables [row][2][FB_WINDOWS][32][K] in Montgomery form
     Operand fb_row;         // idx -> key row of instance i (ptr unused)
     int fb_sel[2];          // which of the row's two tables base[b] is (0 = h1, 1 = h2)
+    // N-adic mode (nadic.cuh, nadic_jobs_kernel only): the job is modulo N^2, `mod` names N and this the key's
+    // constants row (digits of R, R^2, R^3 mod N^2)
+    Operand nadic;
     int count;              // instances
     int item_begin;         // first warp-item of this class in the launch (prefix sum)
 };

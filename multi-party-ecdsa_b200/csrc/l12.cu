@@ -70,10 +70,21 @@ void add_exp(ExpLaunch& l, int K, int count, Operand mod, int nb, Operand b0, Op
     ExpClass& k = l.cls[l.n_classes++];
     k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
     k.mul[0] = m0; k.mul[1] = m1; k.mul[2] = NONE; k.nbases = nb; k.nmul = nm; k.wide0 = 0;
-    k.fb = nullptr; k.fb_row = NONE; k.fb_sel[0] = k.fb_sel[1] = 0;
+    k.fb = nullptr; k.fb_row = NONE; k.fb_sel[0] = k.fb_sel[1] = 0; k.nadic = NONE;
     k.out = out; k.out_stride = out_stride; k.count = count; k.item_begin = l.total_items;
     l.total_items += (count + gpw - 1) / gpw;
 }
+// class modulo N^2 through the N-adic kernel (nadic.cuh): `N` names the K = 64 limb modulus, `consts` its constants row
+void add_nn(ExpLaunch& l, int count, Operand N, Operand consts, int nb, Operand b0, Operand e0, int el0, Operand b1, Operand e1, int el1,
+            int nm, Operand m0, Operand m1, uint32_t* out, uint32_t out_stride) {
+    add_exp(l, 128, count, N, nb, b0, e0, el0, b1, e1, el1, nm, m0, m1, out, out_stride);
+    ExpClass& k = l.cls[l.n_classes - 1];
+    const int gpw = 32 / tecdsa_nadic_tpi();
+    k.nadic = consts;
+    l.total_items = k.item_begin + (count + gpw - 1) / gpw;
+}
+Operand key_n(const tecdsa_keyset* ks, const uint32_t* rows) { return tab(ks->tab[KT_N], rows, 64); }
+Operand key_nadic(const tecdsa_keyset* ks, const uint32_t* rows) { return tab(ks->nadic, rows, 6 * 64); }
 void add_fb(ExpLaunch& l, int count, const tecdsa_keyset* ks, const uint32_t* rows, Operand e_h2, int el_h2, Operand e_h1, int el_h1,
             int nm, Operand m0, uint32_t* out) {
     add_exp(l, 64, count, tab(ks->tab[KT_NT], rows, 64), 2, NONE, e_h2, el_h2, NONE, e_h1, el_h1, nm, m0, NONE, out, 64);
@@ -92,6 +103,12 @@ int run(tecdsa_ctx* c, ExpLaunch& l, int K) {
     l.n_classes = l.total_items = 0;
     return rc;
 }
+int run_nn(tecdsa_ctx* c, ExpLaunch& l) {
+    if (!l.n_classes) return 0;
+    int rc = c->launch_nadic(l);
+    l.n_classes = l.total_items = 0;
+    return rc;
+}
 int run(tecdsa_ctx* c, InvLaunch& l, int K) {
     if (!l.n_classes) return 0;
     int rc = c->launch_inv(l, K);
@@ -107,11 +124,6 @@ __global__ void k_lin(uint32_t* out, const uint32_t* m, int m_limbs, const uint3
     if (i >= count) return;
     uint32_t one = 1;
     st::mul_add(out + (size_t)i * 128, 128, m + (size_t)i * m_limbs, m_limbs, n_tab + (size_t)(rows ? rows[i] : i) * 64, 64, &one, 1);
-}
-__global__ void k_square(uint32_t* nn, const uint32_t* n, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    st::mul(nn + (size_t)i * 128, n + (size_t)i * 64, 64, n + (size_t)i * 64, 64);
 }
 __global__ void k_secp_mul(uint32_t* out, const uint32_t* pts, const uint32_t* scalars, int count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -486,17 +498,16 @@ extern "C" int tecdsa_paillier_encrypt_batch(tecdsa_ctx* c, const uint32_t* n, c
     Stage S(c, mem);
     const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *dm = S.in(m, count * 64), *dr = S.in(r, count * 64);
     uint32_t* dc = S.out(c_out, count * 128);
-    uint32_t *nn = S.tmp<uint32_t>(nk * 128), *lin = S.tmp<uint32_t>(count * 128);
+    uint32_t *nd = S.tmp<uint32_t>(nk * 6 * 64), *lin = S.tmp<uint32_t>(count * 128);
     if (S.err) return S.finish();
-    k_square<<<grid_for(nk), 64, 0, c->stream>>>(nn, dn, (int)nk);
-    KCHECK();
+    RUN(c->nadic_setup(dn, nd, (int)nk));
     k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dm, 64, dn, di, (int)count);
     KCHECK();
     Launches L;
-    Operand N = di ? tab(dn, di, 64) : arr(dn, 64), NN = di ? tab(nn, di, 128) : arr(nn, 128);
+    Operand N = di ? tab(dn, di, 64) : arr(dn, 64), ND = di ? tab(nd, di, 6 * 64) : arr(nd, 6 * 64);
     Operand rb = arr(dr, 64);
-    add_exp(L.e128, 128, (int)count, NN, 1, rb, N, 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, dc, 128);     // (1 + m n) * r^n mod n^2
-    RUN(run(c, L.e128, 128));
+    add_nn(L.e128, (int)count, N, ND, 1, rb, N, 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, dc, 128);     // (1 + m n) * r^n mod n^2
+    RUN(run_nn(c, L.e128));
     return S.finish();
 }
 
@@ -509,13 +520,12 @@ extern "C" int tecdsa_paillier_mul_batch(tecdsa_ctx* c, const uint32_t* n, const
     Stage S(c, mem);
     const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *dct = S.in(ct, count * 128), *dk = S.in(k, count * (size_t)k_limbs);
     uint32_t* dc = S.out(c_out, count * 128);
-    uint32_t* nn = S.tmp<uint32_t>(nk * 128);
+    uint32_t* nd = S.tmp<uint32_t>(nk * 6 * 64);
     if (S.err) return S.finish();
-    k_square<<<grid_for(nk), 64, 0, c->stream>>>(nn, dn, (int)nk);
-    KCHECK();
+    RUN(c->nadic_setup(dn, nd, (int)nk));
     Launches L;
-    add_exp(L.e128, 128, (int)count, di ? tab(nn, di, 128) : arr(nn, 128), 1, arr(dct, 128), arr(dk, k_limbs), k_limbs, NONE, NONE, 0, 0, NONE, NONE, dc, 128);
-    RUN(run(c, L.e128, 128));
+    add_nn(L.e128, (int)count, di ? tab(dn, di, 64) : arr(dn, 64), di ? tab(nd, di, 6 * 64) : arr(nd, 6 * 64), 1, arr(dct, 128), arr(dk, k_limbs), k_limbs, NONE, NONE, 0, 0, NONE, NONE, dc, 128);
+    RUN(run_nn(c, L.e128));
     return S.finish();
 }
 
@@ -528,13 +538,12 @@ extern "C" int tecdsa_paillier_add_batch(tecdsa_ctx* c, const uint32_t* n, const
     Stage S(c, mem);
     const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *d1 = S.in(c1, count * 128), *d2 = S.in(c2, count * 128);
     uint32_t* dc = S.out(c_out, count * 128);
-    uint32_t* nn = S.tmp<uint32_t>(nk * 128);
+    uint32_t* nd = S.tmp<uint32_t>(nk * 6 * 64);
     if (S.err) return S.finish();
-    k_square<<<grid_for(nk), 64, 0, c->stream>>>(nn, dn, (int)nk);
-    KCHECK();
+    RUN(c->nadic_setup(dn, nd, (int)nk));
     Launches L;
-    add_exp(L.e128, 128, (int)count, di ? tab(nn, di, 128) : arr(nn, 128), 0, NONE, NONE, 0, NONE, NONE, 0, 2, arr(d1, 128), arr(d2, 128), dc, 128);
-    RUN(run(c, L.e128, 128));
+    add_nn(L.e128, (int)count, di ? tab(dn, di, 64) : arr(dn, 64), di ? tab(nd, di, 6 * 64) : arr(nd, 6 * 64), 0, NONE, NONE, 0, NONE, NONE, 0, 2, arr(d1, 128), arr(d2, 128), dc, 128);
+    RUN(run_nn(c, L.e128));
     return S.finish();
 }
 
@@ -572,10 +581,10 @@ static int alice_generate_dev(tecdsa_ctx* c, Stage& S, const tecdsa_keyset* ks, 
     k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dal, 24, ks->tab[KT_N], er, n);
     c->count_launch();
     Launches L;
-    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, u, 128);  // u (:53-55)
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, u, 128);  // u (:53-55)
     add_fb(L.e64, n, ks, sr, arr(dga, 88), 88, arr(dal, 24), 24, 0, NONE, w);       // w = h1^alpha h2^gamma (:56-57)
     add_fb(L.e64, n, ks, sr, arr(dro, 72), 72, arr(da, 8), 8, 0, NONE, dz);         // z = h1^a h2^ro       (:52)
-    int rc = run(c, L.e128, 128); if (rc) return rc;
+    int rc = run_nn(c, L.e128); if (rc) return rc;
     rc = run(c, L.e64, 64); if (rc) return rc;
     k_alice_mid<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, da, dal, dga, dro, de, ds1, ds2, n);
     c->count_launch();
@@ -618,16 +627,16 @@ static int alice_verify_dev(tecdsa_ctx* c, Stage& S, const tecdsa_keyset* ks, in
     Launches L;
     Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
     add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);            // z^e (:122)
-    add_exp(L.e128, 128, n, NN, 1, arr(dc, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);        // c^e (:135)
-    int rc = run(c, L.e128, 128); if (rc) return rc;
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(dc, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);        // c^e (:135)
+    int rc = run_nn(c, L.e128); if (rc) return rc;
     rc = run(c, L.e64, 64); if (rc) return rc;
     add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, okz);
     add_inv(L.i128, 128, n, NN, arr(ce, 128), cei, okc);
     rc = run(c, L.i128, 128); if (rc) return rc;
     rc = run(c, L.i64, 64); if (rc) return rc;
     add_fb(L.e64, n, ks, sr, arr(ds2, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), w);                             // w' (:129-132)
-    add_exp(L.e128, 128, n, NN, 1, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(gs1, 128), arr(cei, 128), u, 128);   // u' (:141)
-    rc = run(c, L.e128, 128); if (rc) return rc;
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(gs1, 128), arr(cei, 128), u, 128);   // u' (:141)
+    rc = run_nn(c, L.e128); if (rc) return rc;
     rc = run(c, L.e64, 64); if (rc) return rc;
     k_alice_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, dc, dz, u, w, de, bad, okz, okc, e2, dst, n);
     c->count_launch();
@@ -675,8 +684,8 @@ extern "C" int tecdsa_pdl_prove_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, co
     Launches L;
     add_fb(L.e64, n, ks, sr, arr(dro, 72), 72, arr(dx, 8), 8, 0, NONE, dz);                 // z  = h1^x h2^rho       (:78-84)
     add_fb(L.e64, n, ks, sr, arr(dga, 88), 88, arr(dal, 24), 24, 0, NONE, du3);             // u3 = h1^alpha h2^gamma (:93-99)
-    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, du2, 128);   // u2 (:86-92)
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, du2, 128);   // u2 (:86-92)
+    RUN(run_nn(c, L.e128)); RUN(run(c, L.e64, 64));
     k_pdl_mid<<<grid_for(count), 64, 0, c->stream>>>(dG, dQ, dc, dz, du1, du2, du3, dx, dal, dro, dga, e, ds1, ds3, n);
     KCHECK();
     add_exp(L.e64, 64, n, tab(ks->tab[KT_N], er, 64), 1, arr(dr, 64), arr(e, 8), 8, NONE, NONE, 0, 1, arr(dbe, 64), NONE, ds2, 64);   // s2 = r^e beta mod N (:113)
@@ -707,14 +716,14 @@ extern "C" int tecdsa_pdl_verify_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, c
     Launches L;
     Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
     add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(e, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);          // z^e; (z^-1)^e == (z^e)^-1
-    add_exp(L.e128, 128, n, NN, 1, arr(dc, 128), arr(e, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);      // c^e
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(dc, 128), arr(e, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ce, 128);      // c^e
+    RUN(run_nn(c, L.e128)); RUN(run(c, L.e64, 64));
     add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, okz);
     add_inv(L.i128, 128, n, NN, arr(ce, 128), cei, okc);
     RUN(run(c, L.i128, 128)); RUN(run(c, L.i64, 64));
     add_fb(L.e64, n, ks, sr, arr(ds3, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), u3t);                        // u3' (:158-172)
-    add_exp(L.e128, 128, n, NN, 1, arr(ds2, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(lin, 128), arr(cei, 128), u2t, 128);   // u2' (:144-157)
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(ds2, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 2, arr(lin, 128), arr(cei, 128), u2t, 128);   // u2' (:144-157)
+    RUN(run_nn(c, L.e128)); RUN(run(c, L.e64, 64));
     k_pdl_vpost<<<grid_for(count), 64, 0, c->stream>>>(dG, dQ, du1, du2, du3, ds1, e, u2t, u3t, okz, okc, dst, n);
     KCHECK();
     return S.finish();
@@ -751,8 +760,8 @@ extern "C" int tecdsa_bob_proof_generate_batch(tecdsa_ctx* c, const tecdsa_keyse
     add_fb(L.e64, n, ks, sr, arr(dsi, 72), 72, arr(dbp, 64), 64, 0, NONE, dt);              // t  = h1^beta' h2^sigma      (:242-243)
     add_fb(L.e64, n, ks, sr, arr(dta, 88), 88, arr(dga, 80), 80, 0, NONE, w);               // w  = h1^gamma h2^tau        (:244-245)
     // v = a_enc^alpha * (gamma N + 1) * beta^N mod N^2                                      (:246-249)
-    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 2, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, arr(da, 128), arr(dal, 24), 24, 1, arr(lin, 128), NONE, v, 128);
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 2, arr(dbe, 64), tab(ks->tab[KT_N], er, 64), 64, arr(da, 128), arr(dal, 24), 24, 1, arr(lin, 128), NONE, v, 128);
+    RUN(run_nn(c, L.e128)); RUN(run(c, L.e64, 64));
     k_bob_mid<<<grid_for(count), 64, 0, c->stream>>>(A, er, check, da, dm, dz, zp, dt, v, w, db, dbp, dal, dga, dro, drp, dsi, dta, de, ds1, ds2, dt1, dt2, du, n);
     KCHECK();
     add_exp(L.e64, 64, n, tab(ks->tab[KT_N], er, 64), 1, arr(dr, 64), arr(de, 8), 8, NONE, NONE, 0, 1, arr(dbe, 64), NONE, ds, 64);   // s = r^e beta mod N (:291)
@@ -788,8 +797,8 @@ extern "C" int tecdsa_bob_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyset*
     Operand NT = tab(ks->tab[KT_NT], sr, 64), NN = tab(ks->tab[KT_NN], er, 128);
     add_exp(L.e64, 64, n, NT, 1, arr(dz, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, ze, 64);           // z^e   (:339)
     add_exp(L.e64, 64, n, NT, 1, arr(dt, 64), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, te, 64);           // t^e   (:363)
-    add_exp(L.e128, 128, n, NN, 1, arr(dm, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, me, 128);       // mta^e (:351)
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(dm, 128), arr(de, 8), 8, NONE, NONE, 0, 0, NONE, NONE, me, 128);       // mta^e (:351)
+    RUN(run_nn(c, L.e128)); RUN(run(c, L.e64, 64));
     add_inv(L.i64, 64, n, NT, arr(ze, 64), zei, ok1);
     add_inv(L.i64, 64, n, NT, arr(te, 64), tei, ok3);
     add_inv(L.i128, 128, n, NN, arr(me, 128), mei, ok2);
@@ -797,8 +806,8 @@ extern "C" int tecdsa_bob_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyset*
     add_fb(L.e64, n, ks, sr, arr(ds2, 92), 92, arr(ds1, 28), 28, 1, arr(zei, 64), zp);                          // z' (:346-349)
     add_fb(L.e64, n, ks, sr, arr(dt2, 92), 92, arr(dt1, 84), 84, 1, arr(tei, 64), w);                           // w  (:369-372)
     // v = a_enc^s1 * s^N * (t1 N + 1) * (mta^e)^-1 mod N^2                                                      (:357-361)
-    add_exp(L.e128, 128, n, NN, 2, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, arr(da, 128), arr(ds1, 28), 28, 2, arr(lin, 128), arr(mei, 128), v, 128);
-    RUN(run(c, L.e128, 128)); RUN(run(c, L.e64, 64));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 2, arr(ds, 64), tab(ks->tab[KT_N], er, 64), 64, arr(da, 128), arr(ds1, 28), 28, 2, arr(lin, 128), arr(mei, 128), v, 128);
+    RUN(run_nn(c, L.e128)); RUN(run(c, L.e64, 64));
     k_bob_vpost<<<grid_for(count), 64, 0, c->stream>>>(A, er, da, dm, dz, zp, dt, v, w, de, ds1, dX, dU, bad, ok1, ok2, ok3, e2, dst, n);
     KCHECK();
     return S.finish();
@@ -925,8 +934,8 @@ extern "C" int tecdsa_mta_message_a_batch(tecdsa_ctx* c, const tecdsa_keyset* ks
     k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, a64, 64, ks->tab[KT_N], er, n);
     KCHECK();
     Launches L;
-    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 1, arr(dr, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, dc, 128);
-    RUN(run(c, L.e128, 128));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 1, arr(dr, 64), tab(ks->tab[KT_N], er, 64), 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, dc, 128);
+    RUN(run_nn(c, L.e128));
     if (n_st > 0) {
         const uint32_t *sr = S.in(st_rows, np), *dal = S.in(alpha, np * 24), *dbe = S.in(beta, np * 64), *dga = S.in(gamma, np * 88), *dro = S.in(rho, np * 72);
         uint32_t *dz = S.out(z, np * 64), *de = S.out(e, np * 8), *ds = S.out(s, np * 64), *ds1 = S.out(s1, np * 28), *ds2 = S.out(s2, np * 92);
@@ -977,8 +986,8 @@ extern "C" int tecdsa_mta_message_b_batch(tecdsa_ctx* c, const tecdsa_keyset* ks
     k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dbt, 64, ks->tab[KT_N], er, n);
     KCHECK();
     Launches L;
-    add_exp(L.e128, 128, n, tab(ks->tab[KT_NN], er, 128), 2, arr(dr, 64), tab(ks->tab[KT_N], er, 64), 64, arr(dca, 128), arr(db, 8), 8, 1, arr(lin, 128), NONE, dcb, 128);
-    RUN(run(c, L.e128, 128));
+    add_nn(L.e128, n, key_n(ks, er), key_nadic(ks, er), 2, arr(dr, 64), tab(ks->tab[KT_N], er, 64), 64, arr(dca, 128), arr(db, 8), 8, 1, arr(lin, 128), NONE, dcb, 128);
+    RUN(run_nn(c, L.e128));
     k_mta_b_post<<<grid_for(count), 64, 0, c->stream>>>(pst, n_st, db, dbt, dnb, dnt, dbeta, dbp, dtp, dst, n);
     KCHECK();
     return S.finish();

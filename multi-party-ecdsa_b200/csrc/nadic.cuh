@@ -1,0 +1,313 @@
+// Arithmetic modulo a perfect square M = N^2 in "N-adic" Montgomery form.
+//
+// Every exponentiation modulo N^2 on the path (Paillier encrypt / homomorphic multiply, the u, v
+// terms of the range and PDL proofs: /root/reference/src/utilities/mta/mod.rs:133-145,
+// src/utilities/mta/range_proofs.rs:54,135,141, src/utilities/zk_pdl_with_slack/mod.rs:144-157)
+// is 4096-bit arithmetic in the reference (GMP) and costs 2*(2K)^2 MACs per Montgomery product in
+// exp_jobs_kernel<128,8>.  Here a residue x mod N^2 is kept as two digits x = x0 + x1*N
+// (0 <= x0, x1 < N) and all work is done modulo N (K limbs, R = 2^(32K)):
+//
+//   X*Y*R^-1 mod N^2,  with  t = X0*Y0,  u' = (t + m*N)/R  (the Montgomery step, quotient number m):
+//       Z0 = u' mod N,   Z1 = montmul(X0,Y1) + montmul(X1,Y0) - m*R^-1 + [u' >= N]   (mod N)
+//
+// (t = u'*R - m*N, so t*R^-1 = u' - N*(m*R^-1) mod N^2, and N*x mod N^2 only depends on x mod N.)
+// A squaring costs 2.5 K-limb products (5K^2 MACs), a multiplication 3.5 (7K^2), against 4 (8K^2)
+// for the direct 2K-limb product.  The values are identical: operands come in and results go out
+// as plain 2K-limb integers.  Per-key constants (digits of R, R^2, R^3 mod N^2) are built at key
+// upload by nadic_setup_kernel.
+#pragma once
+#include "jobs.cuh"
+
+namespace tecdsa {
+
+template <int L> struct Dig { uint32_t d0[L], d1[L]; };
+
+// (a + b) mod n, (a - b) mod n for canonical inputs
+template <int TPI, int L>
+__device__ __forceinline__ void mod_add(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L], const uint32_t (&n)[L]) {
+    uint32_t T[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) T[j] = a[j];
+    uint32_t cy = group_add_masked<TPI, L>(T, b, 0xffffffffu);
+    reduce_once<TPI, L>(r, T, cy, n);
+}
+template <int TPI, int L>
+__device__ __forceinline__ void mod_sub(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L], const uint32_t (&n)[L]) {
+    uint32_t T[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) T[j] = a[j];
+    uint32_t ge = group_sub_masked<TPI, L>(T, b, 0xffffffffu, 1u);       // a + ~b + 1; carry out == (a >= b)
+    (void)group_add_masked<TPI, L>(T, n, ge ? 0u : 0xffffffffu);          // borrowed: add n back
+#pragma unroll
+    for (int j = 0; j < L; j++) r[j] = T[j];
+}
+template <int TPI, int L>
+__device__ __forceinline__ void mod_inc(uint32_t (&r)[L], uint32_t c, const uint32_t (&n)[L]) {      // r = (r + c) mod n, c in {0,1}
+    uint32_t one[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) one[j] = 0;
+    if (group_lane<TPI>() == 0) one[0] = c;
+    mod_add<TPI, L>(r, r, one, n);
+}
+
+// Z = X*Y*R^-1 mod N^2 in digits; `sq` => Y is taken to be X.  X0 may be any value < R (a plain,
+// non-canonical low digit with X1 = 0 is how plain operands are lifted); everything else canonical.
+// The up-to-three K-limb products run through ONE copy of the row loop (operands selected per
+// phase) to keep the instruction footprint of the exponentiation loop small.
+template <int TPI, int L>
+__device__ __forceinline__ void nadic_mul(Dig<L>& Z, const Dig<L>& X, const Dig<L>& Y, bool sq, const uint32_t (&n)[L], uint32_t n0inv) {
+    const int gl = group_lane<TPI>();
+    uint32_t u[L], w[L];
+    uint32_t uc = 0;
+#pragma unroll
+    for (int j = 0; j < L; j++) { u[j] = 0; w[j] = 0; }
+#pragma unroll 1
+    for (int p = 0; p < 3; p++) {
+        if (p == 1 && sq) continue;
+        // p = 0: X0*Y0 (records the quotient digits m)   p = 1: X1*Y0   p = 2: X0*Y1
+        uint32_t a[L], m[L];
+#pragma unroll
+        for (int j = 0; j < L; j++) { a[j] = (p == 1) ? X.d1[j] : X.d0[j]; m[j] = 0; }
+        uint32_t E[L + 2], O[L + 2];
+#pragma unroll
+        for (int j = 0; j < L + 2; j++) { E[j] = 0; O[j] = 0; }
+        uint32_t inc = 0;
+        const bool hi_b = p == 2;
+#pragma unroll 1
+        for (int gi = 0; gi < TPI; gi++) {
+            const bool rec = (gi == gl) && (p == 0);
+#pragma unroll
+            for (int li = 0; li < L; li += 2) {
+                const uint32_t s0 = sq ? (hi_b ? X.d1[li] : X.d0[li]) : (hi_b ? Y.d1[li] : Y.d0[li]);
+                const uint32_t s1 = sq ? (hi_b ? X.d1[li + 1] : X.d0[li + 1]) : (hi_b ? Y.d1[li + 1] : Y.d0[li + 1]);
+                uint32_t b0 = __shfl_sync(FULL, s0, gi, TPI);
+                uint32_t b1 = __shfl_sync(FULL, s1, gi, TPI);
+                uint32_t q0, q1;
+                inc = mont_row_q<TPI, L>(E, O, a, n, b0, n0inv, inc, q0);
+                inc = mont_row_q<TPI, L>(O, E, a, n, b1, n0inv, inc, q1);
+                if (rec) { m[li] = q0; m[li + 1] = q1; }
+            }
+        }
+        uint32_t T[L], D[L];
+        const uint32_t ov = rows_finish<TPI, L>(T, E, O, inc);
+#pragma unroll
+        for (int j = 0; j < L; j++) D[j] = T[j];
+        const uint32_t ge = group_sub_masked<TPI, L>(D, n, 0xffffffffu, 1u);
+        const bool take = (ov | ge) != 0;
+#pragma unroll
+        for (int j = 0; j < L; j++) T[j] = take ? D[j] : T[j];
+        if (p == 0) {
+            uc = take ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < L; j++) u[j] = T[j];
+            mont_redc<TPI, L>(T, m, n, n0inv);                 // m * R^-1 mod N
+            mod_sub<TPI, L>(w, w, T, n);                       // w = -m R^-1
+        } else {
+            mod_add<TPI, L>(w, w, T, n);
+            if (sq) mod_add<TPI, L>(w, w, T, n);
+        }
+    }
+    mod_inc<TPI, L>(w, uc, n);
+#pragma unroll
+    for (int j = 0; j < L; j++) { Z.d0[j] = u[j]; Z.d1[j] = w[j]; }
+}
+
+// (A + B) mod N^2 in digits
+template <int TPI, int L>
+__device__ __forceinline__ void dig_add(Dig<L>& Z, const Dig<L>& A, const Dig<L>& B, const uint32_t (&n)[L]) {
+    uint32_t T[L], D[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) T[j] = A.d0[j];
+    const uint32_t cy = group_add_masked<TPI, L>(T, B.d0, 0xffffffffu);
+#pragma unroll
+    for (int j = 0; j < L; j++) D[j] = T[j];
+    const uint32_t ge = group_sub_masked<TPI, L>(D, n, 0xffffffffu, 1u);
+    const uint32_t c = (cy | ge) ? 1u : 0u;
+    uint32_t hi[L];
+    mod_add<TPI, L>(hi, A.d1, B.d1, n);
+    mod_inc<TPI, L>(hi, c, n);
+#pragma unroll
+    for (int j = 0; j < L; j++) { Z.d0[j] = c ? D[j] : T[j]; Z.d1[j] = hi[j]; }
+}
+
+template <int TPI, int L>
+__device__ __forceinline__ void load_dig(Dig<L>& D, const uint32_t* p) {
+    constexpr int K = TPI * L;
+    load_limbs<TPI, L>(D.d0, p);
+    load_limbs<TPI, L>(D.d1, p + K);
+}
+template <int TPI, int L>
+__device__ __forceinline__ void store_dig(uint32_t* p, const Dig<L>& D) {
+    constexpr int K = TPI * L;
+    store_limbs<TPI, L>(p, D.d0);
+    store_limbs<TPI, L>(p + K, D.d1);
+}
+
+// per-key constants row, 6K limbs: digits of R ("one"), R^2 and R^3 modulo N^2
+static constexpr int NADIC_ONE = 0, NADIC_RR2 = 2, NADIC_RR3 = 4;    // offsets in units of K limbs
+static constexpr int NADIC_TABLE_ENTRIES = 2 * (1 << WINDOW_BITS) + 1;  // per lane group: two window tables + one parked value, 2K limbs each
+
+// plain operand c = c_hi * R + c_lo (2K limbs, zero-extended from o.limbs, any value) -> Montgomery digits of c mod N^2:
+// (c_hi, 0) * R^3 * R^-1 + (c_lo, 0) * R^2 * R^-1
+template <int TPI, int L>
+__device__ __forceinline__ void to_nadic(Dig<L>& X, const Operand& o, int i, const uint32_t* consts, const uint32_t (&n)[L], uint32_t n0inv) {
+    constexpr int K = TPI * L;
+    Dig<L> a, c, hi;
+#pragma unroll
+    for (int j = 0; j < L; j++) { a.d1[j] = 0; hi.d0[j] = 0; hi.d1[j] = 0; X.d0[j] = 0; X.d1[j] = 0; }
+    const int halves = o.limbs > (uint32_t)K ? 2 : 1;          // uniform per class
+#pragma unroll 1
+    for (int h = 0; h < halves; h++) {
+        load_operand<TPI, L>(a.d0, o, i, h ? (uint32_t)K : 0u);
+        load_dig<TPI, L>(c, consts + (h ? NADIC_RR3 : NADIC_RR2) * K);
+        nadic_mul<TPI, L>(hi, a, c, false, n, n0inv);
+        dig_add<TPI, L>(X, X, hi, n);
+    }
+}
+
+// Same job semantics as exp_jobs_kernel (out = m1*m2*m3 * b1^e1 * b2^e2 mod N^2, plain 2K-limb operands and result), but
+// `mod` names N (K limbs) and `nadic` the per-key constants row.  K is the width of N.
+template <int K, int TPI, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tables, unsigned int* __restrict__ counter) {
+    constexpr int L = K / TPI;
+    constexpr int GPW = 32 / TPI;
+    constexpr int TBL = 1 << WINDOW_BITS;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (TPI - 1);
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t* my_tbl = tables + ((size_t)warp_global * GPW + lane / TPI) * (size_t)(NADIC_TABLE_ENTRIES * 2 * K);
+    uint32_t* p_slot = my_tbl + (size_t)(2 * TBL) * 2 * K;    // product of the plain multipliers, parked during the exponentiation
+    const int total = launch->total_items;
+    const int ncls = launch->n_classes;
+
+    while (true) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if ((int)item >= total) break;
+        int ci = 0;
+        while (ci + 1 < ncls && launch->cls[ci + 1].item_begin <= (int)item) ci++;
+        const ExpClass& c = launch->cls[ci];
+        const int g = ((int)item - c.item_begin) * GPW + lane / TPI;
+        const bool live = g < c.count;
+        const int i = live ? g : c.count - 1;
+
+        uint32_t n[L];
+        load_operand<TPI, L>(n, c.mod, i);
+        const uint32_t n0inv = neg_inv32(__shfl_sync(FULL, n[0], 0, TPI));
+        const uint32_t* consts = operand_at(c.nadic, i);
+
+        // operands 0..nbases-1 are bases (window tables), the rest plain multipliers (folded into P)
+        Dig<L> acc, Y;
+        {
+            Dig<L> P;
+            load_dig<TPI, L>(P, consts + NADIC_ONE * K);
+            store_dig<TPI, L>(p_slot, P);
+        }
+#pragma unroll 1
+        for (int k = 0; k < c.nbases + c.nmul; k++) {
+            const bool is_base = k < c.nbases;
+            Dig<L> xr;
+            to_nadic<TPI, L>(xr, is_base ? c.base[k] : c.mul[k - c.nbases], i, consts, n, n0inv);
+            uint32_t* tb = my_tbl + (size_t)k * TBL * 2 * K;
+            if (is_base) {
+                load_dig<TPI, L>(Y, consts + NADIC_ONE * K);
+                store_dig<TPI, L>(tb, Y);
+                store_dig<TPI, L>(tb + 2 * K, xr);
+                Y = xr;
+            } else {
+                load_dig<TPI, L>(Y, p_slot);
+            }
+            // base: Y runs through xr^2 .. xr^31 into the table; multiplier: one product P *= xr
+            const int steps = is_base ? TBL - 2 : 1;
+#pragma unroll 1
+            for (int e = 0; e < steps; e++) {
+                nadic_mul<TPI, L>(Y, Y, xr, false, n, n0inv);
+                if (is_base) store_dig<TPI, L>(tb + (size_t)(e + 2) * 2 * K, Y);
+            }
+            if (!is_base) store_dig<TPI, L>(p_slot, Y);
+        }
+        __syncwarp();
+        // exponentiation; the multiplier product P and the exit from the Montgomery domain (times (1, 0)) are the two
+        // last steps of the same loop
+        load_dig<TPI, L>(acc, consts + NADIC_ONE * K);
+        {
+            const uint32_t* e0 = operand_at(c.exp[0], i);
+            const uint32_t* e1 = c.nbases > 1 ? operand_at(c.exp[1], i) : e0;
+            const int nw0 = c.nbases > 0 ? (c.exp_limbs[0] * 32 + WINDOW_BITS - 1) / WINDOW_BITS : 0;
+            const int nw1 = c.nbases > 1 ? (c.exp_limbs[1] * 32 + WINDOW_BITS - 1) / WINDOW_BITS : 0;
+            const int nw = nw0 > nw1 ? nw0 : nw1;
+            int w = nw - 1, ph = WINDOW_BITS;
+#pragma unroll 1
+            while (w >= -2) {
+                bool do_mul = true, sq = false;
+                if (w == -1) { load_dig<TPI, L>(Y, p_slot); do_mul = c.nmul > 0; w = -2; }
+                else if (w == -2) {
+#pragma unroll
+                    for (int j = 0; j < L; j++) { Y.d0[j] = 0; Y.d1[j] = 0; }
+                    if (gl == 0) Y.d0[0] = 1;
+                    w = -3;
+                }
+                else if (ph < WINDOW_BITS) { sq = true; ph++; }
+                else if (ph == WINDOW_BITS) {
+                    if (w < nw0) load_dig<TPI, L>(Y, my_tbl + (size_t)exp_window(e0, c.exp_limbs[0], w) * 2 * K);
+                    else do_mul = false;
+                    ph++;
+                } else {
+                    if (w < nw1) load_dig<TPI, L>(Y, my_tbl + ((size_t)TBL + exp_window(e1, c.exp_limbs[1], w)) * 2 * K);
+                    else do_mul = false;
+                    ph = 0; w--;
+                }
+                if (do_mul) nadic_mul<TPI, L>(acc, acc, Y, sq, n, n0inv);
+            }
+        }
+        // plain value = d0 + d1 * N  (2K limbs)
+        uint32_t lo[L], hi[L];
+        group_mul_wide<TPI, L>(lo, hi, acc.d1, n);
+        const uint32_t cy = group_add_masked<TPI, L>(lo, acc.d0, 0xffffffffu);
+        {
+            uint32_t one[L];
+#pragma unroll
+            for (int j = 0; j < L; j++) one[j] = 0;
+            if (gl == 0) one[0] = cy;
+            (void)group_add_masked<TPI, L>(hi, one, 0xffffffffu);
+        }
+        if (live) {
+            uint32_t* o = c.out + (size_t)g * c.out_stride;
+            store_limbs<TPI, L>(o, lo);
+            store_limbs<TPI, L>(o + K, hi);
+        }
+        __syncwarp();
+    }
+}
+
+// One lane-group per key row: digits of R, R^2, R^3 modulo N^2 (N odd, > 1).  R^2 = 2^(64K) comes from doubling (1, 0).
+template <int K, int TPI>
+__global__ void __launch_bounds__(128)
+nadic_setup_kernel(const uint32_t* __restrict__ n_tab, uint32_t* __restrict__ out, int rows) {
+    constexpr int L = K / TPI;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
+    const bool live = g < rows;
+    const int row = live ? g : rows - 1;
+    uint32_t n[L];
+    load_limbs<TPI, L>(n, n_tab + (size_t)row * K);
+    const uint32_t n0inv = neg_inv32(__shfl_sync(FULL, n[0], 0, TPI));
+    Dig<L> lift, rr2, t;
+#pragma unroll
+    for (int j = 0; j < L; j++) { lift.d0[j] = 0; lift.d1[j] = 0; }
+    if (group_lane<TPI>() == 0) lift.d0[0] = 1;
+    rr2 = lift;
+#pragma unroll 1
+    for (int i = 0; i < 64 * K; i++) dig_add<TPI, L>(rr2, rr2, rr2, n);
+    uint32_t* o = out + (size_t)row * 6 * K;
+#pragma unroll 1
+    for (int s = 0; s < 2; s++) {
+        // s = 0: 1 * R^2 * R^-1 = R;  s = 1: R^2 * R^2 * R^-1 = R^3
+        nadic_mul<TPI, L>(t, s ? rr2 : lift, rr2, false, n, n0inv);
+        if (live) store_dig<TPI, L>(o + (s ? NADIC_RR3 : NADIC_ONE) * K, t);
+    }
+    if (live) store_dig<TPI, L>(o + NADIC_RR2 * K, rr2);
+}
+
+}  // namespace tecdsa

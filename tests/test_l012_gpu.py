@@ -80,6 +80,31 @@ def test_paillier_ops(engine, pkg, keyset):
     ks.free()
 
 
+def test_paillier_nadic_edge_cases(engine):
+    """The N^2 jobs run in N-adic form (csrc/nadic.cuh); the value must equal plain 4096-bit arithmetic for ANY odd N
+    and ANY 4096-bit operand: short moduli, N = 3, all-ones N, ciphertexts >= N^2, zero / one operands and exponents."""
+    rng = random.Random(77)
+    B = 2048
+    ns = [3, (1 << B) - 1, rng.getrandbits(1500) | 1, rng.getrandbits(B - 1) | 1 | (1 << (B - 2)), (1 << (B - 1)) + 1, 5 ** 800]
+    ns += [rng.getrandbits(B) | 1 | (1 << (B - 1)) for _ in range(10)]
+    n = 96
+    idx = [i % len(ns) for i in range(n)]
+    c = [rng.getrandbits(4096) for _ in range(n)]                 # mostly >= N^2: reduced like BigInt::mod_pow does
+    k = [rng.getrandbits(2048) for _ in range(n)]
+    c[0] = 0; c[1] = 1; k[2] = 0; k[3] = 1; c[4] = (1 << 4096) - 1; k[5] = (1 << 2048) - 1
+    for j in range(6, 22):
+        c[j] = ns[idx[j]] ** 2 - 1 - (j & 1) * rng.getrandbits(40)   # just below N^2: -1 and neighbours
+    got = engine.paillier_mul(ns, idx, c, k, k_limbs=64)
+    assert got == [pow(cc, kk, ns[i] ** 2) for i, cc, kk in zip(idx, c, k)]
+    c2 = [rng.getrandbits(4096) for _ in range(n)]
+    got = engine.paillier_add(ns, idx, c, c2)
+    assert got == [x * y % ns[i] ** 2 for i, x, y in zip(idx, c, c2)]
+    m = [rng.getrandbits(2048) for _ in range(n)]
+    r = [rng.getrandbits(2048) for _ in range(n)]
+    got = engine.paillier_encrypt(ns, idx, m, r)
+    assert got == [(1 + mm * ns[i]) * pow(rr, ns[i], ns[i] ** 2) % ns[i] ** 2 for i, mm, rr in zip(idx, m, r)]
+
+
 def test_alice_proof_generate_verify_batch(engine, pkg, keyset):
     """BASELINE.json configs[3] shape at a size the oracle checks in seconds: proofs generated on the
     GPU are byte-identical to the oracle's, verify on the GPU and under the oracle; tampered ones are
