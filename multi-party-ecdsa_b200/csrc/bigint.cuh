@@ -220,12 +220,9 @@ __device__ __forceinline__ void mont_mul(uint32_t (&r)[L], const uint32_t (&a)[L
 }
 
 // ---------------------------------------------------------------------------------------------
-// Variants of the row machinery used by the N-adic arithmetic modulo a perfect square (nadic.cuh):
-//   mont_mul_q : the Montgomery product that also hands back its K quotient digits (the number m
-//                with a*b + m*n == u*R), lane g keeping digits [g*L, (g+1)*L)
-//   mont_redc  : t * R^-1 mod n for a K-limb t (reduction rows only: half the MACs of a product)
+// Pieces of the row machinery shared with the N-adic arithmetic modulo a perfect square (nadic.cuh):
+//   rows_finish / reduce_once : the tail of a product (set merge, carry resolve, conditional subtract)
 //   group_mul_wide : the plain 2K-limb product a*b (no reduction), low half / high half per lane
-// They share the tail (set merge, carry resolve) with mont_mul.
 
 // merge the two accumulator sets after the last row into K limbs + the overflow word
 template <int TPI, int L>
@@ -262,83 +259,6 @@ __device__ __forceinline__ void reduce_once(uint32_t (&r)[L], const uint32_t (&T
     const bool take = (ov | ge) != 0;
 #pragma unroll
     for (int j = 0; j < L; j++) r[j] = take ? D[j] : T[j];
-}
-
-template <int TPI, int L>
-__device__ __forceinline__ uint32_t mont_row_q(uint32_t (&A)[L + 2], uint32_t (&B)[L + 2], const uint32_t (&a)[L],
-                                               const uint32_t (&n)[L], uint32_t bi, uint32_t n0inv, uint32_t inc, uint32_t& q_out) {
-    B[L] = add_cc(B[L], inc);
-    B[L + 1] = addc(0, 0);
-    A[0] = add_cc(A[0], B[1]);
-    madc_odd_rshift<L>(B, a, bi);
-    mad_even<L>(A, a, bi);
-    uint32_t q = __shfl_sync(FULL, A[0] * n0inv, 0, TPI);
-    q_out = q;
-    mad_odd<L>(B, n, q);
-    mad_even<L>(A, n, q);
-    uint32_t dn = __shfl_down_sync(FULL, A[0], 1, TPI);
-    return (group_lane<TPI>() == TPI - 1) ? 0u : dn;
-}
-template <int TPI, int L>
-__device__ __forceinline__ void mont_mul_q(uint32_t (&r)[L], uint32_t (&m)[L], const uint32_t (&a)[L], const uint32_t (&b)[L],
-                                           const uint32_t (&n)[L], uint32_t n0inv) {
-    const int gl = group_lane<TPI>();
-    uint32_t E[L + 2], O[L + 2];
-#pragma unroll
-    for (int j = 0; j < L + 2; j++) { E[j] = 0; O[j] = 0; }
-    uint32_t inc = 0;
-#pragma unroll 1
-    for (int gi = 0; gi < TPI; gi++) {
-        const bool mine = gi == gl;
-#pragma unroll
-        for (int li = 0; li < L; li += 2) {
-            uint32_t b0 = __shfl_sync(FULL, b[li], gi, TPI);
-            uint32_t b1 = __shfl_sync(FULL, b[li + 1], gi, TPI);
-            uint32_t q0, q1;
-            inc = mont_row_q<TPI, L>(E, O, a, n, b0, n0inv, inc, q0);
-            inc = mont_row_q<TPI, L>(O, E, a, n, b1, n0inv, inc, q1);
-            if (mine) { m[li] = q0; m[li + 1] = q1; }
-        }
-    }
-    uint32_t T[L];
-    uint32_t ov = rows_finish<TPI, L>(T, E, O, inc);
-    reduce_once<TPI, L>(r, T, ov, n);
-}
-
-// reduction-only row: the previous even set is shifted into the odd set by plain adds
-template <int TPI, int L>
-__device__ __forceinline__ uint32_t redc_row(uint32_t (&A)[L + 2], uint32_t (&B)[L + 2], const uint32_t (&n)[L], uint32_t n0inv, uint32_t inc) {
-    B[L] = add_cc(B[L], inc);
-    B[L + 1] = addc(0, 0);
-    A[0] = add_cc(A[0], B[1]);
-#pragma unroll
-    for (int j = 0; j < L; j++) B[j] = addc_cc(B[j + 2], 0);
-    B[L] = addc(0, 0);
-    B[L + 1] = 0;
-    uint32_t q = __shfl_sync(FULL, A[0] * n0inv, 0, TPI);
-    mad_odd<L>(B, n, q);
-    mad_even<L>(A, n, q);
-    uint32_t dn = __shfl_down_sync(FULL, A[0], 1, TPI);
-    return (group_lane<TPI>() == TPI - 1) ? 0u : dn;
-}
-template <int TPI, int L>
-__device__ __forceinline__ void mont_redc(uint32_t (&r)[L], const uint32_t (&t)[L], const uint32_t (&n)[L], uint32_t n0inv) {
-    uint32_t E[L + 2], O[L + 2];
-#pragma unroll
-    for (int j = 0; j < L; j++) { E[j] = t[j]; O[j] = 0; }
-    E[L] = 0; E[L + 1] = 0; O[L] = 0; O[L + 1] = 0;
-    uint32_t inc = 0;
-#pragma unroll 1
-    for (int gi = 0; gi < TPI; gi++) {
-#pragma unroll
-        for (int li = 0; li < L; li += 2) {
-            inc = redc_row<TPI, L>(E, O, n, n0inv, inc);
-            inc = redc_row<TPI, L>(O, E, n, n0inv, inc);
-        }
-    }
-    uint32_t T[L];
-    uint32_t ov = rows_finish<TPI, L>(T, E, O, inc);
-    reduce_once<TPI, L>(r, T, ov, n);
 }
 
 // product-only row; lane 0's column 0 is a finished limb of the product

@@ -325,7 +325,7 @@ int tecdsa_ctx::launch_exp(const ExpLaunch& l, int K) {
     return 0;
 }
 namespace {
-struct NadicShape { int tpi = 4, minb = 1; };
+struct NadicShape { int tpi = 8, minb = 1; };      // measured: (8,1) 12.0 k, (4,1) 12.0 k, (4,3) 11.7 k party-phases/s
 const NadicShape& nadic_shape() {
     static const NadicShape sh = [] {
         NadicShape s;
@@ -337,17 +337,17 @@ const NadicShape& nadic_shape() {
     }();
     return sh;
 }
-template <int TPI, int MINB>
+template <int K, int TPI, int MINB>
 int launch_nadic_shape(tecdsa_ctx* c, const ExpLaunch& l) {
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nadic_jobs_kernel<64, TPI, MINB>, JOB_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nadic_jobs_kernel<K, TPI, MINB>, JOB_BLOCK, 0);
     if (per_sm < 1) per_sm = 1;
     const int grid = c->sm_count * per_sm;
-    const size_t table_bytes = (size_t)grid * (JOB_BLOCK / 32) * (32 / TPI) * (size_t)NADIC_TABLE_ENTRIES * 2 * 64 * 4;
+    const size_t table_bytes = (size_t)grid * (JOB_BLOCK / 32) * (32 / TPI) * (size_t)NADIC_TABLE_ENTRIES * 2 * K * 4;
     char* d_desc; unsigned int* d_counter; uint32_t* d_tables;
     int rc = job_prepare(c, table_bytes, &l, sizeof(ExpLaunch), &d_desc, &d_counter, &d_tables);
     if (rc) return rc;
-    nadic_jobs_kernel<64, TPI, MINB><<<grid, JOB_BLOCK, 0, c->stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
+    nadic_jobs_kernel<K, TPI, MINB><<<grid, JOB_BLOCK, 0, c->stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
     c->count_launch();
     CK(cudaGetLastError());
     return 0;
@@ -358,17 +358,19 @@ int tecdsa_nadic_tpi() { return nadic_shape().tpi; }
 int tecdsa_nadic_minb() { return nadic_shape().minb; }
 }
 
-int tecdsa_ctx::launch_nadic(const ExpLaunch& l) {
+int tecdsa_ctx::launch_nadic(const ExpLaunch& l, int K) {
     for (int i = 0; i < l.n_classes; i++)
         if (!l.cls[i].nadic.ptr || l.cls[i].fb) return tecdsa_fail(TECDSA_E_ARG, "launch_nadic: class without N-adic constants");
+    if (K == 32) return launch_nadic_shape<32, TPI_NADIC32, 1>(this, l);
     const NadicShape& sh = nadic_shape();
-    if (sh.tpi == 8) return launch_nadic_shape<8, 1>(this, l);
-    return sh.minb == 3 ? launch_nadic_shape<4, 3>(this, l) : launch_nadic_shape<4, 1>(this, l);
+    if (sh.tpi == 8) return launch_nadic_shape<64, 8, 1>(this, l);
+    return sh.minb == 3 ? launch_nadic_shape<64, 4, 3>(this, l) : launch_nadic_shape<64, 4, 1>(this, l);
 }
-int tecdsa_ctx::nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows) {
+int tecdsa_ctx::nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows, int K) {
     if (rows <= 0) return 0;
     const int per_block = JOB_BLOCK / 8;
-    nadic_setup_kernel<64, 8><<<(rows + per_block - 1) / per_block, JOB_BLOCK, 0, stream>>>(n_tab, out, rows);
+    if (K == 32) nadic_setup_kernel<32, 8><<<(rows + per_block - 1) / per_block, JOB_BLOCK, 0, stream>>>(n_tab, out, rows);
+    else nadic_setup_kernel<64, 8><<<(rows + per_block - 1) / per_block, JOB_BLOCK, 0, stream>>>(n_tab, out, rows);
     count_launch();
     CK(cudaGetLastError());
     return 0;

@@ -16,6 +16,8 @@ constexpr int TPI_2048 = 4;
 constexpr int TPI_4096 = 8;
 // N-adic jobs modulo N^2: lane groups are N wide (64 limbs).  Shape of the kernel (lanes per group, min blocks per SM) is a
 // process-wide tuning choice; TECDSA_NADIC_SHAPE="<tpi>,<minb>" overrides the default for measurements.
+constexpr int TPI_NADIC32 = 4;   // p-adic jobs modulo p^2, q^2 (32-limb primes): 8 limbs per lane
+constexpr int NADIC_ROW = 10;    // constants row of a modulus: 10 * K limbs (nadic.cuh)
 int tecdsa_nadic_tpi();
 int tecdsa_nadic_minb();
 }  // namespace tecdsa
@@ -36,7 +38,9 @@ struct tecdsa_keyset {
     uint32_t* tab[tecdsa::KT_COUNT] = {};
     uint32_t* ypk = nullptr;
     uint32_t* fb = nullptr;      // fixed-base tables of (h1, h2) per key row, see jobs.cuh
-    uint32_t* nadic = nullptr;   // [rows][6*64] N-adic constants of the Paillier moduli, see nadic.cuh
+    uint32_t* nadic = nullptr;   // [rows][10*64] N-adic constants of the Paillier moduli N, see nadic.cuh
+    uint32_t* nadic_p = nullptr; // [rows][10*32] the same for the primes p and q (jobs modulo p^2, q^2)
+    uint32_t* nadic_q = nullptr;
     int n_keysets = 0;
 };
 
@@ -63,6 +67,6 @@ struct tecdsa_ctx {
     int reserve_arena(size_t bytes);
     int launch_exp(const tecdsa::ExpLaunch& l, int K);
     int launch_inv(const tecdsa::InvLaunch& l, int K);
-    int launch_nadic(const tecdsa::ExpLaunch& l);                               // every class modulo N^2 (ExpClass::nadic set)
-    int nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows);           // device pointers; out = [rows][6*64]
+    int launch_nadic(const tecdsa::ExpLaunch& l, int K);                        // every class modulo a square (ExpClass::nadic set); K = limbs of the root
+    int nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows, int K);    // device pointers; out = [rows][NADIC_ROW*K]
 };

@@ -20,7 +20,7 @@ struct Builder {
     const tecdsa_keyset* ks;
     Arena A;
     int U;
-    ExpLaunch L32, L64, L128;
+    ExpLaunch L32, L64, L128, LPQ;      // 1024-bit, 2048-bit, N-adic mod N^2, p-adic mod p^2 / q^2
     InvLaunch I64, I128;
 
     Operand fld(int f, int limbs = 0) const {
@@ -38,19 +38,28 @@ struct Builder {
 
     static void reset(ExpLaunch& l) { l.n_classes = 0; l.total_items = 0; }
     static void reset(InvLaunch& l) { l.n_classes = 0; l.total_items = 0; }
+    // Jobs modulo a square whose root the key tables hold (N^2, and the unit's own p^2 / q^2) are routed to the N-adic
+    // lists (nadic.cuh: same value, about half the MACs of the double-width Montgomery product); `l` / `gpw` then only say
+    // where the class would have gone otherwise.
     void exp_class(ExpLaunch& l, int gpw, Operand mod, int nb, Operand b0, Operand e0, int el0, Operand b1, Operand e1, int el1,
                    int nm, Operand m0, Operand m1, int out_field, int wide0 = 0, Operand m2 = Operand{nullptr, nullptr, 0, 0, 0}) {
-        ExpClass& k = l.cls[l.n_classes++];
+        ExpLaunch* dst = &l;
+        Operand nadic = Operand{nullptr, nullptr, 0, 0, 0};
+        if (mod.ptr == A.key[KT_NN]) {
+            dst = &L128; gpw = 32 / tecdsa_nadic_tpi();
+            mod = key(KT_N, mod.idx); nadic = Operand{ks->nadic, mod.idx, NADIC_ROW * 64, 1, NADIC_ROW * 64};
+        } else if (mod.ptr == A.key[KT_PP] || mod.ptr == A.key[KT_QQ]) {
+            const bool is_p = mod.ptr == A.key[KT_PP];
+            dst = &LPQ; gpw = 32 / TPI_NADIC32; wide0 = 0;      // operand width is handled by the lift (any width up to 4K)
+            mod = key(is_p ? KT_P : KT_Q, mod.idx); nadic = Operand{is_p ? ks->nadic_p : ks->nadic_q, mod.idx, NADIC_ROW * 32, 1, NADIC_ROW * 32};
+        }
+        ExpClass& k = dst->cls[dst->n_classes++];
         k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
         k.mul[0] = m0; k.mul[1] = m1; k.mul[2] = m2; k.nbases = nb; k.nmul = nm; k.wide0 = wide0;
         k.fb = nullptr; k.fb_row = Operand{nullptr, nullptr, 0, 0, 0}; k.fb_sel[0] = k.fb_sel[1] = 0;
-        k.nadic = Operand{nullptr, nullptr, 0, 0, 0};
-        if (mod.ptr == A.key[KT_NN]) {      // every job modulo a Paillier N^2 runs in N-adic form (nadic.cuh): same value, ~2/3 of the MACs
-            k.mod = key(KT_N, mod.idx);
-            k.nadic = Operand{ks->nadic, mod.idx, 6 * 64, 1, 6 * 64};
-        }
-        k.out = out(out_field); k.out_stride = A.size[out_field]; k.count = U; k.item_begin = l.total_items;
-        l.total_items += (U + gpw - 1) / gpw;
+        k.nadic = nadic;
+        k.out = out(out_field); k.out_stride = A.size[out_field]; k.count = U; k.item_begin = dst->total_items;
+        dst->total_items += (U + gpw - 1) / gpw;
     }
     // out = [m0 *] h2^e_h2 * h1^e_h1 mod N_tilde(rows) through the per-key fixed-base tables
     void fb_class(ExpLaunch& l, int gpw, const uint32_t* rows, Operand e_h2, int el_h2, Operand e_h1, int el_h1, int nm, Operand m0, int out_field) {
@@ -158,15 +167,19 @@ extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_ke
         CK(cudaGetLastError());
     }
     {   // N-adic constants of every Paillier modulus (KT_N was derived by gg20_key_setup above)
-        CK(cudaMalloc(&ks->nadic, (size_t)rows * 6 * 64 * 4));
-        int rc = c->nadic_setup(ks->tab[KT_N], ks->nadic, rows);
+        CK(cudaMalloc(&ks->nadic, (size_t)rows * NADIC_ROW * 64 * 4));
+        CK(cudaMalloc(&ks->nadic_p, (size_t)rows * NADIC_ROW * 32 * 4));
+        CK(cudaMalloc(&ks->nadic_q, (size_t)rows * NADIC_ROW * 32 * 4));
+        int rc = c->nadic_setup(ks->tab[KT_N], ks->nadic, rows, 64);
+        if (!rc) rc = c->nadic_setup(ks->tab[KT_P], ks->nadic_p, rows, 32);
+        if (!rc) rc = c->nadic_setup(ks->tab[KT_Q], ks->nadic_q, rows, 32);
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(c->stream));
     // parity bits of the uploaded moduli are validated on the host copy of the inputs only
     for (int r = 0; r < rows; r++) {
         if (!(k->paillier_p[(size_t)r * 32] & 1) || !(k->paillier_q[(size_t)r * 32] & 1) || !(k->n_tilde[(size_t)r * 64] & 1)) {
-            cudaFree(ks->mem); cudaFree(ks->fb); cudaFree(ks->nadic); delete ks;
+            cudaFree(ks->mem); cudaFree(ks->fb); cudaFree(ks->nadic); cudaFree(ks->nadic_p); cudaFree(ks->nadic_q); delete ks;
             return tecdsa_fail(TECDSA_E_ARG, "keys_upload: even modulus");
         }
     }
@@ -179,6 +192,8 @@ extern "C" int tecdsa_keys_free(tecdsa_ctx* c, tecdsa_keyset* ks) {
     if (ks->mem) cudaFree(ks->mem);
     if (ks->fb) cudaFree(ks->fb);
     if (ks->nadic) cudaFree(ks->nadic);
+    if (ks->nadic_p) cudaFree(ks->nadic_p);
+    if (ks->nadic_q) cudaFree(ks->nadic_q);
     delete ks;
     return 0;
 }
@@ -192,7 +207,7 @@ extern "C" int tecdsa_keys_table(tecdsa_ctx* c, const tecdsa_keyset* ks, int tab
 // ------------------------------------------------------------------------------------------ job launches
 static int run_exp(tecdsa_ctx* c, ExpLaunch& l, int K) {
     if (l.n_classes == 0) return 0;
-    int rc = K == 128 ? c->launch_nadic(l) : c->launch_exp(l, K);       // the 4096-bit list is all modulo N^2
+    int rc = K == 128 ? c->launch_nadic(l, 64) : K == -32 ? c->launch_nadic(l, 32) : c->launch_exp(l, K);   // 128: N-adic mod N^2, -32: p-adic
     l.n_classes = 0; l.total_items = 0;
     return rc;
 }
@@ -257,8 +272,8 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
 
     ExpLaunch &L32 = B.L32, &L64 = B.L64, &L128 = B.L128;
     InvLaunch &I64 = B.I64, &I128 = B.I128;
-    Builder::reset(L32); Builder::reset(L64); Builder::reset(L128); Builder::reset(I64); Builder::reset(I128);
-    const int GPW128 = 32 / tecdsa_nadic_tpi();
+    Builder::reset(L32); Builder::reset(L64); Builder::reset(L128); Builder::reset(B.LPQ); Builder::reset(I64); Builder::reset(I128);
+    const int GPW128 = 0;        // classes modulo N^2 are routed (and sized) by Builder::exp_class
     const uint32_t *ro = A.row_own, *rp = A.row_peer;
     auto st_rows = [&](int x) { return A.row_st + (size_t)x * U; };
 #define RUN(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
@@ -279,7 +294,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         // z = h1^a * h2^ro mod N_tilde                                  (range_proofs.rs:52)
         B.fb_class(L64, GPW64, st_rows(x), B.rnd(al + RND_AL_RHO, 72), 72, B.rnd(RND_K, 8), 8, 0, NONE, F_Z0 + x);
     }
-    RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
     RUN(glue_crt(c, A, 0, 4));
     B.exp_class(L128, GPW128, B.key(KT_NN, ro), 0, NONE, NONE, 0, NONE, NONE, 0, 2, B.fld(F_MK), B.fld(F_XC0), F_CK);
     for (int x = 0; x < 3; x++)
@@ -289,7 +304,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     for (int x = 0; x < 3; x++)    // s = r^e * beta mod N                (range_proofs.rs:86)
         B.exp_class(L64, GPW64, B.key(KT_N, ro), 1, B.rnd(RND_RK, 64), B.fld(F_E0 + x), 8, NONE, NONE, 0, 1,
                     B.rnd(RND_AL + x * RND_AL_STRIDE + RND_AL_BETA, 64), NONE, F_S0 + x);
-    RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
 
     // ================= Round 1 (rounds.rs:122-206): 2 x MessageB::b — the three AliceProof::verify
     // of the peer's MessageA are computed ONCE and used for both calls (declared de-duplication).
@@ -303,7 +318,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 1, B.peer(F_Z0 + x), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_ZE0 + x);   // z^e (:122)
         B.exp_class(L128, GPW128, B.key(KT_NN, rp), 1, B.fld(F_CINVP), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_CEI0 + x);           // (c^-1)^e (:135)
     }
-    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
     for (int x = 0; x < 3; x++) B.inv_class(I64, GPW64, B.key(KT_NT, st_rows(x)), B.fld(F_ZE0 + x), F_ZEI0 + x, x);
     RUN(run_inv(c, I64, 64));
     for (int x = 0; x < 3; x++) {
@@ -315,7 +330,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     // c_b = c_a^b * Enc(beta'; r') mod N^2 for b = gamma_i and b = w_i  (mta/mod.rs:133-145)
     B.exp_class(L128, GPW128, B.key(KT_NN, rp), 2, B.rnd(RND_R_G, 64), B.key(KT_N, rp), 64, B.peer(F_CK), B.rnd(RND_GAMMA, 8), 8, 1, B.fld(F_LBG), NONE, F_CBG);
     B.exp_class(L128, GPW128, B.key(KT_NN, rp), 2, B.rnd(RND_R_W, 64), B.key(KT_N, rp), 64, B.peer(F_CK), B.fld(F_W), 8, 1, B.fld(F_LBW), NONE, F_CBW);
-    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
     RUN(glue(c, gg20_r1_post_hash, A, 3));
     RUN(glue(c, gg20_r1_post_dlog, A, 4));
 
@@ -324,7 +339,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     B.exp_class(L64, GPW64, B.key(KT_QQ, ro), 1, B.peer(F_CBG), B.key(KT_QM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DQG, 1);
     B.exp_class(L64, GPW64, B.key(KT_PP, ro), 1, B.peer(F_CBW), B.key(KT_PM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DPW, 1);
     B.exp_class(L64, GPW64, B.key(KT_QQ, ro), 1, B.peer(F_CBW), B.key(KT_QM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DQW, 1);
-    RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
     RUN(glue(c, gg20_r2_check, A, 3));
     RUN(glue(c, gg20_r2_finish, A));
     // ================= Round 3 (rounds.rs:347-402)
@@ -339,13 +354,13 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     B.crt_stage1(L32, GPW32, ro, 4, B.rnd(RND_PDL_BETA, 64));
     RUN(run_exp(c, L32, 32));
     B.crt_stage2(L64, GPW64, ro, 4);
-    RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
     RUN(glue_crt(c, A, 4, 1));
     B.exp_class(L128, GPW128, B.key(KT_NN, ro), 0, NONE, NONE, 0, NONE, NONE, 0, 2, B.fld(F_PLIN), B.fld(F_XC4), F_PU2);
     RUN(run_exp(c, L128, 128));
     RUN(glue(c, gg20_r4_mid, A));
     B.exp_class(L64, GPW64, B.key(KT_N, ro), 1, B.rnd(RND_RK, 64), B.fld(F_PE), 8, NONE, NONE, 0, 1, B.rnd(RND_PDL_BETA, 64), NONE, F_PS2);   // s2 = r^e * beta mod N (:113)
-    RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
 
     // ================= Round 5 (rounds.rs:525-592): verify both signers' PDL proofs (own one included)
     RUN(glue(c, gg20_r5_pre, A));
@@ -361,7 +376,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     B.crt_stage1(L32, GPW32, ro, 5, B.fld(F_PS2, 64));       // own proof's s2^N mod N^2_own through the CRT stages
     RUN(run_exp(c, L32, 32));
     B.crt_stage2(L64, GPW64, ro, 5);
-    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
     RUN(glue_crt(c, A, 5, 1));
     for (int j = 0; j < 2; j++) B.inv_class(I64, GPW64, B.key(KT_NT, j ? ro : rp), B.fld(F_VZE0 + j), F_VZEI0 + j, 6 + j);
     RUN(run_inv(c, I64, 64));
@@ -375,7 +390,7 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         if (j == 0) B.exp_class(L128, GPW128, B.key(KT_NN, prover), 0, NONE, NONE, 0, NONE, NONE, 0, 3, B.fld(F_VLIN0), B.fld(F_VCEI0), F_VU20, 0, B.fld(F_XC5));
         else B.exp_class(L128, GPW128, B.key(KT_NN, prover), 1, s2, B.key(KT_N, prover), 64, NONE, NONE, 0, 2, B.fld(F_VLIN0 + j), B.fld(F_VCEI0 + j), F_VU20 + j);
     }
-    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, L64, 64));
+    RUN(run_exp(c, L128, 128)); RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
     RUN(glue(c, gg20_r5_check, A, 2));
     RUN(glue(c, gg20_r5_finish, A));
     // ================= Round 6 (rounds.rs:612-636) + result records

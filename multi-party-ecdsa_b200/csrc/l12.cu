@@ -79,12 +79,12 @@ void add_nn(ExpLaunch& l, int count, Operand N, Operand consts, int nb, Operand 
             int nm, Operand m0, Operand m1, uint32_t* out, uint32_t out_stride) {
     add_exp(l, 128, count, N, nb, b0, e0, el0, b1, e1, el1, nm, m0, m1, out, out_stride);
     ExpClass& k = l.cls[l.n_classes - 1];
-    const int gpw = 32 / tecdsa_nadic_tpi();
+    const int gpw = N.limbs == 32 ? 32 / TPI_NADIC32 : 32 / tecdsa_nadic_tpi();
     k.nadic = consts;
     l.total_items = k.item_begin + (count + gpw - 1) / gpw;
 }
 Operand key_n(const tecdsa_keyset* ks, const uint32_t* rows) { return tab(ks->tab[KT_N], rows, 64); }
-Operand key_nadic(const tecdsa_keyset* ks, const uint32_t* rows) { return tab(ks->nadic, rows, 6 * 64); }
+Operand key_nadic(const tecdsa_keyset* ks, const uint32_t* rows) { return tab(ks->nadic, rows, NADIC_ROW * 64); }
 void add_fb(ExpLaunch& l, int count, const tecdsa_keyset* ks, const uint32_t* rows, Operand e_h2, int el_h2, Operand e_h1, int el_h1,
             int nm, Operand m0, uint32_t* out) {
     add_exp(l, 64, count, tab(ks->tab[KT_NT], rows, 64), 2, NONE, e_h2, el_h2, NONE, e_h1, el_h1, nm, m0, NONE, out, 64);
@@ -103,9 +103,9 @@ int run(tecdsa_ctx* c, ExpLaunch& l, int K) {
     l.n_classes = l.total_items = 0;
     return rc;
 }
-int run_nn(tecdsa_ctx* c, ExpLaunch& l) {
+int run_nn(tecdsa_ctx* c, ExpLaunch& l, int K = 64) {
     if (!l.n_classes) return 0;
-    int rc = c->launch_nadic(l);
+    int rc = c->launch_nadic(l, K);
     l.n_classes = l.total_items = 0;
     return rc;
 }
@@ -498,13 +498,13 @@ extern "C" int tecdsa_paillier_encrypt_batch(tecdsa_ctx* c, const uint32_t* n, c
     Stage S(c, mem);
     const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *dm = S.in(m, count * 64), *dr = S.in(r, count * 64);
     uint32_t* dc = S.out(c_out, count * 128);
-    uint32_t *nd = S.tmp<uint32_t>(nk * 6 * 64), *lin = S.tmp<uint32_t>(count * 128);
+    uint32_t *nd = S.tmp<uint32_t>(nk * NADIC_ROW * 64), *lin = S.tmp<uint32_t>(count * 128);
     if (S.err) return S.finish();
-    RUN(c->nadic_setup(dn, nd, (int)nk));
+    RUN(c->nadic_setup(dn, nd, (int)nk, 64));
     k_lin<<<grid_for(count), 64, 0, c->stream>>>(lin, dm, 64, dn, di, (int)count);
     KCHECK();
     Launches L;
-    Operand N = di ? tab(dn, di, 64) : arr(dn, 64), ND = di ? tab(nd, di, 6 * 64) : arr(nd, 6 * 64);
+    Operand N = di ? tab(dn, di, 64) : arr(dn, 64), ND = di ? tab(nd, di, NADIC_ROW * 64) : arr(nd, NADIC_ROW * 64);
     Operand rb = arr(dr, 64);
     add_nn(L.e128, (int)count, N, ND, 1, rb, N, 64, NONE, NONE, 0, 1, arr(lin, 128), NONE, dc, 128);     // (1 + m n) * r^n mod n^2
     RUN(run_nn(c, L.e128));
@@ -520,11 +520,11 @@ extern "C" int tecdsa_paillier_mul_batch(tecdsa_ctx* c, const uint32_t* n, const
     Stage S(c, mem);
     const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *dct = S.in(ct, count * 128), *dk = S.in(k, count * (size_t)k_limbs);
     uint32_t* dc = S.out(c_out, count * 128);
-    uint32_t* nd = S.tmp<uint32_t>(nk * 6 * 64);
+    uint32_t* nd = S.tmp<uint32_t>(nk * NADIC_ROW * 64);
     if (S.err) return S.finish();
-    RUN(c->nadic_setup(dn, nd, (int)nk));
+    RUN(c->nadic_setup(dn, nd, (int)nk, 64));
     Launches L;
-    add_nn(L.e128, (int)count, di ? tab(dn, di, 64) : arr(dn, 64), di ? tab(nd, di, 6 * 64) : arr(nd, 6 * 64), 1, arr(dct, 128), arr(dk, k_limbs), k_limbs, NONE, NONE, 0, 0, NONE, NONE, dc, 128);
+    add_nn(L.e128, (int)count, di ? tab(dn, di, 64) : arr(dn, 64), di ? tab(nd, di, NADIC_ROW * 64) : arr(nd, NADIC_ROW * 64), 1, arr(dct, 128), arr(dk, k_limbs), k_limbs, NONE, NONE, 0, 0, NONE, NONE, dc, 128);
     RUN(run_nn(c, L.e128));
     return S.finish();
 }
@@ -538,11 +538,11 @@ extern "C" int tecdsa_paillier_add_batch(tecdsa_ctx* c, const uint32_t* n, const
     Stage S(c, mem);
     const uint32_t *dn = S.in(n, nk * 64), *di = S.in(key_idx, count), *d1 = S.in(c1, count * 128), *d2 = S.in(c2, count * 128);
     uint32_t* dc = S.out(c_out, count * 128);
-    uint32_t* nd = S.tmp<uint32_t>(nk * 6 * 64);
+    uint32_t* nd = S.tmp<uint32_t>(nk * NADIC_ROW * 64);
     if (S.err) return S.finish();
-    RUN(c->nadic_setup(dn, nd, (int)nk));
+    RUN(c->nadic_setup(dn, nd, (int)nk, 64));
     Launches L;
-    add_nn(L.e128, (int)count, di ? tab(dn, di, 64) : arr(dn, 64), di ? tab(nd, di, 6 * 64) : arr(nd, 6 * 64), 0, NONE, NONE, 0, NONE, NONE, 0, 2, arr(d1, 128), arr(d2, 128), dc, 128);
+    add_nn(L.e128, (int)count, di ? tab(dn, di, 64) : arr(dn, 64), di ? tab(nd, di, NADIC_ROW * 64) : arr(nd, NADIC_ROW * 64), 0, NONE, NONE, 0, NONE, NONE, 0, 2, arr(d1, 128), arr(d2, 128), dc, 128);
     RUN(run_nn(c, L.e128));
     return S.finish();
 }
@@ -559,11 +559,10 @@ extern "C" int tecdsa_paillier_decrypt_batch(tecdsa_ctx* c, const tecdsa_keyset*
     if (S.err) return S.finish();
     Launches L;
     Operand cw = arr(dct, 128);
-    add_exp(L.e64, 64, (int)count, tab(ks->tab[KT_PP], dr, 64), 1, cw, tab(ks->tab[KT_PM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dp, 64);
-    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
-    add_exp(L.e64, 64, (int)count, tab(ks->tab[KT_QQ], dr, 64), 1, cw, tab(ks->tab[KT_QM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dq, 64);
-    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
-    RUN(run(c, L.e64, 64));
+    // c^(p-1) mod p^2 and c^(q-1) mod q^2 in p-adic form (nadic.cuh); the 128-limb ciphertext is lifted as four K-limb parts
+    add_nn(L.e128, (int)count, tab(ks->tab[KT_P], dr, 32), tab(ks->nadic_p, dr, NADIC_ROW * 32), 1, cw, tab(ks->tab[KT_PM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dp, 64);
+    add_nn(L.e128, (int)count, tab(ks->tab[KT_Q], dr, 32), tab(ks->nadic_q, dr, NADIC_ROW * 32), 1, cw, tab(ks->tab[KT_QM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dq, 64);
+    RUN(run_nn(c, L.e128, 32));
     k_decrypt_finish<<<grid_for(count), 64, 0, c->stream>>>(key_arena(ks), dm, dp, dq, dr, (int)count);
     KCHECK();
     return S.finish();
@@ -1009,11 +1008,10 @@ extern "C" int tecdsa_mta_get_alpha_batch(tecdsa_ctx* c, const tecdsa_keyset* ks
     if (S.err) return S.finish();
     Launches L;
     Operand cw = arr(dcb, 128);
-    add_exp(L.e64, 64, n, tab(ks->tab[KT_PP], dr, 64), 1, cw, tab(ks->tab[KT_PM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dp, 64);
-    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
-    add_exp(L.e64, 64, n, tab(ks->tab[KT_QQ], dr, 64), 1, cw, tab(ks->tab[KT_QM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dq, 64);
-    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
-    RUN(run(c, L.e64, 64));
+    // c^(p-1) mod p^2 and c^(q-1) mod q^2 in p-adic form (nadic.cuh); the 128-limb ciphertext is lifted as four K-limb parts
+    add_nn(L.e128, n, tab(ks->tab[KT_P], dr, 32), tab(ks->nadic_p, dr, NADIC_ROW * 32), 1, cw, tab(ks->tab[KT_PM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dp, 64);
+    add_nn(L.e128, n, tab(ks->tab[KT_Q], dr, 32), tab(ks->nadic_q, dr, NADIC_ROW * 32), 1, cw, tab(ks->tab[KT_QM1], dr, 32), 32, NONE, NONE, 0, 0, NONE, NONE, dq, 64);
+    RUN(run_nn(c, L.e128, 32));
     k_mta_alpha<<<grid_for(count), 64, 0, c->stream>>>(key_arena(ks), dr, dp, dq, da, dbp, dtp, dpl, dal, dst, n);
     KCHECK();
     return S.finish();

@@ -8,13 +8,14 @@
 // (0 <= x0, x1 < N) and all work is done modulo N (K limbs, R = 2^(32K)):
 //
 //   X*Y*R^-1 mod N^2,  with  t = X0*Y0,  u' = (t + m*N)/R  (the Montgomery step, quotient number m):
-//       Z0 = u' mod N,   Z1 = montmul(X0,Y1) + montmul(X1,Y0) - m*R^-1 + [u' >= N]   (mod N)
+//       Z0 = u' mod N,   Z1 = (X0*Y1 + X1*Y0 - m) * R^-1 + [u' >= N]   (mod N)
 //
 // (t = u'*R - m*N, so t*R^-1 = u' - N*(m*R^-1) mod N^2, and N*x mod N^2 only depends on x mod N.)
-// A squaring costs 2.5 K-limb products (5K^2 MACs), a multiplication 3.5 (7K^2), against 4 (8K^2)
-// for the direct 2K-limb product.  The values are identical: operands come in and results go out
-// as plain 2K-limb integers.  Per-key constants (digits of R, R^2, R^3 mod N^2) are built at key
-// upload by nadic_setup_kernel.
+// Z1 is ONE interleaved Montgomery reduction over both cross products with -m folded into the
+// starting accumulator, so a multiplication costs 2K^2 + 3K^2 = 5K^2 MACs and a squaring 4K^2
+// (cross term X0 * (2*X1 mod N)), against 8K^2 for the direct 2K-limb Montgomery product.  The
+// values are identical: operands come in and results go out as plain 2K-limb integers.  Per-key
+// constants (digits of R, R^2, R^3 mod N^2) are built at key upload by nadic_setup_kernel.
 #pragma once
 #include "jobs.cuh"
 
@@ -50,66 +51,114 @@ __device__ __forceinline__ void mod_inc(uint32_t (&r)[L], uint32_t c, const uint
     mod_add<TPI, L>(r, r, one, n);
 }
 
-// Z = X*Y*R^-1 mod N^2 in digits; `sq` => Y is taken to be X.  X0 may be any value < R (a plain,
-// non-canonical low digit with X1 = 0 is how plain operands are lifted); everything else canonical.
-// The up-to-three K-limb products run through ONE copy of the row loop (operands selected per
-// phase) to keep the instruction footprint of the exponentiation loop small.
-template <int TPI, int L>
-__device__ __forceinline__ void nadic_mul(Dig<L>& Z, const Dig<L>& X, const Dig<L>& Y, bool sq, const uint32_t (&n)[L], uint32_t n0inv) {
+// One row of the fused product: the accumulator pair takes x0*b (and x1*b2 when THREE), then the Montgomery step.
+template <int TPI, int L, bool THREE>
+__device__ __forceinline__ uint32_t nadic_row(uint32_t (&A)[L + 2], uint32_t (&B)[L + 2], const uint32_t (&x0)[L], const uint32_t (&x1)[L],
+                                              const uint32_t (&n)[L], uint32_t b, uint32_t b2, uint32_t n0inv, uint32_t inc, uint32_t& q_out) {
+    B[L] = add_cc(B[L], inc);
+    B[L + 1] = addc(0, 0);
+    A[0] = add_cc(A[0], B[1]);
+    madc_odd_rshift<L>(B, x0, b);
+    mad_even<L>(A, x0, b);
+    if (THREE) {
+        mad_odd<L>(B, x1, b2);
+        mad_even<L>(A, x1, b2);
+    }
+    uint32_t q = __shfl_sync(FULL, A[0] * n0inv, 0, TPI);
+    q_out = q;
+    mad_odd<L>(B, n, q);
+    mad_even<L>(A, n, q);
+    uint32_t dn = __shfl_down_sync(FULL, A[0], 1, TPI);
+    return (group_lane<TPI>() == TPI - 1) ? 0u : dn;
+}
+// All K rows of one pass over accumulators E/O (pre-loaded by the caller): sum_i (x0*b[i] + [THREE] x1*b2[i] + q_i*n) 2^(32i),
+// divided by R.  REC keeps the quotient digits (lane g its own L).  Result: T (K limbs), return = words above them.
+template <int TPI, int L, bool THREE, bool REC>
+__device__ __forceinline__ uint32_t nadic_pass(uint32_t (&T)[L], uint32_t (&E)[L + 2], uint32_t (&O)[L + 2], const uint32_t (&x0)[L],
+                                               const uint32_t (&x1)[L], const uint32_t (&b)[L], const uint32_t (&b2)[L], const uint32_t (&n)[L],
+                                               uint32_t n0inv, uint32_t (&m)[L]) {
     const int gl = group_lane<TPI>();
-    uint32_t u[L], w[L];
-    uint32_t uc = 0;
-#pragma unroll
-    for (int j = 0; j < L; j++) { u[j] = 0; w[j] = 0; }
+    uint32_t inc = 0;
 #pragma unroll 1
-    for (int p = 0; p < 3; p++) {
-        if (p == 1 && sq) continue;
-        // p = 0: X0*Y0 (records the quotient digits m)   p = 1: X1*Y0   p = 2: X0*Y1
-        uint32_t a[L], m[L];
+    for (int gi = 0; gi < TPI; gi++) {
+        const bool rec = gi == gl;
 #pragma unroll
-        for (int j = 0; j < L; j++) { a[j] = (p == 1) ? X.d1[j] : X.d0[j]; m[j] = 0; }
-        uint32_t E[L + 2], O[L + 2];
-#pragma unroll
-        for (int j = 0; j < L + 2; j++) { E[j] = 0; O[j] = 0; }
-        uint32_t inc = 0;
-        const bool hi_b = p == 2;
-#pragma unroll 1
-        for (int gi = 0; gi < TPI; gi++) {
-            const bool rec = (gi == gl) && (p == 0);
-#pragma unroll
-            for (int li = 0; li < L; li += 2) {
-                const uint32_t s0 = sq ? (hi_b ? X.d1[li] : X.d0[li]) : (hi_b ? Y.d1[li] : Y.d0[li]);
-                const uint32_t s1 = sq ? (hi_b ? X.d1[li + 1] : X.d0[li + 1]) : (hi_b ? Y.d1[li + 1] : Y.d0[li + 1]);
-                uint32_t b0 = __shfl_sync(FULL, s0, gi, TPI);
-                uint32_t b1 = __shfl_sync(FULL, s1, gi, TPI);
-                uint32_t q0, q1;
-                inc = mont_row_q<TPI, L>(E, O, a, n, b0, n0inv, inc, q0);
-                inc = mont_row_q<TPI, L>(O, E, a, n, b1, n0inv, inc, q1);
-                if (rec) { m[li] = q0; m[li + 1] = q1; }
+        for (int li = 0; li < L; li += 2) {
+            const uint32_t b0 = __shfl_sync(FULL, b[li], gi, TPI);
+            const uint32_t b1 = __shfl_sync(FULL, b[li + 1], gi, TPI);
+            uint32_t c0 = 0, c1 = 0;
+            if (THREE) {
+                c0 = __shfl_sync(FULL, b2[li], gi, TPI);
+                c1 = __shfl_sync(FULL, b2[li + 1], gi, TPI);
             }
+            uint32_t q0, q1;
+            inc = nadic_row<TPI, L, THREE>(E, O, x0, x1, n, b0, c0, n0inv, inc, q0);
+            inc = nadic_row<TPI, L, THREE>(O, E, x0, x1, n, b1, c1, n0inv, inc, q1);
+            if (REC && rec) { m[li] = q0; m[li + 1] = q1; }
         }
-        uint32_t T[L], D[L];
-        const uint32_t ov = rows_finish<TPI, L>(T, E, O, inc);
+    }
+    return rows_finish<TPI, L>(T, E, O, inc);
+}
+// value = ov * R + T < 3N  ->  canonical T; returns how many times N was subtracted
+template <int TPI, int L>
+__device__ __forceinline__ uint32_t reduce_twice(uint32_t (&T)[L], uint32_t ov, const uint32_t (&n)[L]) {
+    uint32_t cnt = 0;
+#pragma unroll 1
+    for (int r = 0; r < 2; r++) {
+        uint32_t D[L];
 #pragma unroll
         for (int j = 0; j < L; j++) D[j] = T[j];
         const uint32_t ge = group_sub_masked<TPI, L>(D, n, 0xffffffffu, 1u);
         const bool take = (ov | ge) != 0;
 #pragma unroll
         for (int j = 0; j < L; j++) T[j] = take ? D[j] : T[j];
-        if (p == 0) {
-            uc = take ? 1u : 0u;
-#pragma unroll
-            for (int j = 0; j < L; j++) u[j] = T[j];
-            mont_redc<TPI, L>(T, m, n, n0inv);                 // m * R^-1 mod N
-            mod_sub<TPI, L>(w, w, T, n);                       // w = -m R^-1
-        } else {
-            mod_add<TPI, L>(w, w, T, n);
-            if (sq) mod_add<TPI, L>(w, w, T, n);
-        }
+        if (take) { cnt++; if (!ge) ov--; }
     }
-    mod_inc<TPI, L>(w, uc, n);
+    return cnt;
+}
+
+// Z = X*Y*R^-1 mod N^2 in digits, in two passes of K rows:
+//   pass 0:  u' = (X0*Y0 + m*N)/R, recording the quotient digits m;        Z0 = u' mod N, uc = [u' >= N]
+//   pass 1:  (X0*Y1 + X1*Y0 - m) * R^-1 mod N in one interleaved reduction: the accumulator starts at ~m + 1
+//            (T - m = T + ~m + 1 - R, and R*R^-1 = 1), so Z1 = redc(T + ~m + 1) - 1 + uc.
+// Cost 5K^2 MACs; 4K^2 with `cross2` false, which drops the X1*Y0 term — valid when X1 == 0 (lifting a plain operand: X0
+// may then be any value < R) or when the caller passes Y = (X0, 2*X1 mod N) to square X.  Y is canonical, X1 < N.
+template <int TPI, int L>
+__device__ __forceinline__ void nadic_mul(Dig<L>& Z, const Dig<L>& X, const Dig<L>& Y, bool cross2, const uint32_t (&n)[L], uint32_t n0inv) {
+    const int gl = group_lane<TPI>();
+    uint32_t u[L], m[L], T[L];
+    uint32_t E[L + 2], O[L + 2];
 #pragma unroll
-    for (int j = 0; j < L; j++) { Z.d0[j] = u[j]; Z.d1[j] = w[j]; }
+    for (int j = 0; j < L; j++) m[j] = 0;
+#pragma unroll
+    for (int j = 0; j < L + 2; j++) { E[j] = 0; O[j] = 0; }
+    uint32_t ov = nadic_pass<TPI, L, false, true>(u, E, O, X.d0, X.d1, Y.d0, Y.d0, n, n0inv, m);
+    const uint32_t uc = reduce_twice<TPI, L>(u, ov, n);
+#pragma unroll
+    for (int j = 0; j < L; j++) { E[j] = ~m[j]; O[j] = 0; }
+    E[L] = 0; E[L + 1] = 0; O[L] = 0; O[L + 1] = 0;
+    if (gl == 0) O[1] = 1;                                     // enters column 0 with the first row
+    if (cross2) ov = nadic_pass<TPI, L, true, false>(T, E, O, X.d0, X.d1, Y.d1, Y.d0, n, n0inv, m);
+    else ov = nadic_pass<TPI, L, false, false>(T, E, O, X.d0, X.d1, Y.d1, Y.d0, n, n0inv, m);
+    (void)reduce_twice<TPI, L>(T, ov, n);
+    // Z1 = T - 1 + uc
+    {
+        uint32_t one[L];
+#pragma unroll
+        for (int j = 0; j < L; j++) one[j] = 0;
+        if (gl == 0) one[0] = 1u - uc;
+        mod_sub<TPI, L>(T, T, one, n);
+    }
+#pragma unroll
+    for (int j = 0; j < L; j++) { Z.d0[j] = u[j]; Z.d1[j] = T[j]; }
+}
+
+// Y = (X0, 2*X1 mod N): nadic_mul(Z, X, Y, false) then squares X
+template <int TPI, int L>
+__device__ __forceinline__ void square_operand(Dig<L>& Y, const Dig<L>& X, const uint32_t (&n)[L]) {
+#pragma unroll
+    for (int j = 0; j < L; j++) Y.d0[j] = X.d0[j];
+    mod_add<TPI, L>(Y.d1, X.d1, X.d1, n);
 }
 
 // (A + B) mod N^2 in digits
@@ -143,25 +192,27 @@ __device__ __forceinline__ void store_dig(uint32_t* p, const Dig<L>& D) {
     store_limbs<TPI, L>(p + K, D.d1);
 }
 
-// per-key constants row, 6K limbs: digits of R ("one"), R^2 and R^3 modulo N^2
-static constexpr int NADIC_ONE = 0, NADIC_RR2 = 2, NADIC_RR3 = 4;    // offsets in units of K limbs
+// per-key constants row, NADIC_CONST_K * K limbs: digits of R ("one") and of R^2 .. R^5 modulo N^2
+static constexpr int NADIC_ONE = 0, NADIC_RR2 = 2;                    // offsets in units of K limbs; R^(2+h) at NADIC_RR2 + 2h
+static constexpr int NADIC_CONST_K = 10;
 static constexpr int NADIC_TABLE_ENTRIES = 2 * (1 << WINDOW_BITS) + 1;  // per lane group: two window tables + one parked value, 2K limbs each
 
-// plain operand c = c_hi * R + c_lo (2K limbs, zero-extended from o.limbs, any value) -> Montgomery digits of c mod N^2:
-// (c_hi, 0) * R^3 * R^-1 + (c_lo, 0) * R^2 * R^-1
+// plain operand c = sum_h c_h R^h (up to 4K limbs, zero-extended from o.limbs, any value) -> Montgomery digits of c mod N^2:
+// sum_h (c_h, 0) * R^(h+2) * R^-1
 template <int TPI, int L>
 __device__ __forceinline__ void to_nadic(Dig<L>& X, const Operand& o, int i, const uint32_t* consts, const uint32_t (&n)[L], uint32_t n0inv) {
     constexpr int K = TPI * L;
-    Dig<L> a, c, hi;
+    Dig<L> a, c, part;
 #pragma unroll
-    for (int j = 0; j < L; j++) { a.d1[j] = 0; hi.d0[j] = 0; hi.d1[j] = 0; X.d0[j] = 0; X.d1[j] = 0; }
-    const int halves = o.limbs > (uint32_t)K ? 2 : 1;          // uniform per class
+    for (int j = 0; j < L; j++) { a.d1[j] = 0; part.d0[j] = 0; part.d1[j] = 0; X.d0[j] = 0; X.d1[j] = 0; }
+    int parts = ((int)o.limbs + K - 1) / K;                    // uniform per class
+    if (parts > 4) parts = 4;
 #pragma unroll 1
-    for (int h = 0; h < halves; h++) {
-        load_operand<TPI, L>(a.d0, o, i, h ? (uint32_t)K : 0u);
-        load_dig<TPI, L>(c, consts + (h ? NADIC_RR3 : NADIC_RR2) * K);
-        nadic_mul<TPI, L>(hi, a, c, false, n, n0inv);
-        dig_add<TPI, L>(X, X, hi, n);
+    for (int h = 0; h < parts; h++) {
+        load_operand<TPI, L>(a.d0, o, i, (uint32_t)(h * K));
+        load_dig<TPI, L>(c, consts + (NADIC_RR2 + 2 * h) * K);
+        nadic_mul<TPI, L>(part, a, c, false, n, n0inv);        // a.d1 == 0: no X1*Y0 term
+        dig_add<TPI, L>(X, X, part, n);
     }
 }
 
@@ -223,7 +274,7 @@ nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ t
             const int steps = is_base ? TBL - 2 : 1;
 #pragma unroll 1
             for (int e = 0; e < steps; e++) {
-                nadic_mul<TPI, L>(Y, Y, xr, false, n, n0inv);
+                nadic_mul<TPI, L>(Y, Y, xr, true, n, n0inv);
                 if (is_base) store_dig<TPI, L>(tb + (size_t)(e + 2) * 2 * K, Y);
             }
             if (!is_base) store_dig<TPI, L>(p_slot, Y);
@@ -241,7 +292,7 @@ nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ t
             int w = nw - 1, ph = WINDOW_BITS;
 #pragma unroll 1
             while (w >= -2) {
-                bool do_mul = true, sq = false;
+                bool do_mul = true, cross2 = true;
                 if (w == -1) { load_dig<TPI, L>(Y, p_slot); do_mul = c.nmul > 0; w = -2; }
                 else if (w == -2) {
 #pragma unroll
@@ -249,7 +300,7 @@ nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ t
                     if (gl == 0) Y.d0[0] = 1;
                     w = -3;
                 }
-                else if (ph < WINDOW_BITS) { sq = true; ph++; }
+                else if (ph < WINDOW_BITS) { square_operand<TPI, L>(Y, acc, n); cross2 = false; ph++; }
                 else if (ph == WINDOW_BITS) {
                     if (w < nw0) load_dig<TPI, L>(Y, my_tbl + (size_t)exp_window(e0, c.exp_limbs[0], w) * 2 * K);
                     else do_mul = false;
@@ -259,7 +310,7 @@ nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ t
                     else do_mul = false;
                     ph = 0; w--;
                 }
-                if (do_mul) nadic_mul<TPI, L>(acc, acc, Y, sq, n, n0inv);
+                if (do_mul) nadic_mul<TPI, L>(acc, acc, Y, cross2, n, n0inv);
             }
         }
         // plain value = d0 + d1 * N  (2K limbs)
@@ -282,7 +333,7 @@ nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ t
     }
 }
 
-// One lane-group per key row: digits of R, R^2, R^3 modulo N^2 (N odd, > 1).  R^2 = 2^(64K) comes from doubling (1, 0).
+// One lane-group per key row: digits of R, R^2 .. R^5 modulo N^2 (N odd, > 1).  R^2 = 2^(64K) comes from doubling (1, 0).
 template <int K, int TPI>
 __global__ void __launch_bounds__(128)
 nadic_setup_kernel(const uint32_t* __restrict__ n_tab, uint32_t* __restrict__ out, int rows) {
@@ -293,21 +344,23 @@ nadic_setup_kernel(const uint32_t* __restrict__ n_tab, uint32_t* __restrict__ ou
     uint32_t n[L];
     load_limbs<TPI, L>(n, n_tab + (size_t)row * K);
     const uint32_t n0inv = neg_inv32(__shfl_sync(FULL, n[0], 0, TPI));
-    Dig<L> lift, rr2, t;
+    Dig<L> t, rr2;
 #pragma unroll
-    for (int j = 0; j < L; j++) { lift.d0[j] = 0; lift.d1[j] = 0; }
-    if (group_lane<TPI>() == 0) lift.d0[0] = 1;
-    rr2 = lift;
+    for (int j = 0; j < L; j++) { t.d0[j] = 0; t.d1[j] = 0; }
+    if (group_lane<TPI>() == 0) t.d0[0] = 1;
+    rr2 = t;
 #pragma unroll 1
     for (int i = 0; i < 64 * K; i++) dig_add<TPI, L>(rr2, rr2, rr2, n);
-    uint32_t* o = out + (size_t)row * 6 * K;
-#pragma unroll 1
-    for (int s = 0; s < 2; s++) {
-        // s = 0: 1 * R^2 * R^-1 = R;  s = 1: R^2 * R^2 * R^-1 = R^3
-        nadic_mul<TPI, L>(t, s ? rr2 : lift, rr2, false, n, n0inv);
-        if (live) store_dig<TPI, L>(o + (s ? NADIC_RR3 : NADIC_ONE) * K, t);
-    }
+    uint32_t* o = out + (size_t)row * NADIC_CONST_K * K;
     if (live) store_dig<TPI, L>(o + NADIC_RR2 * K, rr2);
+    // s = 0: (1, 0) * R^2 * R^-1 = R;   s >= 1: R^(s+1) * R^2 * R^-1 = R^(s+2)
+    Dig<L> cur = rr2;
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {
+        nadic_mul<TPI, L>(t, s ? cur : t, rr2, true, n, n0inv);
+        if (s) cur = t;
+        if (live) store_dig<TPI, L>(o + (s ? NADIC_RR2 + 2 * s : NADIC_ONE) * K, t);
+    }
 }
 
 }  // namespace tecdsa
