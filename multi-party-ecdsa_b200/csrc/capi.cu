@@ -72,6 +72,11 @@ extern "C" int tecdsa_ctx_destroy(tecdsa_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int h = 0; h < 2; h++) {
+        if (c->child[h]) tecdsa_ctx_destroy(c->child[h]);
+        if (c->ev_join[h]) cudaEventDestroy(c->ev_join[h]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     // secrets may sit in every scratch buffer: wipe before release (the reference zeroizes its
     // proof round-1 secrets on drop, utilities/mta/range_proofs.rs:26-27)
     char* bufs[3] = {c->ws, c->jobmem, c->arena};
@@ -80,6 +85,7 @@ extern "C" int tecdsa_ctx_destroy(tecdsa_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 3; i++) if (bufs[i]) cudaFree(bufs[i]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
@@ -325,13 +331,16 @@ int tecdsa_ctx::launch_exp(const ExpLaunch& l, int K) {
     return 0;
 }
 namespace {
-struct NadicShape { int tpi = 8, minb = 1; };      // measured: (8,1) 12.0 k, (4,1) 12.0 k, (4,3) 11.7 k party-phases/s
+struct NadicShape { int tpi = 8, minb = 1, tpi32 = 4, minb32 = 1; };
+// TECDSA_NADIC_SHAPE="<tpi>,<minb>[,<tpi32>,<minb32>]": lanes per group and min blocks per SM of the N-adic kernels (K = 64 and K = 32)
 const NadicShape& nadic_shape() {
     static const NadicShape sh = [] {
         NadicShape s;
         if (const char* e = getenv("TECDSA_NADIC_SHAPE")) {
-            int t = 0, b = 0;
-            if (sscanf(e, "%d,%d", &t, &b) == 2 && (t == 4 || t == 8) && (b == 1 || b == 3)) { s.tpi = t; s.minb = t == 8 ? 1 : b; }
+            int t = 0, b = 0, t2 = 0, b2 = 0;
+            const int n = sscanf(e, "%d,%d,%d,%d", &t, &b, &t2, &b2);
+            if (n >= 2 && ((t == 4 && (b == 1 || b == 3)) || (t == 8 && (b == 1 || b == 4)))) { s.tpi = t; s.minb = b; }
+            if (n == 4 && ((t2 == 4 && (b2 == 1 || b2 == 4)) || (t2 == 2 && b2 == 1))) { s.tpi32 = t2; s.minb32 = b2; }
         }
         return s;
     }();
@@ -355,15 +364,19 @@ int launch_nadic_shape(tecdsa_ctx* c, const ExpLaunch& l) {
 }  // namespace
 namespace tecdsa {
 int tecdsa_nadic_tpi() { return nadic_shape().tpi; }
+int tecdsa_nadic32_tpi() { return nadic_shape().tpi32; }
 int tecdsa_nadic_minb() { return nadic_shape().minb; }
 }
 
 int tecdsa_ctx::launch_nadic(const ExpLaunch& l, int K) {
     for (int i = 0; i < l.n_classes; i++)
         if (!l.cls[i].nadic.ptr || l.cls[i].fb) return tecdsa_fail(TECDSA_E_ARG, "launch_nadic: class without N-adic constants");
-    if (K == 32) return launch_nadic_shape<32, TPI_NADIC32, 1>(this, l);
     const NadicShape& sh = nadic_shape();
-    if (sh.tpi == 8) return launch_nadic_shape<64, 8, 1>(this, l);
+    if (K == 32) {
+        if (sh.tpi32 == 2) return launch_nadic_shape<32, 2, 1>(this, l);
+        return sh.minb32 == 4 ? launch_nadic_shape<32, 4, 4>(this, l) : launch_nadic_shape<32, 4, 1>(this, l);
+    }
+    if (sh.tpi == 8) return sh.minb == 4 ? launch_nadic_shape<64, 8, 4>(this, l) : launch_nadic_shape<64, 8, 1>(this, l);
     return sh.minb == 3 ? launch_nadic_shape<64, 4, 3>(this, l) : launch_nadic_shape<64, 4, 1>(this, l);
 }
 int tecdsa_ctx::nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows, int K) {

@@ -16,9 +16,9 @@ constexpr int TPI_2048 = 4;
 constexpr int TPI_4096 = 8;
 // N-adic jobs modulo N^2: lane groups are N wide (64 limbs).  Shape of the kernel (lanes per group, min blocks per SM) is a
 // process-wide tuning choice; TECDSA_NADIC_SHAPE="<tpi>,<minb>" overrides the default for measurements.
-constexpr int TPI_NADIC32 = 4;   // p-adic jobs modulo p^2, q^2 (32-limb primes): 8 limbs per lane
 constexpr int NADIC_ROW = 10;    // constants row of a modulus: 10 * K limbs (nadic.cuh)
 int tecdsa_nadic_tpi();
+int tecdsa_nadic32_tpi();       // p-adic jobs modulo p^2, q^2 (32-limb primes)
 int tecdsa_nadic_minb();
 }  // namespace tecdsa
 
@@ -61,6 +61,11 @@ struct tecdsa_ctx {
     uint64_t launches = 0;
     int tpi[3] = {0, 0, 0};        // modexp_batch override for 1024, 2048, 4096
     int last_U = 0;
+    // large gg20 batches run as two half-batches on two private streams (gg20.cu): the tail of one half's persistent
+    // launch and its latency-bound glue kernels overlap the other half's job lists
+    tecdsa_ctx* child[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    bool owns_stream = false;
     uint32_t last_off[tecdsa::F_COUNT] = {};
 
     void count_launch() { launches++; }

@@ -9,6 +9,9 @@
 #include "gg20_glue.cuh"
 #include "modinv.cuh"
 
+#include <cstdlib>
+#include <string>
+#include <thread>
 #include <vector>
 
 using namespace tecdsa;
@@ -50,7 +53,7 @@ struct Builder {
             mod = key(KT_N, mod.idx); nadic = Operand{ks->nadic, mod.idx, NADIC_ROW * 64, 1, NADIC_ROW * 64};
         } else if (mod.ptr == A.key[KT_PP] || mod.ptr == A.key[KT_QQ]) {
             const bool is_p = mod.ptr == A.key[KT_PP];
-            dst = &LPQ; gpw = 32 / TPI_NADIC32; wide0 = 0;      // operand width is handled by the lift (any width up to 4K)
+            dst = &LPQ; gpw = 32 / tecdsa_nadic32_tpi(); wide0 = 0;      // operand width is handled by the lift (any width up to 4K)
             mod = key(is_p ? KT_P : KT_Q, mod.idx); nadic = Operand{is_p ? ks->nadic_p : ks->nadic_q, mod.idx, NADIC_ROW * 32, 1, NADIC_ROW * 32};
         }
         ExpClass& k = dst->cls[dst->n_classes++];
@@ -159,10 +162,13 @@ extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_ke
     c->count_launch();
     CK(cudaGetLastError());
     {   // fixed-base tables for (h1, h2) mod N_tilde of every key row
-        const size_t fb_limbs = (size_t)rows * 2 * FB_WINDOWS * (1 << WINDOW_BITS) * 64;
+        const size_t fb_limbs = (size_t)rows * 2 * FB_WINDOWS * FB_TBL * 64;
         CK(cudaMalloc(&ks->fb, fb_limbs * 4));
-        const int groups = rows * 2, per_block = 128 / TPI_2048;
-        fb_build_kernel<64, TPI_2048><<<(groups + per_block - 1) / per_block, 128, 0, c->stream>>>(ks->tab[KT_NT], ks->tab[KT_H1], ks->tab[KT_H2], ks->fb, rows);
+        const int per_block = 128 / TPI_2048;
+        fb_chain_kernel<64, TPI_2048><<<(rows * 2 + per_block - 1) / per_block, 128, 0, c->stream>>>(ks->tab[KT_NT], ks->tab[KT_H1], ks->tab[KT_H2], ks->fb, rows);
+        c->count_launch();
+        CK(cudaGetLastError());
+        fb_fill_kernel<64, TPI_2048><<<(rows * 2 * FB_WINDOWS + per_block - 1) / per_block, 128, 0, c->stream>>>(ks->tab[KT_NT], ks->fb, rows);
         c->count_launch();
         CK(cudaGetLastError());
     }
@@ -219,13 +225,9 @@ static int run_inv(tecdsa_ctx* c, InvLaunch& l, int K) {
 }
 
 // ------------------------------------------------------------------------------------------ offline stage
-extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
-                                         const uint32_t* rnd, uint8_t* status, uint32_t* R_out, uint32_t* sigma_out,
-                                         uint32_t* tvec_out, uint32_t* digest_out, int mem) {
-    if (!c || !ks || !sessions || !rnd || !status) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: null argument");
-    if (mem != TECDSA_HOST && mem != TECDSA_DEVICE) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: bad mem");
-    if (n_sessions == 0) return 0;
-    if (n_sessions > (1u << 22)) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: too many sessions");
+static int offline_impl(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
+                        const uint32_t* rnd, uint8_t* status, uint32_t* R_out, uint32_t* sigma_out,
+                        uint32_t* tvec_out, uint32_t* digest_out, int mem) {
     CK(cudaSetDevice(c->device));
     const int U = (int)n_sessions * 2;
 
@@ -413,6 +415,75 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     }
     c->last_U = U;
     memcpy(c->last_off, A.off, sizeof(A.off));
+    if (mem == TECDSA_HOST) CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Batches of at least SPLIT_MIN sessions run as two half-batches on two private streams, driven by two host threads: units
+// are independent, so the results are those of the single-stream run, while the tail of each persistent job-list launch
+// and the latency-bound glue kernels of one half overlap the job lists of the other.  TECDSA_SPLIT=0 turns it off.
+static size_t split_min_sessions() {
+    static const size_t v = [] {
+        const char* e = getenv("TECDSA_SPLIT");
+        return (e && atoi(e) == 0) ? (size_t)-1 : (size_t)2048;
+    }();
+    return v;
+}
+extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
+                                         const uint32_t* rnd, uint8_t* status, uint32_t* R_out, uint32_t* sigma_out,
+                                         uint32_t* tvec_out, uint32_t* digest_out, int mem) {
+    if (!c || !ks || !sessions || !rnd || !status) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: null argument");
+    if (mem != TECDSA_HOST && mem != TECDSA_DEVICE) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: bad mem");
+    if (n_sessions == 0) return 0;
+    if (n_sessions > (1u << 22)) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: too many sessions");
+    if (n_sessions < split_min_sessions()) return offline_impl(c, ks, sessions, n_sessions, rnd, status, R_out, sigma_out, tvec_out, digest_out, mem);
+
+    CK(cudaSetDevice(c->device));
+    for (int h = 0; h < 2; h++) {
+        if (c->child[h]) continue;
+        cudaStream_t s = nullptr;
+        CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        int rc = tecdsa_ctx_create(&c->child[h], c->device, s);
+        if (rc) { cudaStreamDestroy(s); return rc; }
+        c->child[h]->owns_stream = true;
+        CK(cudaEventCreateWithFlags(&c->ev_join[h], cudaEventDisableTiming));
+    }
+    if (!c->ev_fork) CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    // fork: both halves start after everything already queued on the caller's stream (device-resident inputs)
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    const size_t n0 = n_sessions / 2;
+    int rcs[2] = {0, 0};
+    std::string errs[2];
+    auto half = [&](int h) {
+        tecdsa_ctx* cc = c->child[h];
+        const size_t s0 = h ? n0 : 0, ns = h ? n_sessions - n0 : n0, u0 = 2 * s0;
+        cudaSetDevice(cc->device);
+        cudaError_t e = cudaStreamWaitEvent(cc->stream, c->ev_fork, 0);
+        int rc = e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "gg20_offline: fork", e);
+        if (!rc) rc = offline_impl(cc, ks, sessions + 3 * s0, ns, rnd + u0 * RND_LIMBS, status + u0, R_out ? R_out + u0 * 16 : nullptr,
+                                   sigma_out ? sigma_out + u0 * 8 : nullptr, tvec_out ? tvec_out + s0 * 64 : nullptr,
+                                   digest_out ? digest_out + u0 * 8 : nullptr, mem);
+        if (!rc) {
+            e = cudaEventRecord(c->ev_join[h], cc->stream);
+            if (e != cudaSuccess) rc = tecdsa_fail(TECDSA_E_CUDA, "gg20_offline: join", e);
+        }
+        rcs[h] = rc;
+        if (rc) errs[h] = tecdsa_last_error();
+    };
+    const uint64_t l0 = c->child[0]->launches + c->child[1]->launches;
+    std::thread other(half, 1);
+    half(0);
+    other.join();
+    for (int h = 0; h < 2; h++) {
+        if (rcs[h]) { cudaDeviceSynchronize(); return tecdsa_fail(rcs[h], errs[h].c_str()); }
+        CK(cudaStreamWaitEvent(c->stream, c->ev_join[h], 0));
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    const uint64_t dl = c->child[0]->launches + c->child[1]->launches - l0;
+    c->launches += dl;
+    c->last_launches = (int)dl;
+    c->last_U = 0;                                  // debug_field addresses one arena: not available for split batches
     if (mem == TECDSA_HOST) CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -56,7 +56,7 @@ struct ExpClass {
     int wide0;              // base[0] is 2K limbs wide and is reduced mod n first (c mod p^2, kzen-paillier decrypt)
     // fixed-base mode: both bases are per-key constants (h1, h2 of a DLogStatement) whose powers
     // base^(j * 2^(5w)) were tabulated at key upload; the job is then a pure product, no squarings.
-    const uint32_t* fb;     // nullptr = off; else tables [row][2][FB_WINDOWS][32][K] in Montgomery form
+    const uint32_t* fb;     // nullptr = off; else tables [row][2][FB_WINDOWS][FB_TBL][K] in Montgomery form
     Operand fb_row;         // idx -> key row of instance i (ptr unused)
     int fb_sel[2];          // which of the row's two tables base[b] is (0 = h1, 1 = h2)
     // N-adic mode (nadic.cuh, nadic_jobs_kernel only): the job is modulo N^2, `mod` names N and this the key's
@@ -67,7 +67,17 @@ struct ExpClass {
 };
 
 static constexpr int MAX_CLASSES = 64;
-static constexpr int FB_WINDOWS = 589;          // covers 92-limb (2944-bit) exponents
+static constexpr int FB_WINDOW_BITS = 8;        // fixed-base windows are wider than the 5-bit windows of variable bases: no squarings to amortise
+static constexpr int FB_TBL = 1 << FB_WINDOW_BITS;
+static constexpr int FB_WINDOWS = (92 * 32 + FB_WINDOW_BITS - 1) / FB_WINDOW_BITS;   // covers 92-limb (2944-bit) exponents
+// window `w` (FB_WINDOW_BITS wide) of a little-endian limb array
+__device__ __forceinline__ uint32_t fb_window(const uint32_t* __restrict__ e, int exp_limbs, int w) {
+    const int bit = w * FB_WINDOW_BITS;
+    const int limb = bit >> 5, off = bit & 31;
+    const uint32_t lo = __ldg(e + limb);
+    const uint32_t hi = (limb + 1 < exp_limbs) ? __ldg(e + limb + 1) : 0u;
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> off) & (FB_TBL - 1);
+}
 struct ExpLaunch {
     ExpClass cls[MAX_CLASSES];
     int n_classes;
@@ -107,18 +117,23 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
 #pragma unroll
         for (int j = 0; j < L; j++) acc[j] = m.one[j];
         if (c.fb) {
-            // fixed-base product: acc = prod_b prod_w T_b[w][window_w(e_b)]
+            // fixed-base product: acc = prod_b prod_w T_b[w][window_w(e_b)]; the next entry is fetched while the current
+            // product runs
             const size_t row = __ldg(c.fb_row.idx + (size_t)i * c.fb_row.idx_stride);
-            uint32_t bb[L];
+            uint32_t bb[L], nb[L];
 #pragma unroll 1
             for (int b = 0; b < c.nbases; b++) {
-                const uint32_t* tb = c.fb + (row * 2 + c.fb_sel[b]) * (size_t)FB_WINDOWS * TBL * K;
+                const uint32_t* tb = c.fb + (row * 2 + c.fb_sel[b]) * (size_t)FB_WINDOWS * FB_TBL * K;
                 const uint32_t* e = operand_at(c.exp[b], i);
-                const int nwb = (c.exp_limbs[b] * 32 + WINDOW_BITS - 1) / WINDOW_BITS;
+                const int nwb = (c.exp_limbs[b] * 32 + FB_WINDOW_BITS - 1) / FB_WINDOW_BITS;
+                load_limbs<TPI, L>(bb, tb + (size_t)fb_window(e, c.exp_limbs[b], 0) * K);
 #pragma unroll 1
                 for (int w = 0; w < nwb; w++) {
-                    load_limbs<TPI, L>(bb, tb + ((size_t)w * TBL + exp_window(e, c.exp_limbs[b], w)) * K);
+                    const int wn = w + 1 < nwb ? w + 1 : w;
+                    load_limbs<TPI, L>(nb, tb + ((size_t)wn * FB_TBL + fb_window(e, c.exp_limbs[b], wn)) * K);
                     mont_mul<TPI, L>(acc, acc, bb, m.n, m.n0inv);
+#pragma unroll
+                    for (int j = 0; j < L; j++) bb[j] = nb[j];
                 }
             }
         } else {
@@ -210,14 +225,14 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
     }
 }
 
-// One lane-group per (key row, base): T[w][j] = base^(j * 2^(5w)) * R mod N_tilde for
-// w < FB_WINDOWS, j < 32 (entry 0 = R mod n).  Run once per key upload.
+// Fixed-base tables T[w][j] = base^(j * 2^(FB_WINDOW_BITS * w)) * R mod N_tilde, w < FB_WINDOWS, j < FB_TBL (entry 0 = R mod n),
+// built once per key upload in two steps: the chain of window bases (sequential squarings, one lane-group per (row, base))
+// and the fill of every window (one lane-group per (row, base, window)).
 template <int K, int TPI>
 __global__ void __launch_bounds__(128)
-fb_build_kernel(const uint32_t* __restrict__ mod_tab, const uint32_t* __restrict__ h1_tab, const uint32_t* __restrict__ h2_tab,
+fb_chain_kernel(const uint32_t* __restrict__ mod_tab, const uint32_t* __restrict__ h1_tab, const uint32_t* __restrict__ h2_tab,
                 uint32_t* __restrict__ fb, int rows) {
     constexpr int L = K / TPI;
-    constexpr int TBL = 1 << WINDOW_BITS;
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
     const bool live = g < rows * 2;
     const int gi = live ? g : rows * 2 - 1;
@@ -225,22 +240,38 @@ fb_build_kernel(const uint32_t* __restrict__ mod_tab, const uint32_t* __restrict
     MontCtx<L> m;
     load_limbs<TPI, L>(m.n, mod_tab + (size_t)row * K);
     mont_setup<TPI, L>(m);
-    uint32_t x[L], bw[L], t[L];
+    uint32_t x[L], bw[L];
     load_limbs<TPI, L>(x, (sel ? h2_tab : h1_tab) + (size_t)row * K);
     mont_mul<TPI, L>(bw, x, m.rr, m.n, m.n0inv);                 // base * R
-    uint32_t* tb = fb + (size_t)gi * FB_WINDOWS * TBL * K;
+    uint32_t* tb = fb + (size_t)gi * FB_WINDOWS * FB_TBL * K;
 #pragma unroll 1
     for (int w = 0; w < FB_WINDOWS; w++) {
-        uint32_t* tw = tb + (size_t)w * TBL * K;
+        uint32_t* tw = tb + (size_t)w * FB_TBL * K;
         if (live) { store_limbs<TPI, L>(tw, m.one); store_limbs<TPI, L>(tw + K, bw); }
-#pragma unroll
-        for (int j = 0; j < L; j++) t[j] = bw[j];
 #pragma unroll 1
-        for (int e = 2; e < TBL; e++) {
-            mont_mul<TPI, L>(t, t, bw, m.n, m.n0inv);
-            if (live) store_limbs<TPI, L>(tw + (size_t)e * K, t);
-        }
-        mont_mul<TPI, L>(bw, t, bw, m.n, m.n0inv);               // base^(31 * 2^(5w)) * base^(2^(5w)) = base^(2^(5(w+1)))
+        for (int sq = 0; sq < FB_WINDOW_BITS; sq++) mont_mul<TPI, L>(bw, bw, bw, m.n, m.n0inv);
+    }
+}
+template <int K, int TPI>
+__global__ void __launch_bounds__(128)
+fb_fill_kernel(const uint32_t* __restrict__ mod_tab, uint32_t* __restrict__ fb, int rows) {
+    constexpr int L = K / TPI;
+    const int total = rows * 2 * FB_WINDOWS;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
+    const bool live = g < total;
+    const int gi = live ? g : total - 1;
+    const int row = gi / (2 * FB_WINDOWS);
+    uint32_t n[L], bw[L], t[L];
+    load_limbs<TPI, L>(n, mod_tab + (size_t)row * K);
+    const uint32_t n0inv = neg_inv32(__shfl_sync(FULL, n[0], 0, TPI));
+    uint32_t* tw = fb + (size_t)gi * FB_TBL * K;
+    load_limbs<TPI, L>(bw, tw + K);
+#pragma unroll
+    for (int j = 0; j < L; j++) t[j] = bw[j];
+#pragma unroll 1
+    for (int e = 2; e < FB_TBL; e++) {
+        mont_mul<TPI, L>(t, t, bw, n, n0inv);
+        if (live) store_limbs<TPI, L>(tw + (size_t)e * K, t);
     }
 }
 

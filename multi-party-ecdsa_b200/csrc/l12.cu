@@ -79,7 +79,7 @@ void add_nn(ExpLaunch& l, int count, Operand N, Operand consts, int nb, Operand 
             int nm, Operand m0, Operand m1, uint32_t* out, uint32_t out_stride) {
     add_exp(l, 128, count, N, nb, b0, e0, el0, b1, e1, el1, nm, m0, m1, out, out_stride);
     ExpClass& k = l.cls[l.n_classes - 1];
-    const int gpw = N.limbs == 32 ? 32 / TPI_NADIC32 : 32 / tecdsa_nadic_tpi();
+    const int gpw = N.limbs == 32 ? 32 / tecdsa_nadic32_tpi() : 32 / tecdsa_nadic_tpi();
     k.nadic = consts;
     l.total_items = k.item_begin + (count + gpw - 1) / gpw;
 }

@@ -131,3 +131,26 @@ def test_offline_two_keysets_mixed_batch(engine, pkg):
     res = gg20.offline_batch(engine, ks, sessions, rnd)
     assert not res.status.any()
     ks.free()
+
+
+def test_offline_split_batch_equals_plain_batches(engine, pkg):
+    """batches of >= 2048 sessions run as two half-batches on two streams / host threads (csrc/gg20.cu): every output must
+    equal what the same sessions give in plain single-stream calls (units are independent)."""
+    from mpecdsa_b200 import gg20
+    from tests.golden import fixtures
+    keysets = [fixtures.load_keyset(0), fixtures.load_keyset(1)]
+    ks = gg20.KeySets(engine, keysets)
+    n = 2049                                        # odd: unequal halves
+    sessions, rnd = gg20.synthetic_batch(keysets, n, 11)
+    rnd[7, :] = 0                                   # one unit with degenerate randomness: a failing session inside a half
+    big = gg20.offline_batch(engine, ks, sessions, rnd)
+    for lo, hi in ((0, 700), (700, 1500), (1500, n)):
+        part = gg20.offline_batch(engine, ks, sessions[lo:hi], rnd[2 * lo:2 * hi])
+        assert np.array_equal(part.status, big.status[2 * lo:2 * hi])
+        assert np.array_equal(part.R, big.R[2 * lo:2 * hi])
+        assert np.array_equal(part.sigma, big.sigma[2 * lo:2 * hi])
+        assert np.array_equal(part.digest, big.digest[2 * lo:2 * hi])
+        assert np.array_equal(part.t_vec, big.t_vec[2 * lo:2 * hi])
+    assert big.status[6] != 0 or big.status[7] != 0
+    assert not big.status[8:].any() and not big.status[:6].any()
+    ks.free()
