@@ -145,7 +145,7 @@ class ClockSampler:
 # operation list), ~18 KB moved per unit.
 OFFLINE_SESSIONS = 8192
 W_UNIT = 2.003e9
-W_UNIT_EXECUTED = 0.90e9      # ~109k 64-limb Montgomery products after the declared de-duplication / shortcuts
+W_UNIT_EXECUTED = 0.48e9      # MAC32 actually executed per unit after the declared shortcuts and the N-adic / p-adic forms
 BYTES_PER_UNIT = 18 * 1024
 
 
