@@ -342,7 +342,7 @@ static int offline_impl(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* 
     B.exp_class(L64, GPW64, B.key(KT_PP, ro), 1, B.peer(F_CBW), B.key(KT_PM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DPW, 1);
     B.exp_class(L64, GPW64, B.key(KT_QQ, ro), 1, B.peer(F_CBW), B.key(KT_QM1, ro), 32, NONE, NONE, 0, 0, NONE, NONE, F_DQW, 1);
     RUN(run_exp(c, B.LPQ, -32)); RUN(run_exp(c, L64, 64));
-    RUN(glue(c, gg20_r2_check, A, 3));
+    RUN(glue(c, gg20_r2_check, A, 7));
     RUN(glue(c, gg20_r2_finish, A));
     // ================= Round 3 (rounds.rs:347-402)
     RUN(glue(c, gg20_r3_check, A, 2));

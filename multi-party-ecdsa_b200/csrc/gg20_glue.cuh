@@ -40,7 +40,7 @@ struct Arena {
     __device__ __forceinline__ void fail(int u, uint8_t code) const { if (status[u] == 0) status[u] = code; }
 };
 // FLAGS bytes: 0..2 ZEI ok, 3 peer ciphertext invertible, 6..7 VZEI ok, 8 own ciphertext invertible, 10 range bits, 11..12 MessageB checks ok,
-// 13 g_w_vec ok, 14..15 Pedersen ok, 16..17 PDL ok, 18..19 HomoElGamal ok, 20..22 AliceProof challenge ok
+// 13 g_w_vec ok, 14..15 Pedersen ok, 16..17 PDL ok, 18..19 HomoElGamal ok, 20..22 AliceProof challenge ok, 24..27 MessageB DLogProofs ok
 
 // ------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ U256 load_scalar(const uint32_t* p) { return sc_reduce_once(u256_load(p), 0); }
@@ -233,16 +233,24 @@ static __device__ __noinline__ void decrypt_finish(uint32_t* m64, const Arena& A
     st::mul_add(m64, 64, uu, 32, p, 32, mp, 32);
 }
 // MessageB::verify_proofs_get_alpha (mta/mod.rs:160-179): threads (unit, 0) and (unit, 1) handle the gamma and the
-// w message (Paillier CRT tail, G*alpha == B*k + B', both DLogProofs); thread (unit, 2) the g_w_vec assert
+// w message (Paillier CRT tail, G*alpha == B*k + B'); threads (unit, 2..5) the four DLogProofs; thread (unit, 6) the g_w_vec assert
 // (sign/rounds.rs:281)
 static __global__ void gg20_r2_check(Arena A) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= A.U * 3) return;
-    const int u = t / 3, m = t % 3, pu = A.peer[u];
+    if (t >= A.U * 7) return;
+    const int u = t / 7, job = t % 7, pu = A.peer[u];
     const uint32_t row = A.row_own[u], prow = A.row_peer[u];
-    if (m == 2) {
+    if (job == 6) {
         Affine gw = pt_mul(affine_load(A.k(KT_PK, prow)), lagrange2(prow % 3, row % 3));
         A.flags(u)[13] = affine_eq(gw, affine_load(A.p(F_DL2, pu)));
+        return;
+    }
+    const int m = job & 1;
+    const uint32_t* bp = A.p(m ? F_DL2 : F_DL0, pu);
+    const uint32_t* btp = A.p(m ? F_DL3 : F_DL1, pu);
+    if (job >= 2) {                                  // the two DLogProofs of each MessageB, one thread each
+        const bool second = job >= 4;
+        A.flags(u)[24 + 2 * m + (second ? 1 : 0)] = dlog_verify(second ? btp : bp);
         return;
     }
     // the plaintext goes to the arena (it is also part of the reference's return value, mta/mod.rs:175)
@@ -251,12 +259,9 @@ static __global__ void gg20_r2_check(Arena A) {
     U256 alpha = sc_from_limbs(plain, 64);
     u256_store(A.p(m ? F_MU : F_ALPHA, u), alpha);
     const U256 k = load_scalar(A.p(F_RND, u) + RND_K);
-    const uint32_t* bp = A.p(m ? F_DL2 : F_DL0, pu);
-    const uint32_t* btp = A.p(m ? F_DL3 : F_DL1, pu);
     Affine g_alpha = mul_G(alpha);
     Affine ba_btag = jac_to_affine(jac_add(jac_mul(jac_from_affine(affine_load(bp)), k), jac_from_affine(affine_load(btp))));
-    const bool v1 = dlog_verify(bp), v2 = dlog_verify(btp);
-    A.flags(u)[11 + m] = v1 && v2 && affine_eq(ba_btag, g_alpha);
+    A.flags(u)[11 + m] = affine_eq(ba_btag, g_alpha);
 }
 // phase2_delta_i / phase2_sigma_i (party_i.rs:591-618), phase3_compute_t_i + PedersenProof::prove [R] (party_i.rs:620-634)
 static __global__ void gg20_r2_finish(Arena A) {
@@ -267,7 +272,7 @@ static __global__ void gg20_r2_finish(Arena A) {
     bool ok1 = fl[10] == 0;
     for (int x = 0; x < 3; x++) ok1 = ok1 && fl[x] && fl[3] && fl[20 + x];      // fl[3]: the peer's ciphertext is invertible mod N^2
     if (!ok1) A.fail(u, TECDSA_ST_INVALID_KEY);                    // MessageB::b -> Err(InvalidKey) (mta/mod.rs:123-131)
-    if (!(fl[11] && fl[12] && fl[13])) A.fail(u, TECDSA_ST_INVALID_KEY);
+    if (!(fl[11] && fl[12] && fl[13] && fl[24] && fl[25] && fl[26] && fl[27])) A.fail(u, TECDSA_ST_INVALID_KEY);
     const U256 k = load_scalar(rnd + RND_K), gamma = load_scalar(rnd + RND_GAMMA), w = u256_load(A.p(F_W, u));
     U256 delta = sc_add(sc_add(sc_mul(k, gamma), u256_load(A.p(F_ALPHA, u))), u256_load(A.p(F_BETA_G, u)));
     U256 sigma = sc_add(sc_add(sc_mul(k, w), u256_load(A.p(F_MU, u))), u256_load(A.p(F_NU, u)));
