@@ -238,7 +238,7 @@ static __device__ __noinline__ void decrypt_finish(uint32_t* m64, const Arena& A
 static __global__ void gg20_r2_check(Arena A) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= A.U * 7) return;
-    const int u = t / 7, job = t % 7, pu = A.peer[u];
+    const int job = t / A.U, u = t % A.U, pu = A.peer[u];     // task-major: the threads of a warp run the same kind of check
     const uint32_t row = A.row_own[u], prow = A.row_peer[u];
     if (job == 6) {
         Affine gw = pt_mul(affine_load(A.k(KT_PK, prow)), lagrange2(prow % 3, row % 3));
