@@ -4,6 +4,7 @@
 #include "ctx.h"
 #include "modinv.cuh"
 #include "nadic.cuh"
+#include "nadic_inv.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -365,6 +366,10 @@ int launch_nadic_shape(tecdsa_ctx* c, const ExpLaunch& l) {
 namespace tecdsa {
 int tecdsa_nadic_tpi() { return nadic_shape().tpi; }
 int tecdsa_nadic32_tpi() { return nadic_shape().tpi32; }
+bool tecdsa_hensel_inverse() {
+    static const bool on = [] { const char* e = getenv("TECDSA_HENSEL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
 int tecdsa_nadic_minb() { return nadic_shape().minb; }
 }
 
@@ -378,6 +383,20 @@ int tecdsa_ctx::launch_nadic(const ExpLaunch& l, int K) {
     }
     if (sh.tpi == 8) return sh.minb == 4 ? launch_nadic_shape<64, 8, 4>(this, l) : launch_nadic_shape<64, 8, 1>(this, l);
     return sh.minb == 3 ? launch_nadic_shape<64, 4, 3>(this, l) : launch_nadic_shape<64, 4, 1>(this, l);
+}
+int tecdsa_ctx::launch_nadic_inv(const InvLaunch& l) {
+    for (int i = 0; i < l.n_classes; i++)
+        if (!l.cls[i].nadic.ptr) return tecdsa_fail(TECDSA_E_ARG, "launch_nadic_inv: class without N-adic constants");
+    char* d_desc; unsigned int* d_counter; uint32_t* d_tables;
+    int rc = job_prepare(this, 0, &l, sizeof(InvLaunch), &d_desc, &d_counter, &d_tables);
+    if (rc) return rc;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nadic_inv_kernel<64, TPI_NADIC_INV>, JOB_BLOCK, 0);
+    if (per_sm < 1) per_sm = 1;
+    nadic_inv_kernel<64, TPI_NADIC_INV><<<sm_count * per_sm, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const InvLaunch*>(d_desc), d_counter);
+    count_launch();
+    CK(cudaGetLastError());
+    return 0;
 }
 int tecdsa_ctx::nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows, int K) {
     if (rows <= 0) return 0;

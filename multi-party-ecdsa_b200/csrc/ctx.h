@@ -18,7 +18,9 @@ constexpr int TPI_4096 = 8;
 // process-wide tuning choice; TECDSA_NADIC_SHAPE="<tpi>,<minb>" overrides the default for measurements.
 constexpr int NADIC_ROW = 10;    // constants row of a modulus: 10 * K limbs (nadic.cuh)
 int tecdsa_nadic_tpi();
-int tecdsa_nadic32_tpi();       // p-adic jobs modulo p^2, q^2 (32-limb primes)
+int tecdsa_nadic32_tpi();
+constexpr int TPI_NADIC_INV = 8;
+bool tecdsa_hensel_inverse();   // inverses modulo N^2 through nadic_inv_kernel (TECDSA_HENSEL=0: the 4096-bit Kaliski inversion)       // p-adic jobs modulo p^2, q^2 (32-limb primes)
 int tecdsa_nadic_minb();
 }  // namespace tecdsa
 
@@ -73,5 +75,6 @@ struct tecdsa_ctx {
     int launch_exp(const tecdsa::ExpLaunch& l, int K);
     int launch_inv(const tecdsa::InvLaunch& l, int K);
     int launch_nadic(const tecdsa::ExpLaunch& l, int K);                        // every class modulo a square (ExpClass::nadic set); K = limbs of the root
+    int launch_nadic_inv(const tecdsa::InvLaunch& l);                           // inverses modulo N^2 (InvClass::nadic set), K = 64
     int nadic_setup(const uint32_t* n_tab, uint32_t* out, int rows, int K);    // device pointers; out = [rows][NADIC_ROW*K]
 };

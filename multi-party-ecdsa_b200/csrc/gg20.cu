@@ -24,7 +24,7 @@ struct Builder {
     Arena A;
     int U;
     ExpLaunch L32, L64, L128, LPQ;      // 1024-bit, 2048-bit, N-adic mod N^2, p-adic mod p^2 / q^2
-    InvLaunch I64, I128;
+    InvLaunch I64, I128, I128H;        // I128H: modulo N^2 via the N-wide inversion + Hensel step
 
     Operand fld(int f, int limbs = 0) const {
         return Operand{A.base + (size_t)A.off[f] * U, nullptr, A.size[f], 0, (uint32_t)(limbs ? limbs : A.size[f])};
@@ -87,11 +87,19 @@ struct Builder {
         exp_class(l64, gpw64, key(KT_QQ, rows), 1, fld(F_TQ0 + slot, 32), key(KT_Q, rows), 32, none, none, 0, 0, none, none, F_YQ0 + slot);
     }
     void inv_class(InvLaunch& l, int gpw, Operand mod, Operand in, int out_field, int flag_byte) {
-        InvClass& k = l.cls[l.n_classes++];
+        InvLaunch* dst = &l;
+        Operand nadic = Operand{nullptr, nullptr, 0, 0, 0};
+        if (mod.ptr == A.key[KT_NN] && tecdsa_hensel_inverse()) {     // inverse modulo N plus a Hensel step (nadic_inv.cuh)
+            dst = &I128H; gpw = 32 / TPI_NADIC_INV;
+            mod = key(KT_N, mod.idx); nadic = Operand{ks->nadic, mod.idx, NADIC_ROW * 64, 1, NADIC_ROW * 64};
+        }
+        InvLaunch& ll = *dst;
+        InvClass& k = ll.cls[ll.n_classes++];
+        k.nadic = nadic;
         k.mod = mod; k.in = in; k.out = out(out_field); k.out_stride = A.size[out_field];
         k.ok = reinterpret_cast<uint8_t*>(out(F_FLAGS)) + flag_byte; k.ok_stride = A.size[F_FLAGS] * 4;
-        k.count = U; k.item_begin = l.total_items;
-        l.total_items += (U + gpw - 1) / gpw;
+        k.count = U; k.item_begin = ll.total_items;
+        ll.total_items += (U + gpw - 1) / gpw;
     }
 };
 
@@ -219,7 +227,7 @@ static int run_exp(tecdsa_ctx* c, ExpLaunch& l, int K) {
 }
 static int run_inv(tecdsa_ctx* c, InvLaunch& l, int K) {
     if (l.n_classes == 0) return 0;
-    int rc = c->launch_inv(l, K);
+    int rc = K == -128 ? c->launch_nadic_inv(l) : c->launch_inv(l, K);
     l.n_classes = 0; l.total_items = 0;
     return rc;
 }
@@ -274,7 +282,7 @@ static int offline_impl(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* 
 
     ExpLaunch &L32 = B.L32, &L64 = B.L64, &L128 = B.L128;
     InvLaunch &I64 = B.I64, &I128 = B.I128;
-    Builder::reset(L32); Builder::reset(L64); Builder::reset(L128); Builder::reset(B.LPQ); Builder::reset(I64); Builder::reset(I128);
+    Builder::reset(L32); Builder::reset(L64); Builder::reset(L128); Builder::reset(B.LPQ); Builder::reset(I64); Builder::reset(I128); Builder::reset(B.I128H);
     const int GPW128 = 0;        // classes modulo N^2 are routed (and sized) by Builder::exp_class
     const uint32_t *ro = A.row_own, *rp = A.row_peer;
     auto st_rows = [&](int x) { return A.row_st + (size_t)x * U; };
@@ -315,7 +323,7 @@ static int offline_impl(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* 
     // zk_pdl_with_slack/mod.rs:191-193): ONE inversion of the peer's ciphertext serves the three proofs here and the
     // peer's PDL proof in round 5 (declared shortcut, identical value)
     B.inv_class(I128, GPWI128, B.key(KT_NN, rp), B.peer(F_CK), F_CINVP, 3);
-    RUN(run_inv(c, I128, 128));
+    RUN(run_inv(c, I128, 128)); RUN(run_inv(c, B.I128H, -128));
     for (int x = 0; x < 3; x++) {
         B.exp_class(L64, GPW64, B.key(KT_NT, st_rows(x)), 1, B.peer(F_Z0 + x), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_ZE0 + x);   // z^e (:122)
         B.exp_class(L128, GPW128, B.key(KT_NN, rp), 1, B.fld(F_CINVP), B.peer(F_E0 + x), 8, NONE, NONE, 0, 0, NONE, NONE, F_CEI0 + x);           // (c^-1)^e (:135)
@@ -367,7 +375,7 @@ static int offline_impl(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* 
     // ================= Round 5 (rounds.rs:525-592): verify both signers' PDL proofs (own one included)
     RUN(glue(c, gg20_r5_pre, A));
     B.inv_class(I128, GPWI128, B.key(KT_NN, ro), B.fld(F_CK), F_CINVO, 8);          // own ciphertext (proof j = 0); the peer's inverse is CINVP
-    RUN(run_inv(c, I128, 128));
+    RUN(run_inv(c, I128, 128)); RUN(run_inv(c, B.I128H, -128));
     for (int j = 0; j < 2; j++) {
         const uint32_t* prover = j ? rp : ro;            // key row of the prover
         const uint32_t* stmt = j ? ro : rp;              // whose (N_tilde, h1, h2) the proof was made against

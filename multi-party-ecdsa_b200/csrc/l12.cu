@@ -94,7 +94,7 @@ void add_fb(ExpLaunch& l, int count, const tecdsa_keyset* ks, const uint32_t* ro
 void add_inv(InvLaunch& l, int K, int count, Operand mod, Operand in, uint32_t* out, uint8_t* ok) {
     const int gpw = 32 / (K == 64 ? TPI_2048 : TPI_4096);
     InvClass& k = l.cls[l.n_classes++];
-    k.mod = mod; k.in = in; k.out = out; k.out_stride = K; k.ok = ok; k.ok_stride = 1; k.count = count; k.item_begin = l.total_items;
+    k.mod = mod; k.in = in; k.out = out; k.out_stride = K; k.ok = ok; k.ok_stride = 1; k.nadic = NONE; k.count = count; k.item_begin = l.total_items;
     l.total_items += (count + gpw - 1) / gpw;
 }
 int run(tecdsa_ctx* c, ExpLaunch& l, int K) {

@@ -148,6 +148,7 @@ struct InvClass {
     uint8_t* ok;            // 1 = inverse exists (per instance, ok_stride bytes apart)
     uint32_t ok_stride;
     uint32_t out_stride;
+    Operand nadic;          // nadic_inv_kernel only (nadic_inv.cuh): inverse modulo N^2, `mod` names N and this the key's constants row
     int count;
     int item_begin;
 };
