@@ -10,18 +10,19 @@
 namespace tecdsa {
 struct ExpLaunch;
 struct InvLaunch;
-// lane-group widths of the job-list kernels (16 limbs per lane for both modulus widths)
+// lane-group widths of the job-list kernels working directly on a K-limb modulus
 constexpr int TPI_1024 = 4;     // 8 limbs per lane
-constexpr int TPI_2048 = 4;
-constexpr int TPI_4096 = 8;
-// N-adic jobs modulo N^2: lane groups are N wide (64 limbs).  Shape of the kernel (lanes per group, min blocks per SM) is a
-// process-wide tuning choice; TECDSA_NADIC_SHAPE="<tpi>,<minb>" overrides the default for measurements.
-constexpr int NADIC_ROW = 10;    // constants row of a modulus: 10 * K limbs (nadic.cuh)
-int tecdsa_nadic_tpi();
-int tecdsa_nadic32_tpi();
-constexpr int TPI_NADIC_INV = 8;
-bool tecdsa_hensel_inverse();   // inverses modulo N^2 through nadic_inv_kernel (TECDSA_HENSEL=0: the 4096-bit Kaliski inversion)       // p-adic jobs modulo p^2, q^2 (32-limb primes)
+constexpr int TPI_2048 = 4;     // 16 limbs per lane
+constexpr int TPI_4096 = 8;     // 16 limbs per lane (generic 4096-bit moduli of the L0 entry points; the gg20 driver has none left)
+// Jobs modulo a square (N^2 with 64-limb N; p^2, q^2 with 32-limb primes) run in N-adic form (nadic.cuh): lane groups are as
+// wide as the ROOT.  The kernel shapes (lanes per group, min blocks per SM) are process-wide tuning choices:
+// TECDSA_NADIC_SHAPE="<tpi>,<minb>[,<tpi32>,<minb32>]" overrides the defaults for measurements.
+constexpr int NADIC_ROW = 10;       // constants row of a modulus: 10 * K limbs (nadic.cuh)
+constexpr int TPI_NADIC_INV = 8;    // nadic_inv_kernel<64, .>
+int tecdsa_nadic_tpi();             // K = 64
+int tecdsa_nadic32_tpi();           // K = 32
 int tecdsa_nadic_minb();
+bool tecdsa_hensel_inverse();       // inverses modulo N^2 through nadic_inv_kernel; TECDSA_HENSEL=0 selects the 4096-bit Kaliski inversion
 }  // namespace tecdsa
 
 int tecdsa_fail(int code, const char* what, cudaError_t e = cudaSuccess);

@@ -3,8 +3,8 @@
 // sign/rounds.rs Round0..Round6 for `units` parties at once.  Both parties of a session are
 // resident on the same GPU, so the six message rounds are plain reads of the peer's arena
 // fields.  Every round is: a glue kernel (EC / hashing / plain integers), one persistent
-// job-list launch per modulus width (2048-bit: N_tilde, N, p^2, q^2; 4096-bit: N^2), and, where
-// the verifier needs `mod_inv`, an inversion launch.
+// job-list launch per kind of modulus (1024-bit: p, q; 2048-bit: N_tilde, N; p-adic: p^2, q^2;
+// N-adic: N^2 — nadic.cuh), and, where the verifier needs `mod_inv`, an inversion launch.
 #include "ctx.h"
 #include "gg20_glue.cuh"
 #include "modinv.cuh"
