@@ -187,7 +187,7 @@ extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_ke
         int rc = c->nadic_setup(ks->tab[KT_N], ks->nadic, rows, 64);
         if (!rc) rc = c->nadic_setup(ks->tab[KT_P], ks->nadic_p, rows, 32);
         if (!rc) rc = c->nadic_setup(ks->tab[KT_Q], ks->nadic_q, rows, 32);
-        if (rc) return rc;
+        if (rc) { tecdsa_keys_free(c, ks); return rc; }
     }
     CK(cudaStreamSynchronize(c->stream));
     // parity bits of the uploaded moduli are validated on the host copy of the inputs only
