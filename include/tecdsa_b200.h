@@ -175,6 +175,22 @@ int tecdsa_mta_get_alpha_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const u
                                const uint32_t* b_proof, const uint32_t* beta_tag_proof, uint32_t* alpha, uint32_t* alpha_plain,
                                uint8_t* status, size_t count, int mem);
 
+/* ---- key-generation VERIFICATION path — written, NOT yet validated on a GPU ----------
+ * The checks one party runs on every other party's KeyGenBroadcastMessage1 / shares
+ * (gg_2020/party_i.rs:260-320, 322-367); proof bodies are zk-paillier 0.4.3 / curv 0.9 [R].  status: TECDSA_ST_OK / _PROOF.
+ * correct_key_verify: `NiCorrectKeyProof::verify(&ek, salt)` (party_i.rs:288-291): n = [count][64], sigma = [count][11][64],
+ *   salt = salt_len raw bytes (zk-paillier SALT_STRING = "KZen");
+ * composite_dlog_verify: `CompositeDLogProof::verify(&DLogStatement{N, g, ni})` (party_i.rs:296-303): x = [count][64],
+ *   y = [count][y_limbs] (an integer, not reduced);
+ * vss_validate_share: `VerifiableSS::validate_share(&share, index)` (party_i.rs:337-339): commitments =
+ *   [count][n_commitments][16] affine points (coefficient 0 first), share = [count][8], index = [count].            */
+int tecdsa_correct_key_verify_batch(tecdsa_ctx* ctx, const uint32_t* n, const uint32_t* sigma, const uint8_t* salt, int salt_len,
+                                    uint8_t* status, size_t count, int mem);
+int tecdsa_composite_dlog_verify_batch(tecdsa_ctx* ctx, const uint32_t* n_tilde, const uint32_t* g, const uint32_t* ni, const uint32_t* x,
+                                       const uint32_t* y, int y_limbs, uint8_t* status, size_t count, int mem);
+int tecdsa_vss_validate_share_batch(tecdsa_ctx* ctx, const uint32_t* commitments, int n_commitments, const uint32_t* share,
+                                    const uint32_t* index, uint8_t* status, size_t count, int mem);
+
 /* ---- curv-kzen sigma proofs and hashes used by the protocol (out-of-tree crate; call sites cited) ----------------
  * Scalars are 8 limbs (reduced mod q on entry), points affine x||y 16 limbs.  Verifiers write TECDSA_ST_OK or
  * TECDSA_ST_PROOF.  Encodings [R]: challenges hash 65-byte uncompressed points and reduce the digest mod q.

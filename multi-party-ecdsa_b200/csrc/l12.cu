@@ -1016,3 +1016,175 @@ extern "C" int tecdsa_mta_get_alpha_batch(tecdsa_ctx* c, const tecdsa_keyset* ks
     KCHECK();
     return S.finish();
 }
+
+// ------------------------------------------------------------------------------------------ key-generation verification path
+// SURVEY.md section 8(f) rank 1.  NOT YET VALIDATED ON A GPU (written after this round's GPU budget was spent; the parity
+// tests in tests/test_keygen_gpu.py run only with TECDSA_EXPERIMENTAL=1).  Oracle: oracle/keygen_oracle.py.
+namespace {
+
+// instance t of a flat (key, j) batch belongs to key t / per
+__global__ void k_iota_div(uint32_t* idx, int per, int total) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) idx[t] = (uint32_t)(t / per);
+}
+// NiCorrectKeyProof::verify prologue (zk-paillier 0.4.3 correct_key_ni.rs [R]; call site gg_2020/party_i.rs:288-291):
+// rho_j = mask_generation(|N|, H(N, salt, j)) for j < 11, left un-reduced (<= 72 limbs), and the gcd(6370, N) == 1 test
+__global__ void k_ck_rho(const uint32_t* n_tab, const uint8_t* salt, int salt_len, uint32_t* rho72, uint8_t* gcd_ok, int count) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * 11) return;
+    const int i = t / 11, j = t % 11;
+    const uint32_t* N = n_tab + (size_t)i * 64;
+    int top = 63;
+    while (top > 0 && N[top] == 0) top--;
+    const int key_len = N[top] ? top * 32 + (32 - __clz(N[top])) : 0;
+    Sha256 h; h.init();
+    h.put_bigint(N, 64);
+    {   // BigInt::from_bytes(salt).to_bytes(): leading zero bytes dropped, zero -> one 0x00
+        int s0 = 0;
+        while (s0 < salt_len - 1 && salt[s0] == 0) s0++;
+        if (salt_len <= 0) h.put(0);
+        else h.put_bytes(salt + s0, salt_len - s0);
+    }
+    uint32_t jj = (uint32_t)j;
+    h.put_bigint(&jj, 1);
+    uint32_t seed[8];
+    h.finish(seed);
+    uint32_t* out = rho72 + (size_t)t * 72;
+    for (int k = 0; k < 72; k++) out[k] = 0;
+    int msklen = key_len / 256 + 1;
+    if (msklen > 9) msklen = 9;
+    for (int m = 0; m < msklen; m++) {         // digests occupy disjoint 256-bit slots: the sum is a concatenation
+        Sha256 g; g.init();
+        g.put_bigint(seed, 8);
+        uint32_t mm = (uint32_t)m;
+        g.put_bigint(&mm, 1);
+        g.finish(out + 8 * m);
+    }
+    if (j == 0) {
+        uint32_t r5 = 0, r7 = 0, r13 = 0;
+        for (int k = 63; k >= 0; k--) {
+            r5 = (uint32_t)((((uint64_t)r5 << 32) | N[k]) % 5u);
+            r7 = (uint32_t)((((uint64_t)r7 << 32) | N[k]) % 7u);
+            r13 = (uint32_t)((((uint64_t)r13 << 32) | N[k]) % 13u);
+        }
+        gcd_ok[i] = ((N[0] & 1u) && r5 && r7 && r13) ? 1 : 0;
+    }
+}
+__global__ void k_ck_cmp(const uint32_t* got, const uint32_t* want, const uint8_t* gcd_ok, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    bool ok = gcd_ok[i] != 0;
+    for (int j = 0; j < 11 && ok; j++) ok = st::cmp(got + ((size_t)i * 11 + j) * 64, want + ((size_t)i * 11 + j) * 64, 64) == 0;
+    status[i] = ok ? TECDSA_ST_OK : TECDSA_ST_PROOF;
+}
+// CompositeDLogProof::verify prologue (zk-paillier 0.4.3 composite_dlog_proof.rs [R]; call sites party_i.rs:296-303):
+// e = H(x, g, N, ni) and the N > 2^128 / odd-N preconditions
+__global__ void k_cd_pre(const uint32_t* N, const uint32_t* g, const uint32_t* ni, const uint32_t* x, uint32_t* e8, uint8_t* pre_ok, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t* n = N + (size_t)i * 64;
+    Sha256 h; h.init();
+    h.put_bigint(x + (size_t)i * 64, 64);
+    h.put_bigint(g + (size_t)i * 64, 64);
+    h.put_bigint(n, 64);
+    h.put_bigint(ni + (size_t)i * 64, 64);
+    h.finish(e8 + (size_t)i * 8);
+    int top = 63;
+    while (top > 0 && n[top] == 0) top--;
+    bool big = top > 4 || (top == 4 && (n[4] > 1 || (n[0] | n[1] | n[2] | n[3]) != 0));
+    pre_ok[i] = (big && (n[0] & 1u)) ? 1 : 0;
+}
+__global__ void k_cd_post(const uint32_t* v, const uint32_t* x, const uint8_t* pre_ok, const uint8_t* ok_g, const uint8_t* ok_ni, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const bool ok = pre_ok[i] && ok_g[i] && ok_ni[i] && st::cmp(v + (size_t)i * 64, x + (size_t)i * 64, 64) == 0;
+    status[i] = ok ? TECDSA_ST_OK : TECDSA_ST_PROOF;
+}
+// curv VerifiableSS::validate_share [R] (call site party_i.rs:337-339): share * G == sum_j index^j * C_j (Horner)
+__global__ void k_vss_validate(const uint32_t* commitments, int n_comm, const uint32_t* share, const uint32_t* index, uint8_t* status, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t* C = commitments + (size_t)i * n_comm * 16;
+    U256 idx = u256_zero();
+    idx.v[0] = index[i];
+    bool ok = n_comm > 0;
+    Jac acc = jac_identity();
+    for (int j = n_comm - 1; j >= 0 && ok; j--) {
+        Affine cj = affine_load(C + (size_t)j * 16);
+        if (!cj.inf && !on_curve(cj)) { ok = false; break; }
+        if (j != n_comm - 1) acc = jac_mul(acc, idx);
+        acc = jac_add(acc, jac_from_affine(cj));
+    }
+    Affine lhs = mul_G(sc_from_limbs(share + (size_t)i * 8, 8));
+    status[i] = (ok && affine_eq(lhs, jac_to_affine(acc))) ? TECDSA_ST_OK : TECDSA_ST_PROOF;
+}
+
+}  // namespace
+
+extern "C" int tecdsa_correct_key_verify_batch(tecdsa_ctx* c, const uint32_t* n_mod, const uint32_t* sigma, const uint8_t* salt, int salt_len,
+                                               uint8_t* status, size_t count, int mem) {
+    if (!n_mod || !sigma || !status || salt_len < 0 || salt_len > 64 || (salt_len && !salt)) return tecdsa_fail(TECDSA_E_ARG, "correct_key_verify: bad argument");
+    SIMPLE_PROLOGUE("correct_key_verify")
+    const int tot = n * 11;
+    const uint32_t *dn = S.in(n_mod, count * 64), *ds = S.in(sigma, count * 11 * 64);
+    const uint8_t* dsalt = S.in(salt, (size_t)(salt_len ? salt_len : 0));
+    uint8_t* dst = S.out(status, count);
+    uint32_t *rho72 = S.tmp<uint32_t>((size_t)tot * 72), *rho = S.tmp<uint32_t>((size_t)tot * 64), *got = S.tmp<uint32_t>((size_t)tot * 64);
+    uint32_t *idx = S.tmp<uint32_t>(tot), *one = S.tmp<uint32_t>(4);
+    uint8_t* gcd_ok = S.tmp<uint8_t>(count);
+    if (S.err) return S.finish();
+    static const uint32_t h_one[4] = {1, 0, 0, 0};
+    if (cudaMemcpyAsync(one, h_one, sizeof(h_one), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { S.finish(); return tecdsa_fail(TECDSA_E_CUDA, "correct_key_verify: H2D"); }
+    k_iota_div<<<grid_for(tot), 64, 0, c->stream>>>(idx, 11, tot);
+    KCHECK();
+    k_ck_rho<<<grid_for(tot), 64, 0, c->stream>>>(dn, dsalt, salt_len, rho72, gcd_ok, n);
+    KCHECK();
+    Launches L;
+    const Operand N = tab(dn, idx, 64);
+    // rho mod N: the un-reduced mask as a double-width base to the power 1
+    add_exp(L.e64, 64, tot, N, 1, arr(rho72, 72), Operand{one, nullptr, 0, 0, 4}, 1, NONE, NONE, 0, 0, NONE, NONE, rho, 64);
+    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
+    // sigma^N mod N (party_i.rs:288-291 -> correct_key_ni.rs verify [R])
+    add_exp(L.e64, 64, tot, N, 1, arr(ds, 64), N, 64, NONE, NONE, 0, 0, NONE, NONE, got, 64);
+    RUN(run(c, L.e64, 64));
+    k_ck_cmp<<<grid_for(count), 64, 0, c->stream>>>(got, rho, gcd_ok, dst, n);
+    KCHECK();
+    return S.finish();
+}
+
+extern "C" int tecdsa_composite_dlog_verify_batch(tecdsa_ctx* c, const uint32_t* n_tilde, const uint32_t* g, const uint32_t* ni, const uint32_t* x,
+                                                  const uint32_t* y, int y_limbs, uint8_t* status, size_t count, int mem) {
+    if (!n_tilde || !g || !ni || !x || !y || !status || y_limbs <= 0 || y_limbs > 128) return tecdsa_fail(TECDSA_E_ARG, "composite_dlog_verify: bad argument");
+    SIMPLE_PROLOGUE("composite_dlog_verify")
+    const uint32_t *dN = S.in(n_tilde, count * 64), *dg = S.in(g, count * 64), *dni = S.in(ni, count * 64), *dx = S.in(x, count * 64);
+    const uint32_t* dy = S.in(y, count * (size_t)y_limbs);
+    uint8_t* dst = S.out(status, count);
+    uint32_t *e8 = S.tmp<uint32_t>(count * 8), *v = S.tmp<uint32_t>(count * 64), *scratch = S.tmp<uint32_t>(count * 64 * 2);
+    uint8_t *pre_ok = S.tmp<uint8_t>(count), *ok_g = S.tmp<uint8_t>(count), *ok_ni = S.tmp<uint8_t>(count);
+    if (S.err) return S.finish();
+    k_cd_pre<<<grid_for(count), 64, 0, c->stream>>>(dN, dg, dni, dx, e8, pre_ok, n);
+    KCHECK();
+    Launches L;
+    // gcd(g, N) == 1 and gcd(ni, N) == 1 through the existence of the inverses
+    add_inv(L.i64, 64, n, arr(dN, 64), arr(dg, 64), scratch, ok_g);
+    add_inv(L.i64, 64, n, arr(dN, 64), arr(dni, 64), scratch + count * 64, ok_ni);
+    RUN(run(c, L.i64, 64));
+    // g^y * ni^e mod N (Straus double exponentiation)
+    add_exp(L.e64, 64, n, arr(dN, 64), 2, arr(dg, 64), arr(dy, (uint32_t)y_limbs), y_limbs, arr(dni, 64), arr(e8, 8), 8, 0, NONE, NONE, v, 64);
+    RUN(run(c, L.e64, 64));
+    k_cd_post<<<grid_for(count), 64, 0, c->stream>>>(v, dx, pre_ok, ok_g, ok_ni, dst, n);
+    KCHECK();
+    return S.finish();
+}
+
+extern "C" int tecdsa_vss_validate_share_batch(tecdsa_ctx* c, const uint32_t* commitments, int n_commitments, const uint32_t* share,
+                                               const uint32_t* index, uint8_t* status, size_t count, int mem) {
+    if (!commitments || !share || !index || !status || n_commitments <= 0 || n_commitments > 64) return tecdsa_fail(TECDSA_E_ARG, "vss_validate_share: bad argument");
+    SIMPLE_PROLOGUE("vss_validate_share")
+    const uint32_t *dc = S.in(commitments, count * (size_t)n_commitments * 16), *ds = S.in(share, count * 8), *di = S.in(index, count);
+    uint8_t* dst = S.out(status, count);
+    if (S.err) return S.finish();
+    k_vss_validate<<<grid_for(count), 64, 0, c->stream>>>(dc, n_commitments, ds, di, dst, n);
+    KCHECK();
+    return S.finish();
+}
