@@ -384,7 +384,10 @@ def main():
 
     offline = None
     if args.offline_sessions > 0:
-        offline = bench_offline(args, eng, pkg, torch, dist, rank, world, args.offline_sessions)
+        try:
+            offline = bench_offline(args, eng, pkg, torch, dist, rank, world, args.offline_sessions)
+        except Exception as exc:          # the secondary section must not take the headline line down with it
+            offline = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if world > 1:
@@ -443,7 +446,7 @@ def main():
         "clocks": clocks,
         "offline_stage": offline,
     }
-    if offline is not None:
+    if offline is not None and "error" not in offline:
         offline["roofline_frac_reference_oplist"] = offline["work"]["achieved_reference_oplist_tmac32"] * 1e12 / peak_mac
         offline["roofline_frac_executed"] = offline["work"]["achieved_executed_tmac32"] * 1e12 / peak_mac
         if not args.no_cpu_baseline:
@@ -453,6 +456,8 @@ def main():
         dist.destroy_process_group()
     if not ok:
         raise SystemExit("parity check against the oracle FAILED")
+    if offline is not None and "error" in offline:
+        raise SystemExit("offline stage section failed: " + offline["error"])
     if offline is not None and not (offline["all_units_ok"] and offline["host_and_device_paths_agree"]):
         raise SystemExit("offline stage: a unit failed or the host/device paths disagree")
 
