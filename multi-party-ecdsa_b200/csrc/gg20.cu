@@ -480,9 +480,11 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
         if (rc) errs[h] = tecdsa_last_error();
     };
     const uint64_t l0 = c->child[0]->launches + c->child[1]->launches;
-    std::thread other(half, 1);
+    bool threaded = true;
+    std::thread other;
+    try { other = std::thread(half, 1); } catch (...) { threaded = false; }      // no thread available: queue the halves one after the other
     half(0);
-    other.join();
+    if (threaded) other.join(); else half(1);
     for (int h = 0; h < 2; h++) {
         if (rcs[h]) { cudaDeviceSynchronize(); return tecdsa_fail(rcs[h], errs[h].c_str()); }
         CK(cudaStreamWaitEvent(c->stream, c->ev_join[h], 0));
