@@ -128,3 +128,30 @@ def test_keygen_three_parties_end_to_end(keyset):
     bad_mine = [shares[j][0] for j in range(n)]; bad_mine[1] = (bad_mine[1] + 1) % o.Q
     assert kg.phase2_verify_vss(y_i, bad_mine, vss, 1, 5) is None
     assert not kg.verify_dlog_proofs_check_against_vss([proofs[1], proofs[0], proofs[2]], vss)
+
+
+def test_keygen_golden_vectors(keyset):
+    """tests/golden/vectors_keygen.json (make_keygen_vectors.py): the restatement reproduces its frozen outputs"""
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "vectors_keygen.json")) as f:
+        v = json.load(f)
+    I = lambda s: int(s, 16)
+    for e in v["correct_key"]:
+        dk = keyset[e["row"]].dk
+        n = dk.p * dk.q
+        salt = bytes.fromhex(e["salt"])
+        assert [I(x) for x in e["rho"]] == kg._rho_vec(n, salt)
+        sigma = [I(x) for x in e["sigma"]]
+        assert sigma == kg.correct_key_proof(dk, salt)
+        assert kg.correct_key_verify(sigma, o.EncryptionKey(n, n * n), salt)
+    for e in v["composite_dlog"]:
+        st1 = o.DLogStatement(I(e["n_tilde"]), I(e["h1"]), I(e["h2"]))
+        st2 = o.DLogStatement(st1.N, st1.ni, st1.g)
+        pf1 = kg.composite_dlog_prove(st1, I(e["xhi_neg"]), I(e["r1"]))
+        pf2 = kg.composite_dlog_prove(st2, I(e["xhi_inv_neg"]), I(e["r2"]))
+        assert [pf1.x, pf1.y] == [I(x) for x in e["proof_h1"]] and [pf2.x, pf2.y] == [I(x) for x in e["proof_h2"]]
+        assert kg.composite_dlog_verify(pf1, st1) and kg.composite_dlog_verify(pf2, st2)
+    for e in v["vss"]:
+        vss, shares = kg.vss_share(e["t"], e["n"], I(e["secret"]), [I(c) for c in e["coefficients"]])
+        assert shares == [I(s) for s in e["shares"]]
+        assert vss.commitments == [(I(p[0]), I(p[1])) for p in e["commitments"]]
