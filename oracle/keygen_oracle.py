@@ -1,7 +1,7 @@
 """CPU oracle for SURVEY.md section 8(f) rank 1: the GG20 key-generation VERIFICATION path.
 
-TEST INFRASTRUCTURE ONLY (same rule as gg20_oracle.py): nothing outside tests/ may import this.  No CUDA
-counterpart exists yet — this file is the restatement the next widening step is to be built against.
+TEST INFRASTRUCTURE ONLY (same rule as gg20_oracle.py): nothing outside tests/ may import this.  The CUDA entry
+points built against it (csrc/l12.cu tail, multi-party-ecdsa_b200/keygen.py) are written but not yet validated on a GPU.
 
 PARITY UNPINNED.  The in-tree callers are cited by file:line under /root/reference; the proofs themselves live in
 crates that are NOT vendored (zk-paillier 0.4.3: `NiCorrectKeyProof`, `CompositeDLogProof`; curv-kzen 0.9:

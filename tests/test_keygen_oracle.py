@@ -1,6 +1,6 @@
 """CPU tests of oracle/keygen_oracle.py (the key-generation verification path).
-No CUDA counterpart exists yet; these pin the restatement the next widening step will be built against: every proof
-verifies, every tampered field rejects, the Feldman arithmetic agrees with the committed key fixtures."""
+The CUDA entry points exist but are not validated on a GPU yet (tests/test_keygen_gpu.py is gated); these pin the
+restatement they are built against: every proof verifies, every tampered field rejects, the Feldman arithmetic agrees with the committed key fixtures."""
 import dataclasses
 import random
 
