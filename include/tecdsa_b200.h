@@ -175,11 +175,13 @@ int tecdsa_mta_get_alpha_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const u
                                const uint32_t* b_proof, const uint32_t* beta_tag_proof, uint32_t* alpha, uint32_t* alpha_plain,
                                uint8_t* status, size_t count, int mem);
 
-/* ---- key-generation VERIFICATION path — written, NOT yet validated on a GPU ----------
- * The checks one party runs on every other party's KeyGenBroadcastMessage1 / shares
- * (gg_2020/party_i.rs:260-320, 322-367); proof bodies are zk-paillier 0.4.3 / curv 0.9 [R].  status: TECDSA_ST_OK / _PROOF.
+/* ---- key-generation path -----------------------------------------------------------
+ * The checks one party runs on every other party's KeyGenBroadcastMessage1 / shares (gg_2020/party_i.rs:260-320, 322-367)
+ * and the proofs it produces for its own (party_i.rs:137-156, 219-258, 313); proof bodies are zk-paillier 0.4.3 / curv 0.9
+ * [R].  status: TECDSA_ST_OK / _PROOF (verifiers), _NOT_INVERTIBLE (provers).
  * correct_key_verify: `NiCorrectKeyProof::verify(&ek, salt)` (party_i.rs:288-291): n = [count][64], sigma = [count][11][64],
- *   salt = salt_len raw bytes (zk-paillier SALT_STRING = "KZen");
+ *   salt = salt_len raw bytes (zk-paillier SALT_STRING = "KZen"); includes gcd(P, n) == 1 for the primorial P of all primes
+ *   <= 6379 (an n with a small prime factor is rejected even when every sigma^n == rho holds);
  * composite_dlog_verify: `CompositeDLogProof::verify(&DLogStatement{N, g, ni})` (party_i.rs:296-303): x = [count][64],
  *   y = [count][y_limbs] (an integer, not reduced);
  * vss_validate_share: `VerifiableSS::validate_share(&share, index)` (party_i.rs:337-339): commitments =
@@ -190,6 +192,24 @@ int tecdsa_composite_dlog_verify_batch(tecdsa_ctx* ctx, const uint32_t* n_tilde,
                                        const uint32_t* y, int y_limbs, uint8_t* status, size_t count, int mem);
 int tecdsa_vss_validate_share_batch(tecdsa_ctx* ctx, const uint32_t* commitments, int n_commitments, const uint32_t* share,
                                     const uint32_t* index, uint8_t* status, size_t count, int mem);
+/* correct_key_prove: `NiCorrectKeyProof::proof(&dk, None)` (party_i.rs:225): p, q = [count][32] -> sigma [count][11][64]
+ *   (sigma_j = rho_j^(N^-1 mod phi(N)) mod N);
+ * composite_dlog_prove: `CompositeDLogProof::prove(&statement, &secret)` (party_i.rs:238-241): nonce r = [count][16]
+ *   (< 2^512, the reference samples it), secret = [count][secret_limbs] -> x [count][64], y = r + e*secret [count][y_limbs],
+ *   y_limbs >= secret_limbs + 9 and a multiple of 4;
+ * vss_share: `VerifiableSS::share(t, n, &secret)` (party_i.rs:313) with explicit polynomial coefficients [count][t+1][8]
+ *   (coefficient 0 = the secret) -> shares f(1..n) [count][n][8], commitments a_j*G [count][t+1][16];
+ * h1_h2_n_tilde: `generate_h1_h2_N_tilde` (party_i.rs:137-156) with explicit samples: p~, q~ = [count][32], h1, xhi =
+ *   [count][64] -> N~, h2 = h1^xhi, phi - xhi, phi - xhi^-1 (all [count][64]); NOT_INVERTIBLE where the reference's
+ *   sampling loop would draw xhi again.                                                                              */
+int tecdsa_correct_key_prove_batch(tecdsa_ctx* ctx, const uint32_t* p, const uint32_t* q, const uint8_t* salt, int salt_len,
+                                   uint32_t* sigma, uint8_t* status, size_t count, int mem);
+int tecdsa_composite_dlog_prove_batch(tecdsa_ctx* ctx, const uint32_t* n_tilde, const uint32_t* g, const uint32_t* ni, const uint32_t* secret,
+                                      int secret_limbs, const uint32_t* r, uint32_t* x, uint32_t* y, int y_limbs, size_t count, int mem);
+int tecdsa_vss_share_batch(tecdsa_ctx* ctx, int t, int n_shares, const uint32_t* coefficients, uint32_t* shares, uint32_t* commitments,
+                           size_t count, int mem);
+int tecdsa_h1_h2_n_tilde_batch(tecdsa_ctx* ctx, const uint32_t* p_t, const uint32_t* q_t, const uint32_t* h1, const uint32_t* xhi,
+                               uint32_t* n_tilde, uint32_t* h2, uint32_t* xhi_neg, uint32_t* xhi_inv_neg, uint8_t* status, size_t count, int mem);
 
 /* ---- curv-kzen sigma proofs and hashes used by the protocol (out-of-tree crate; call sites cited) ----------------
  * Scalars are 8 limbs (reduced mod q on entry), points affine x||y 16 limbs.  Verifiers write TECDSA_ST_OK or

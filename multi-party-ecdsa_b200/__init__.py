@@ -38,6 +38,7 @@ EXPORTS = [
     "tecdsa_heg_prove_batch", "tecdsa_heg_verify_batch", "tecdsa_sha256_bigints_batch", "tecdsa_hash_commitment_batch",
     "tecdsa_mta_message_a_batch", "tecdsa_mta_message_b_batch", "tecdsa_mta_get_alpha_batch",
     "tecdsa_correct_key_verify_batch", "tecdsa_composite_dlog_verify_batch", "tecdsa_vss_validate_share_batch",
+    "tecdsa_correct_key_prove_batch", "tecdsa_composite_dlog_prove_batch", "tecdsa_vss_share_batch", "tecdsa_h1_h2_n_tilde_batch",
 ]
 
 

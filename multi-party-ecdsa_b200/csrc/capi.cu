@@ -62,6 +62,7 @@ extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
         const uint32_t* fbp = nullptr;
         int rc = tecdsa_internal_fb_points_init(device, c->stream, &fbp);
         if (rc == 0) rc = tecdsa_internal_fb_points_set_l12(fbp);
+        if (rc == 0) rc = tecdsa_internal_fb_points_set_keygen(fbp);
         if (rc) { delete c; return rc; }
     }
     CK(cudaEventCreate(&c->ev0));

@@ -29,6 +29,7 @@ int tecdsa_fail(int code, const char* what, cudaError_t e = cudaSuccess);
 // per-device fixed-base point tables (G, base_point2): built once, shared by every context of the device
 int tecdsa_internal_fb_points_init(int device, cudaStream_t stream, const uint32_t** table_out);   // gg20.cu
 int tecdsa_internal_fb_points_set_l12(const uint32_t* table);                                        // l12.cu
+int tecdsa_internal_fb_points_set_keygen(const uint32_t* table);                                     // keygen.cu
 
 #define CK(call)                                                               \
     do {                                                                       \

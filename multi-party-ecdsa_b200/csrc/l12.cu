@@ -3,119 +3,11 @@
 // compositions of the same job-list kernels and glue device functions the L3 offline-stage
 // driver uses (jobs.cuh, modinv.cuh, gg20_glue.cuh); results are canonical residues /
 // proof bytes identical to the L3 path and to the oracle.
-#include "ctx.h"
-#include "gg20_glue.cuh"
-#include "modinv.cuh"
-
-#include <vector>
+#include "stage.cuh"
 
 using namespace tecdsa;
 
 namespace {
-
-// Stream-ordered staging of caller buffers: HOST pointers are copied to device scratch (and
-// results copied back by finish()), DEVICE pointers are used in place.
-struct Stage {
-    tecdsa_ctx* c;
-    int mem;
-    std::vector<void*> scratch;
-    struct Back { void* host; void* dev; size_t bytes; };
-    std::vector<Back> back;
-    int err = 0;
-    Stage(tecdsa_ctx* ctx, int m) : c(ctx), mem(m) {}
-    void* alloc(size_t bytes) {
-        void* p = nullptr;
-        if (cudaMallocAsync(&p, bytes ? bytes : 16, c->stream) != cudaSuccess) { err = tecdsa_fail(TECDSA_E_NOMEM, "cudaMallocAsync"); return nullptr; }
-        scratch.push_back(p);
-        return p;
-    }
-    template <typename T> const T* in(const T* p, size_t n) {
-        if (!p || mem == TECDSA_DEVICE) return p;
-        T* d = static_cast<T*>(alloc(n * sizeof(T)));
-        if (d && cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "H2D copy");
-        return d;
-    }
-    template <typename T> T* out(T* p, size_t n) {
-        if (!p || mem == TECDSA_DEVICE) return p;
-        T* d = static_cast<T*>(alloc(n * sizeof(T)));
-        if (d) back.push_back({p, d, n * sizeof(T)});
-        return d;
-    }
-    template <typename T> T* tmp(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
-    int finish() {
-        for (auto& b : back)
-            if (cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "D2H copy");
-        for (void* p : scratch) cudaFreeAsync(p, c->stream);
-        scratch.clear();
-        if (mem == TECDSA_HOST) {
-            cudaError_t e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "stream sync after batch", e);
-        }
-        return err;
-    }
-};
-
-const Operand NONE = {nullptr, nullptr, 0, 0, 0};
-Operand arr(const uint32_t* p, uint32_t limbs) { return Operand{p, nullptr, limbs, 0, limbs}; }
-Operand tab(const uint32_t* p, const uint32_t* idx, uint32_t limbs) { return Operand{p, idx, limbs, 1, limbs}; }
-
-struct Launches {
-    ExpLaunch e64, e128;
-    InvLaunch i64, i128;
-    Launches() { e64.n_classes = e64.total_items = e128.n_classes = e128.total_items = 0; i64.n_classes = i64.total_items = i128.n_classes = i128.total_items = 0; }
-};
-void add_exp(ExpLaunch& l, int K, int count, Operand mod, int nb, Operand b0, Operand e0, int el0, Operand b1, Operand e1, int el1,
-             int nm, Operand m0, Operand m1, uint32_t* out, uint32_t out_stride) {
-    const int gpw = 32 / (K == 64 ? TPI_2048 : TPI_4096);
-    ExpClass& k = l.cls[l.n_classes++];
-    k.mod = mod; k.base[0] = b0; k.base[1] = b1; k.exp[0] = e0; k.exp[1] = e1; k.exp_limbs[0] = el0; k.exp_limbs[1] = el1;
-    k.mul[0] = m0; k.mul[1] = m1; k.mul[2] = NONE; k.nbases = nb; k.nmul = nm; k.wide0 = 0;
-    k.fb = nullptr; k.fb_row = NONE; k.fb_sel[0] = k.fb_sel[1] = 0; k.nadic = NONE;
-    k.out = out; k.out_stride = out_stride; k.count = count; k.item_begin = l.total_items;
-    l.total_items += (count + gpw - 1) / gpw;
-}
-// class modulo N^2 through the N-adic kernel (nadic.cuh): `N` names the K = 64 limb modulus, `consts` its constants row
-void add_nn(ExpLaunch& l, int count, Operand N, Operand consts, int nb, Operand b0, Operand e0, int el0, Operand b1, Operand e1, int el1,
-            int nm, Operand m0, Operand m1, uint32_t* out, uint32_t out_stride) {
-    add_exp(l, 128, count, N, nb, b0, e0, el0, b1, e1, el1, nm, m0, m1, out, out_stride);
-    ExpClass& k = l.cls[l.n_classes - 1];
-    const int gpw = N.limbs == 32 ? 32 / tecdsa_nadic32_tpi() : 32 / tecdsa_nadic_tpi();
-    k.nadic = consts;
-    l.total_items = k.item_begin + (count + gpw - 1) / gpw;
-}
-Operand key_n(const tecdsa_keyset* ks, const uint32_t* rows) { return tab(ks->tab[KT_N], rows, 64); }
-Operand key_nadic(const tecdsa_keyset* ks, const uint32_t* rows) { return tab(ks->nadic, rows, NADIC_ROW * 64); }
-void add_fb(ExpLaunch& l, int count, const tecdsa_keyset* ks, const uint32_t* rows, Operand e_h2, int el_h2, Operand e_h1, int el_h1,
-            int nm, Operand m0, uint32_t* out) {
-    add_exp(l, 64, count, tab(ks->tab[KT_NT], rows, 64), 2, NONE, e_h2, el_h2, NONE, e_h1, el_h1, nm, m0, NONE, out, 64);
-    ExpClass& k = l.cls[l.n_classes - 1];
-    k.fb = ks->fb; k.fb_row = Operand{nullptr, rows, 0, 1, 0}; k.fb_sel[0] = 1; k.fb_sel[1] = 0;
-}
-void add_inv(InvLaunch& l, int K, int count, Operand mod, Operand in, uint32_t* out, uint8_t* ok) {
-    const int gpw = 32 / (K == 64 ? TPI_2048 : TPI_4096);
-    InvClass& k = l.cls[l.n_classes++];
-    k.mod = mod; k.in = in; k.out = out; k.out_stride = K; k.ok = ok; k.ok_stride = 1; k.nadic = NONE; k.count = count; k.item_begin = l.total_items;
-    l.total_items += (count + gpw - 1) / gpw;
-}
-int run(tecdsa_ctx* c, ExpLaunch& l, int K) {
-    if (!l.n_classes) return 0;
-    int rc = c->launch_exp(l, K);
-    l.n_classes = l.total_items = 0;
-    return rc;
-}
-int run_nn(tecdsa_ctx* c, ExpLaunch& l, int K = 64) {
-    if (!l.n_classes) return 0;
-    int rc = c->launch_nadic(l, K);
-    l.n_classes = l.total_items = 0;
-    return rc;
-}
-int run(tecdsa_ctx* c, InvLaunch& l, int K) {
-    if (!l.n_classes) return 0;
-    int rc = c->launch_inv(l, K);
-    l.n_classes = l.total_items = 0;
-    return rc;
-}
-int check_bits(int mod_bits) { return (mod_bits == 2048 || mod_bits == 4096) ? 0 : tecdsa_fail(TECDSA_E_UNSUPPORTED, "mod_bits must be 2048 or 4096"); }
 
 // ---- glue kernels of the stand-alone entry points ----------------------------------------------
 // out[i] (128 limbs) = 1 + m[i] * N[row]      (the (1 + m n) factor of Paillier encrypt)
@@ -418,15 +310,6 @@ __global__ void k_mta_alpha(Arena A, const uint32_t* rows, const uint32_t* dp, c
     status[i] = (v1 && v2 && affine_eq(ba_btag, g_alpha)) ? TECDSA_ST_OK : TECDSA_ST_INVALID_KEY;
 }
 
-Arena key_arena(const tecdsa_keyset* ks) {
-    Arena A;
-    memset(&A, 0, sizeof(A));
-    for (int t = 0; t < KT_COUNT; t++) A.key[t] = ks->tab[t];
-    A.ypk = ks->ypk;
-    return A;
-}
-int grid_for(size_t count) { return (int)((count + 63) / 64); }
-
 }  // namespace
 
 int tecdsa_internal_fb_points_set_l12(const uint32_t* table) {
@@ -434,8 +317,6 @@ int tecdsa_internal_fb_points_set_l12(const uint32_t* table) {
     return 0;
 }
 
-#define RUN(x) do { int _rc = (x); if (_rc) { S.finish(); return _rc; } } while (0)
-#define KCHECK() do { c->count_launch(); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { S.finish(); return tecdsa_fail(TECDSA_E_CUDA, "kernel launch", _e); } } while (0)
 
 // ------------------------------------------------------------------------------------------ L0
 extern "C" int tecdsa_modmul_batch(tecdsa_ctx* c, int mod_bits, const uint32_t* a, const uint32_t* b, const uint32_t* modulus,
@@ -814,13 +695,6 @@ extern "C" int tecdsa_bob_proof_verify_batch(tecdsa_ctx* c, const tecdsa_keyset*
 
 
 // ------------------------------------------------------------------------------------------ curv sigma proofs / hashes
-#define SIMPLE_PROLOGUE(name)                                                        \
-    if (!c) return tecdsa_fail(TECDSA_E_ARG, name ": null ctx");                     \
-    if (count == 0) return 0;                                                        \
-    CK(cudaSetDevice(c->device));                                                    \
-    const int n = (int)count;                                                        \
-    Stage S(c, mem);
-
 extern "C" int tecdsa_dlog_prove_batch(tecdsa_ctx* c, const uint32_t* sk, const uint32_t* nonce, uint32_t* proof, size_t count, int mem) {
     if (!sk || !nonce || !proof) return tecdsa_fail(TECDSA_E_ARG, "dlog_prove: null argument");
     SIMPLE_PROLOGUE("dlog_prove")
@@ -1017,174 +891,3 @@ extern "C" int tecdsa_mta_get_alpha_batch(tecdsa_ctx* c, const tecdsa_keyset* ks
     return S.finish();
 }
 
-// ------------------------------------------------------------------------------------------ key-generation verification path
-// SURVEY.md section 8(f) rank 1.  NOT YET VALIDATED ON A GPU (written after this round's GPU budget was spent; the parity
-// tests in tests/test_keygen_gpu.py run only with TECDSA_EXPERIMENTAL=1).  Oracle: oracle/keygen_oracle.py.
-namespace {
-
-// instance t of a flat (key, j) batch belongs to key t / per
-__global__ void k_iota_div(uint32_t* idx, int per, int total) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < total) idx[t] = (uint32_t)(t / per);
-}
-// NiCorrectKeyProof::verify prologue (zk-paillier 0.4.3 correct_key_ni.rs [R]; call site gg_2020/party_i.rs:288-291):
-// rho_j = mask_generation(|N|, H(N, salt, j)) for j < 11, left un-reduced (<= 72 limbs), and the gcd(6370, N) == 1 test
-__global__ void k_ck_rho(const uint32_t* n_tab, const uint8_t* salt, int salt_len, uint32_t* rho72, uint8_t* gcd_ok, int count) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count * 11) return;
-    const int i = t / 11, j = t % 11;
-    const uint32_t* N = n_tab + (size_t)i * 64;
-    int top = 63;
-    while (top > 0 && N[top] == 0) top--;
-    const int key_len = N[top] ? top * 32 + (32 - __clz(N[top])) : 0;
-    Sha256 h; h.init();
-    h.put_bigint(N, 64);
-    {   // BigInt::from_bytes(salt).to_bytes(): leading zero bytes dropped, zero -> one 0x00
-        int s0 = 0;
-        while (s0 < salt_len - 1 && salt[s0] == 0) s0++;
-        if (salt_len <= 0) h.put(0);
-        else h.put_bytes(salt + s0, salt_len - s0);
-    }
-    uint32_t jj = (uint32_t)j;
-    h.put_bigint(&jj, 1);
-    uint32_t seed[8];
-    h.finish(seed);
-    uint32_t* out = rho72 + (size_t)t * 72;
-    for (int k = 0; k < 72; k++) out[k] = 0;
-    int msklen = key_len / 256 + 1;
-    if (msklen > 9) msklen = 9;
-    for (int m = 0; m < msklen; m++) {         // digests occupy disjoint 256-bit slots: the sum is a concatenation
-        Sha256 g; g.init();
-        g.put_bigint(seed, 8);
-        uint32_t mm = (uint32_t)m;
-        g.put_bigint(&mm, 1);
-        g.finish(out + 8 * m);
-    }
-    if (j == 0) {
-        uint32_t r5 = 0, r7 = 0, r13 = 0;
-        for (int k = 63; k >= 0; k--) {
-            r5 = (uint32_t)((((uint64_t)r5 << 32) | N[k]) % 5u);
-            r7 = (uint32_t)((((uint64_t)r7 << 32) | N[k]) % 7u);
-            r13 = (uint32_t)((((uint64_t)r13 << 32) | N[k]) % 13u);
-        }
-        gcd_ok[i] = ((N[0] & 1u) && r5 && r7 && r13) ? 1 : 0;
-    }
-}
-__global__ void k_ck_cmp(const uint32_t* got, const uint32_t* want, const uint8_t* gcd_ok, uint8_t* status, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    bool ok = gcd_ok[i] != 0;
-    for (int j = 0; j < 11 && ok; j++) ok = st::cmp(got + ((size_t)i * 11 + j) * 64, want + ((size_t)i * 11 + j) * 64, 64) == 0;
-    status[i] = ok ? TECDSA_ST_OK : TECDSA_ST_PROOF;
-}
-// CompositeDLogProof::verify prologue (zk-paillier 0.4.3 composite_dlog_proof.rs [R]; call sites party_i.rs:296-303):
-// e = H(x, g, N, ni) and the N > 2^128 / odd-N preconditions
-__global__ void k_cd_pre(const uint32_t* N, const uint32_t* g, const uint32_t* ni, const uint32_t* x, uint32_t* e8, uint8_t* pre_ok, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t* n = N + (size_t)i * 64;
-    Sha256 h; h.init();
-    h.put_bigint(x + (size_t)i * 64, 64);
-    h.put_bigint(g + (size_t)i * 64, 64);
-    h.put_bigint(n, 64);
-    h.put_bigint(ni + (size_t)i * 64, 64);
-    h.finish(e8 + (size_t)i * 8);
-    int top = 63;
-    while (top > 0 && n[top] == 0) top--;
-    bool big = top > 4 || (top == 4 && (n[4] > 1 || (n[0] | n[1] | n[2] | n[3]) != 0));
-    pre_ok[i] = (big && (n[0] & 1u)) ? 1 : 0;
-}
-__global__ void k_cd_post(const uint32_t* v, const uint32_t* x, const uint8_t* pre_ok, const uint8_t* ok_g, const uint8_t* ok_ni, uint8_t* status, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const bool ok = pre_ok[i] && ok_g[i] && ok_ni[i] && st::cmp(v + (size_t)i * 64, x + (size_t)i * 64, 64) == 0;
-    status[i] = ok ? TECDSA_ST_OK : TECDSA_ST_PROOF;
-}
-// curv VerifiableSS::validate_share [R] (call site party_i.rs:337-339): share * G == sum_j index^j * C_j (Horner)
-__global__ void k_vss_validate(const uint32_t* commitments, int n_comm, const uint32_t* share, const uint32_t* index, uint8_t* status, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t* C = commitments + (size_t)i * n_comm * 16;
-    U256 idx = u256_zero();
-    idx.v[0] = index[i];
-    bool ok = n_comm > 0;
-    Jac acc = jac_identity();
-    for (int j = n_comm - 1; j >= 0 && ok; j--) {
-        Affine cj = affine_load(C + (size_t)j * 16);
-        if (!cj.inf && !on_curve(cj)) { ok = false; break; }
-        if (j != n_comm - 1) acc = jac_mul(acc, idx);
-        acc = jac_add(acc, jac_from_affine(cj));
-    }
-    Affine lhs = mul_G(sc_from_limbs(share + (size_t)i * 8, 8));
-    status[i] = (ok && affine_eq(lhs, jac_to_affine(acc))) ? TECDSA_ST_OK : TECDSA_ST_PROOF;
-}
-
-}  // namespace
-
-extern "C" int tecdsa_correct_key_verify_batch(tecdsa_ctx* c, const uint32_t* n_mod, const uint32_t* sigma, const uint8_t* salt, int salt_len,
-                                               uint8_t* status, size_t count, int mem) {
-    if (!n_mod || !sigma || !status || salt_len < 0 || salt_len > 64 || (salt_len && !salt)) return tecdsa_fail(TECDSA_E_ARG, "correct_key_verify: bad argument");
-    SIMPLE_PROLOGUE("correct_key_verify")
-    const int tot = n * 11;
-    const uint32_t *dn = S.in(n_mod, count * 64), *ds = S.in(sigma, count * 11 * 64);
-    const uint8_t* dsalt = S.in(salt, (size_t)(salt_len ? salt_len : 0));
-    uint8_t* dst = S.out(status, count);
-    uint32_t *rho72 = S.tmp<uint32_t>((size_t)tot * 72), *rho = S.tmp<uint32_t>((size_t)tot * 64), *got = S.tmp<uint32_t>((size_t)tot * 64);
-    uint32_t *idx = S.tmp<uint32_t>(tot), *one = S.tmp<uint32_t>(4);
-    uint8_t* gcd_ok = S.tmp<uint8_t>(count);
-    if (S.err) return S.finish();
-    static const uint32_t h_one[4] = {1, 0, 0, 0};
-    if (cudaMemcpyAsync(one, h_one, sizeof(h_one), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { S.finish(); return tecdsa_fail(TECDSA_E_CUDA, "correct_key_verify: H2D"); }
-    k_iota_div<<<grid_for(tot), 64, 0, c->stream>>>(idx, 11, tot);
-    KCHECK();
-    k_ck_rho<<<grid_for(tot), 64, 0, c->stream>>>(dn, dsalt, salt_len, rho72, gcd_ok, n);
-    KCHECK();
-    Launches L;
-    const Operand N = tab(dn, idx, 64);
-    // rho mod N: the un-reduced mask as a double-width base to the power 1
-    add_exp(L.e64, 64, tot, N, 1, arr(rho72, 72), Operand{one, nullptr, 0, 0, 4}, 1, NONE, NONE, 0, 0, NONE, NONE, rho, 64);
-    L.e64.cls[L.e64.n_classes - 1].wide0 = 1;
-    // sigma^N mod N (party_i.rs:288-291 -> correct_key_ni.rs verify [R])
-    add_exp(L.e64, 64, tot, N, 1, arr(ds, 64), N, 64, NONE, NONE, 0, 0, NONE, NONE, got, 64);
-    RUN(run(c, L.e64, 64));
-    k_ck_cmp<<<grid_for(count), 64, 0, c->stream>>>(got, rho, gcd_ok, dst, n);
-    KCHECK();
-    return S.finish();
-}
-
-extern "C" int tecdsa_composite_dlog_verify_batch(tecdsa_ctx* c, const uint32_t* n_tilde, const uint32_t* g, const uint32_t* ni, const uint32_t* x,
-                                                  const uint32_t* y, int y_limbs, uint8_t* status, size_t count, int mem) {
-    if (!n_tilde || !g || !ni || !x || !y || !status || y_limbs <= 0 || y_limbs > 128) return tecdsa_fail(TECDSA_E_ARG, "composite_dlog_verify: bad argument");
-    SIMPLE_PROLOGUE("composite_dlog_verify")
-    const uint32_t *dN = S.in(n_tilde, count * 64), *dg = S.in(g, count * 64), *dni = S.in(ni, count * 64), *dx = S.in(x, count * 64);
-    const uint32_t* dy = S.in(y, count * (size_t)y_limbs);
-    uint8_t* dst = S.out(status, count);
-    uint32_t *e8 = S.tmp<uint32_t>(count * 8), *v = S.tmp<uint32_t>(count * 64), *scratch = S.tmp<uint32_t>(count * 64 * 2);
-    uint8_t *pre_ok = S.tmp<uint8_t>(count), *ok_g = S.tmp<uint8_t>(count), *ok_ni = S.tmp<uint8_t>(count);
-    if (S.err) return S.finish();
-    k_cd_pre<<<grid_for(count), 64, 0, c->stream>>>(dN, dg, dni, dx, e8, pre_ok, n);
-    KCHECK();
-    Launches L;
-    // gcd(g, N) == 1 and gcd(ni, N) == 1 through the existence of the inverses
-    add_inv(L.i64, 64, n, arr(dN, 64), arr(dg, 64), scratch, ok_g);
-    add_inv(L.i64, 64, n, arr(dN, 64), arr(dni, 64), scratch + count * 64, ok_ni);
-    RUN(run(c, L.i64, 64));
-    // g^y * ni^e mod N (Straus double exponentiation)
-    add_exp(L.e64, 64, n, arr(dN, 64), 2, arr(dg, 64), arr(dy, (uint32_t)y_limbs), y_limbs, arr(dni, 64), arr(e8, 8), 8, 0, NONE, NONE, v, 64);
-    RUN(run(c, L.e64, 64));
-    k_cd_post<<<grid_for(count), 64, 0, c->stream>>>(v, dx, pre_ok, ok_g, ok_ni, dst, n);
-    KCHECK();
-    return S.finish();
-}
-
-extern "C" int tecdsa_vss_validate_share_batch(tecdsa_ctx* c, const uint32_t* commitments, int n_commitments, const uint32_t* share,
-                                               const uint32_t* index, uint8_t* status, size_t count, int mem) {
-    if (!commitments || !share || !index || !status || n_commitments <= 0 || n_commitments > 64) return tecdsa_fail(TECDSA_E_ARG, "vss_validate_share: bad argument");
-    SIMPLE_PROLOGUE("vss_validate_share")
-    const uint32_t *dc = S.in(commitments, count * (size_t)n_commitments * 16), *ds = S.in(share, count * 8), *di = S.in(index, count);
-    uint8_t* dst = S.out(status, count);
-    if (S.err) return S.finish();
-    k_vss_validate<<<grid_for(count), 64, 0, c->stream>>>(dc, n_commitments, ds, di, dst, n);
-    KCHECK();
-    return S.finish();
-}

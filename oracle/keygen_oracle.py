@@ -1,7 +1,7 @@
 """CPU oracle for SURVEY.md section 8(f) rank 1: the GG20 key-generation VERIFICATION path.
 
 TEST INFRASTRUCTURE ONLY (same rule as gg20_oracle.py): nothing outside tests/ may import this.  The CUDA entry
-points built against it (csrc/l12.cu tail, multi-party-ecdsa_b200/keygen.py) are written but not yet validated on a GPU.
+points built against it: csrc/keygen.cu, multi-party-ecdsa_b200/keygen.py, tests/test_keygen_gpu.py.
 
 PARITY UNPINNED.  The in-tree callers are cited by file:line under /root/reference; the proofs themselves live in
 crates that are NOT vendored (zk-paillier 0.4.3: `NiCorrectKeyProof`, `CompositeDLogProof`; curv-kzen 0.9:
@@ -26,7 +26,27 @@ Point = o.Point
 SALT_STRING = bytes([75, 90, 101, 110])         # "KZen"
 M2 = 11
 DIGEST_SIZE = 256
-P_ALPHA = 6370                                   # `const P: u32 = 6370`: verify() checks gcd(P, n) == 1 [R]
+ALPHA = 6379                                     # eprint 2018/987 section 6.2.3: alpha = 6379, m2 = 11
+
+
+def _primorial(alpha: int) -> int:
+    sieve = bytearray([1]) * (alpha + 1)
+    sieve[0:2] = b"\0\0"
+    for i in range(2, int(alpha ** 0.5) + 1):
+        if sieve[i]:
+            sieve[i * i::i] = bytearray(len(sieve[i * i::i]))
+    out = 1
+    for i in range(alpha + 1):
+        if sieve[i]:
+            out *= i
+    return out
+
+
+# `const P: &str = "1824183726245393467247644231302244136...8238796796690"` [R]: the product of all primes <= 6379 (2746 decimal
+# digits); verify() requires gcd(P, n) == 1, which is what bounds the soundness error of the proof (an N with a prime factor
+# below alpha is rejected outright).  Round 1 of this repo wrongly used the number 6370 itself.
+PRIMORIAL = _primorial(ALPHA)
+assert str(PRIMORIAL).startswith("182418372624539346724764423130") and str(PRIMORIAL).endswith("88238796796690")
 # zk-paillier 0.4.3 zkproofs/composite_dlog_proof.rs [R]
 K_BITS, K_PRIME_BITS, SAMPLE_S_BITS = 128, 128, 256
 # gg_2020/party_i.rs:49-50
@@ -66,8 +86,8 @@ def correct_key_proof(dk: o.DecryptionKey, salt: bytes = SALT_STRING) -> List[in
 
 def correct_key_verify(sigma_vec: Sequence[int], ek: o.EncryptionKey, salt: bytes = SALT_STRING) -> bool:
     """`NiCorrectKeyProof::verify(&ek, SALT_STRING)` (call site party_i.rs:288-291): gcd(P, N) == 1 and
-    sigma_i^N == rho_i (mod N) for all i [R]"""
-    if len(sigma_vec) != M2 or gcd(P_ALPHA, ek.n) != 1:
+    sigma_i^N == rho_i (mod N) for all i [R]; P = the primorial of all primes <= 6379"""
+    if len(sigma_vec) != M2 or gcd(PRIMORIAL, ek.n) != 1:
         return False
     return all(pow(s, ek.n, ek.n) == rho for s, rho in zip(sigma_vec, _rho_vec(ek.n, salt)))
 

@@ -55,6 +55,19 @@ def build():
         vss, shares = kg.vss_share(t, n, secret, coeff)
         v["vss"].append({"t": t, "n": n, "secret": H(secret), "coefficients": [H(c) for c in coeff], "shares": [H(s) for s in shares],
                          "commitments": [[H(p[0]), H(p[1])] for p in vss.commitments]})
+    # moduli with ONE small prime factor f and gcd(N, phi(N)) = 1: every sigma^N == rho check passes, so only the primorial
+    # test gcd(P, N) == 1 (P = product of the primes <= 6379) can reject them; 6389 is the first prime P does not contain
+    while True:
+        big = _prime(rng, 2034)
+        if all(big % f != 1 and (f - 1) % big != 0 for f in (3, 11, 6361, 6379, 6389)):
+            break
+    v["small_factor"] = {"q": H(big), "cases": []}
+    for f, accept in ((3, False), (11, False), (6361, False), (6379, False), (6389, True)):
+        dk = o.DecryptionKey(f, big)
+        sigma = kg.correct_key_proof(dk)
+        n = f * big
+        assert kg.correct_key_verify(sigma, o.EncryptionKey(n, n * n)) == accept
+        v["small_factor"]["cases"].append({"p": f, "accept": accept, "sigma": [H(x) for x in sigma]})
     return v
 
 

@@ -1,6 +1,5 @@
-"""CPU tests of oracle/keygen_oracle.py (the key-generation verification path).
-The CUDA entry points exist but are not validated on a GPU yet (tests/test_keygen_gpu.py is gated); these pin the
-restatement they are built against: every proof verifies, every tampered field rejects, the Feldman arithmetic agrees with the committed key fixtures."""
+"""CPU tests of oracle/keygen_oracle.py (the key-generation path).  They pin the restatement
+the CUDA entry points (tests/test_keygen_gpu.py) are checked against: every proof verifies, every tampered field rejects, the Feldman arithmetic agrees with the committed key fixtures."""
 import dataclasses
 import random
 
@@ -29,8 +28,10 @@ def test_correct_key_proof_roundtrip_and_tamper(keyset):
     assert not kg.correct_key_verify(sigma, ek, salt=b"other")
     other = keyset[1].dk.p * keyset[1].dk.q
     assert not kg.correct_key_verify(sigma, o.EncryptionKey(other, other * other))
-    # a modulus sharing a factor with P = 6370 fails the gcd test before any exponentiation
-    assert not kg.correct_key_verify(sigma, o.EncryptionKey(13 * n, (13 * n) ** 2))
+    # a modulus sharing a factor with the primorial P (all primes <= 6379) fails the gcd test before any exponentiation
+    for f in (2, 3, 11, 13, 6361, 6379):
+        assert not kg.correct_key_verify(sigma, o.EncryptionKey(f * n, (f * n) ** 2))
+    assert kg.PRIMORIAL.bit_length() == 9120 and kg.PRIMORIAL % 6379 == 0 and kg.PRIMORIAL % 6389 != 0
     # mask_generation covers the key length: 2048-bit N -> 9 digests -> a 2304-bit mask, reduced mod N
     assert kg.mask_generation(2048, 1).bit_length() > 2048
 
@@ -151,6 +152,13 @@ def test_keygen_golden_vectors(keyset):
         pf2 = kg.composite_dlog_prove(st2, I(e["xhi_inv_neg"]), I(e["r2"]))
         assert [pf1.x, pf1.y] == [I(x) for x in e["proof_h1"]] and [pf2.x, pf2.y] == [I(x) for x in e["proof_h2"]]
         assert kg.composite_dlog_verify(pf1, st1) and kg.composite_dlog_verify(pf2, st2)
+    # N = f * q with gcd(N, phi(N)) = 1: all eleven sigma^N == rho checks pass, only gcd(P, N) decides
+    q_big = I(v["small_factor"]["q"])
+    for e in v["small_factor"]["cases"]:
+        n = e["p"] * q_big
+        sigma = [I(x) for x in e["sigma"]]
+        assert all(pow(s_, n, n) == r for s_, r in zip(sigma, kg._rho_vec(n, kg.SALT_STRING)))
+        assert kg.correct_key_verify(sigma, o.EncryptionKey(n, n * n)) == e["accept"] == (e["p"] > 6379)
     for e in v["vss"]:
         vss, shares = kg.vss_share(e["t"], e["n"], I(e["secret"]), [I(c) for c in e["coefficients"]])
         assert shares == [I(s) for s in e["shares"]]
