@@ -1,26 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the GG20 offline-signing arithmetic engine.
+"""bench.py — GG20 offline-signing phases/s on B200 (BASELINE.json metric, configs[4] sharded per GPU).
 
-A "step" is one pass of the hot path over one batch of synthetic input.  At N=1 the
-workload is BASELINE.json configs[1]: a batch of 65 536 independent 2048-bit Montgomery
-modular exponentiations (2048-bit odd modulus, 2048-bit exponent), bit-exact vs GMP.
-With N>1 every rank runs the same batch size on its own GPU (independent operands shard
-with no data-path collective; "weak" scaling) and the ranks all-gather a fixed-size result
-record (status summary + digest) over NCCL at the end of every step.
+A "step" is one pass of the hot path over one batch: every rank runs 8 192 two-signer sessions = 16 384 party-phases
+("units": one party's OfflineStage Round0..Round6, t = 1, n = 3) over 8 synthetic key sets, builds the 256-byte result
+record of every unit and joins the single NCCL all-gather of those records.  Ranks hold
+disjoint sessions (weak scaling: the batch per GPU is fixed).
 
-  value  : modexp/s, whole job, operands resident in HBM, CUDA-event timed, max over ranks.
-  e2e    : same metric through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H inside
-           the timed region.
-  roofline: the path is bound by the INT32 multiply-add pipe (IMAD.WIDE.U32), not HBM and not
-           the tensor cores — `peak` is the on-box IMAD saturation
-           micro-benchmark of the library (no integer entry exists in MEASURED_PEAKS.json);
-           the HBM view (algorithmic bytes / time vs measured copy bandwidth) is reported
-           beside it under "hbm".
-  cpu_baseline: the oracle's C twin (GMP mpz_powm, the reference's default BigInt backend) on
-           the host cores — a reported baseline, not the target.
-
-`--impl reference` times that same CPU path as the reference arm (the Rust reference cannot be
-built in this image: no cargo/rustc, crates not vendored).
+  value  : phases/s, whole job, inputs resident in HBM, CUDA-event timed on the engine's stream, max over ranks.
+  e2e    : the same metric through ONE C-ABI call with HOST (pinned) buffers — tecdsa_gg20_offline_records: H2D of the
+           randomness records and session descriptors -> seven rounds -> record packing -> NCCL gather -> D2H of the
+           gathered records, all inside the timed region.
+  roofline: the path is bound by the INT32 multiply-add pipe (IMAD.WIDE.U32), not HBM and not the tensor cores
+           (SURVEY.md section 8d).  `achieved` = multiply-accumulates counted by the kernels themselves (tecdsa_ctx_work)
+           for the dominant kernel, divided by its launch durations measured with CUDA events around each of its launches
+           in this run; `peak` = the on-box IMAD.WIDE.U32 saturation micro-benchmark (MEASURED_PEAKS.json has no integer
+           entry).  The reference-operation-list view (W_unit = 2.003e9 MAC32 per unit) and the HBM view are reported beside it.
+  parity : inside the run — 256 sampled units (status, R, sigma_i, k_i, transcript digest) bit-compared with the CPU twin
+           of the oracle (GMP + OpenSSL), every session signed on the device (online step) and the sampled sessions'
+           signatures verified under OpenSSL (`cryptography`), as gg_2020/test.rs:711-748 does with libsecp256k1.
+  cpu_baseline / --impl reference: the same protocol executed the way the reference executes it on a CPU (scalar GMP
+           mpz_powm / mpz_invert, every redundant verification kept) on all host threads — oracle/gg20_twin.c; the Rust
+           reference itself cannot be built in this image (no cargo/rustc, crates not vendored).
+Secondary block `modexp`: BASELINE.json configs[1], 65 536 x 2048-bit modexp, ALL outputs compared with GMP.
 """
 from __future__ import annotations
 
@@ -39,44 +40,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH = 65536
-MOD_BITS = 2048
-EXP_BITS = 2048
-K = MOD_BITS // 32
-EL = EXP_BITS // 32
-SEED = 0xB2000002
-# W_modexp(b,e) = 1.2 * e * (2k^2 + k) MAC32, k = b/32
-W_MODEXP = 1.2 * EXP_BITS * (2 * K * K + K)
-BYTES_PER_MODEXP = 4 * K * 4            # base, exponent, modulus in, result out (1 KiB)
-WORKLOAD = "batch 64k 2048-bit Montgomery modexp on 1xB200, bit-exact vs GMP (BASELINE.json configs[1])"
+SESSIONS_PER_GPU = 8192                 # 16 384 units per GPU: configs[4] (128k units over 8 GPUs)
+SEED = 0xB2000005
+METRIC = "GG20 offline-sign phases/sec (batched)"
+UNIT = "phases/s"
+WORKLOAD = ("batch 128k full GG20 offline-signing phases (t=1,n=3) sharded over 8xB200 with NCCL gather (BASELINE.json configs[4]): "
+            "16384 phases (8192 two-signer sessions) per GPU, 8 key sets")
+W_UNIT = 2.003e9                        # MAC32 per unit, reference operation list
+BYTES_PER_UNIT = 18 * 1024              # SURVEY.md section 8(d)
+REC = 256
+# modexp block (configs[1])
+MODEXP_BATCH, K, EL, MODEXP_SEED = 65536, 64, 64, 0xB2000002
+W_MODEXP = 1.2 * 2048 * (2 * K * K + K)
+Q = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 
 
-def make_inputs(count: int, seed: int):
-    """Random odd 2048-bit moduli with the top bit set, bases below 2^2048, 2048-bit exponents
-    with the top bit set (fully-distinct-moduli variant)."""
-    rng = np.random.default_rng(seed)
-    base = rng.integers(0, 2**32, size=(count, K), dtype=np.uint32)
-    exp = rng.integers(0, 2**32, size=(count, EL), dtype=np.uint32)
-    mod = rng.integers(0, 2**32, size=(count, K), dtype=np.uint32)
-    mod[:, 0] |= 1
-    mod[:, K - 1] |= 0x80000000
-    exp[:, EL - 1] |= 0x80000000
-    return base, exp, mod
-
-
-def load_oracle_lib():
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "libgg20_ref.so"))
-    lib.oracle_gmp_version.restype = ctypes.c_char_p
-    lib.oracle_modexp_batch.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int]
-    return lib
-
-
-def cpu_modexp(lib, base, exp, mod, threads: int):
-    out = np.zeros_like(base)
-    t0 = time.perf_counter()
-    lib.oracle_modexp_batch(base.ctypes.data, exp.ctypes.data, mod.ctypes.data, None, out.ctypes.data,
-                            base.shape[0], K, EL, threads)
-    return out, time.perf_counter() - t0
+def config_dict(world: int) -> dict:
+    return {"workload": WORKLOAD, "sessions_per_gpu": SESSIONS_PER_GPU, "units_per_gpu": 2 * SESSIONS_PER_GPU, "keysets": 8, "t": 1, "n": 3,
+            "signers": 2, "seed": SEED, "parallelism": f"shard{world}", "record_bytes": REC,
+            "cache": "per-step working set (92 MB randomness records + 0.65 GB per-unit arena) exceeds the 126 MB L2"}
 
 
 def host_threads() -> int:
@@ -138,151 +120,133 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-
-# ---------------------------------------------------------------------------------------------
-# Secondary workload: the full GG20 offline-signing stage (BASELINE.json metric part 1,
-# configs[4] sharded per GPU).  SURVEY.md section 8(d): W_unit = 2.003e9 MAC32 (reference
-# operation list), ~18 KB moved per unit.
-OFFLINE_SESSIONS = 8192
-W_UNIT = 2.003e9
-W_UNIT_EXECUTED = 0.48e9      # MAC32 actually executed per unit after the declared shortcuts and the N-adic / p-adic forms
-BYTES_PER_UNIT = 18 * 1024
-
-
-def bench_offline(args, eng, pkg, torch, dist, rank, world, n_sessions):
-    from mpecdsa_b200 import gg20
+# ------------------------------------------------------------------------------------------------- workload
+def load_keysets():
     from tests.golden import fixtures
-    keysets = [fixtures.load_keyset(0), fixtures.load_keyset(1)]
-    ks = gg20.KeySets(eng, keysets)
-    sess, rnd = gg20.synthetic_batch(keysets, n_sessions, SEED + 17 * rank)
-    U = 2 * n_sessions
-    h_rnd = torch.from_numpy(rnd.view(np.int32)).pin_memory()
-    h_sess = torch.from_numpy(sess.view(np.int32)).pin_memory()
-    d_rnd, d_sess = h_rnd.cuda(), h_sess.cuda()
-    d_status = torch.empty(U, dtype=torch.uint8, device="cuda")
-    d_digest = torch.empty((U, 8), dtype=torch.int32, device="cuda")
-    d_R = torch.empty((U, 16), dtype=torch.int32, device="cuda")
-    d_sigma = torch.empty((U, 8), dtype=torch.int32, device="cuda")
-    h_status = torch.empty(U, dtype=torch.uint8).pin_memory()
-    h_digest = torch.empty((U, 8), dtype=torch.int32).pin_memory()
-    h_R = torch.empty((U, 16), dtype=torch.int32).pin_memory()
-    h_sigma = torch.empty((U, 8), dtype=torch.int32).pin_memory()
-    record = torch.zeros((U, 9), dtype=torch.int32, device="cuda")       # status + digest per unit
-    from mpecdsa_b200 import sharding
+    ks = fixtures.load_all_keysets()
+    assert len(ks) == 8, "tests/golden/keys_t1n3.json must hold the 8 key sets of config 5"
+    return ks
 
-    def call(sessions, r, status, R, sigma, digest, mem):
-        eng._ck(eng.lib.tecdsa_gg20_offline_batch(eng._ctx, ks.handle, sessions.data_ptr(), n_sessions, r.data_ptr(),
-                                                  status.data_ptr(), R.data_ptr(), sigma.data_ptr(), None, digest.data_ptr(), mem),
-                "gg20_offline_batch")
 
-    gathered = [None]
+def make_batch(keysets, n_sessions: int, rank: int):
+    """Sessions and randomness records of this rank's block (oracle-free: mpecdsa_b200.gg20.synthetic_batch)."""
+    from mpecdsa_b200 import gg20
+    return gg20.synthetic_batch(keysets, n_sessions, SEED + 0x1000 * rank)
 
-    def step_device():
-        call(d_sess, d_rnd, d_status, d_R, d_sigma, d_digest, pkg.DEVICE)
-        record[:, 0] = d_status
-        record[:, 1:] = d_digest
-        gathered[0] = sharding.gather_records(record, world)              # the single NCCL all-gather
 
-    def step_host():
-        call(h_sess, h_rnd, h_status, h_R, h_sigma, h_digest, pkg.HOST)
+def message_limbs(n_sessions: int) -> np.ndarray:
+    """The message of the reference's tests: Sha256.chain_bigint(from_bytes(b"ZenGo")).result_bigint() (sign.rs:693-696)."""
+    m = int.from_bytes(hashlib.sha256(b"ZenGo").digest(), "big")
+    row = np.frombuffer(m.to_bytes(32, "little"), dtype="<u4")
+    return np.ascontiguousarray(np.tile(row, (n_sessions, 1))), m
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier(); torch.cuda.synchronize()
 
-    steps = max(1, min(args.steps, 3))
-    step_device(); barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = eng.launch_count()
-    ev0.record()
-    for _ in range(steps):
-        step_device()
-    ev1.record(); barrier()
-    dev_ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - launches0
-    k_ms, k_launches = eng.last_kernel_ms()
-    step_host(); barrier()
+# ------------------------------------------------------------------------------------------------- CPU arm (oracle twin)
+def cpu_phases(keysets, n_sessions: int, threads: int, seed_rank: int = 1000):
+    """Time the oracle's C twin (the reference's scalar GMP path) on `n_sessions` sessions of the same workload."""
+    from oracle import twin
+    kt = twin.KeyTables(keysets)
+    sess, rnd = make_batch(keysets, n_sessions, seed_rank)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step_host()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([dev_ms, e2e_ms, k_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, k_ms = (float(x) for x in t.tolist())
-    all_ok = bool((gathered[0][:, :, 0] == 0).all().item()) and bool((h_status == 0).all().item())
-    same = bool(torch.equal(h_digest, d_digest.cpu()))
-    ks.free()
-    total_units = U * world
-    return {
-        "metric": "GG20 (t=1,n=3) offline-signing phases/s", "value": total_units * steps / (dev_ms * 1e-3), "unit": "phases/s",
-        "units_per_gpu": U, "sessions_per_gpu": n_sessions, "steps": steps, "ms_per_step": dev_ms / steps,
-        "e2e": {"value": total_units * steps / (e2e_ms * 1e-3), "unit": "phases/s", "h2d_bytes_per_step": int(rnd.nbytes + sess.nbytes),
-                "d2h_bytes_per_step": int(U * (1 + 32 + 64 + 32)), "ms_per_step": e2e_ms / steps},
-        "gpu_launches_per_step": int(launches // steps), "kernels_ms_per_step": k_ms,
-        "all_units_ok": all_ok, "host_and_device_paths_agree": same,
-        "work": {"W_unit_reference_oplist_mac32": W_UNIT, "W_unit_executed_mac32": W_UNIT_EXECUTED,
-                 "achieved_reference_oplist_tmac32": W_UNIT * U / (k_ms * 1e-3) / 1e12,
-                 "achieved_executed_tmac32": W_UNIT_EXECUTED * U / (k_ms * 1e-3) / 1e12,
-                 "hbm_algorithmic_gbs": BYTES_PER_UNIT * U / (k_ms * 1e-3) / 1e9},
-    }
-
-
-def cpu_unit_baseline(threads: int):
-    lib = load_oracle_lib()
-    lib.oracle_unit_oplist.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64]
-    units = max(threads, 8)
-    t0 = time.perf_counter()
-    lib.oracle_unit_oplist(units, threads, 7)
+    res = twin.offline_batch(kt, sess, rnd, threads)
     dt = time.perf_counter() - t0
-    return {"value": units / dt, "unit": "phases/s", "cores": threads, "kind": "port",
-            "sample": f"{units} units: the reference's big-integer operation list of one OfflineStage (76 mpz_powm + 22 mpz_invert at the "
-                      f"reference's operand sizes, redundant verifications included; EC/hash <1 % omitted), GMP {lib.oracle_gmp_version().decode()}"}
+    if not (res.status == 0).all():
+        raise SystemExit("CPU twin: a unit failed on valid inputs")
+    return 2 * n_sessions / dt, dt
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path (GMP mpz_powm behind
-    BigInt::mod_pow) on all host threads; each step a bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """Reference arm: the reference's CPU implementation of the path (scalar BigInt calls over GMP, secp256k1 on the CPU) on all
+    host threads through a persistent thread pool; each step is a bounded sample of the workload."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    lib = load_oracle_lib()
+    from oracle import twin
     threads = host_threads()
-    sample = max(threads * 16, 512)
-    base, exp, mod = make_inputs(sample, SEED)
-    for _ in range(args.warmup):
-        cpu_modexp(lib, base[: threads * 2], exp[: threads * 2], mod[: threads * 2], threads)
-    t = 0.0
-    for _ in range(args.steps):
-        _, dt = cpu_modexp(lib, base, exp, mod, threads)
-        t += dt
-    value = sample * args.steps / t
+    keysets = load_keysets()
+    per_step = max(threads * 4, 16)                     # sessions per step: 8 units per thread (~2.7 s of GMP work per thread)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_phases(keysets, max(threads, 8), threads)
+    t, units = 0.0, 0
+    for i in range(args.steps):
+        v, dt = cpu_phases(keysets, per_step, threads, seed_rank=2000 + i)
+        t += dt; units += 2 * per_step
+    value = units / t
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     line = {
-        "impl": "reference", "metric": "2048-bit modexp/s", "value": value, "unit": "modexp/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "mod_bits": MOD_BITS, "exp_bits": EXP_BITS,
-                   "note": "CPU arm: oracle C twin over GMP %s (the backend of the reference's default feature); the Rust "
-                           "reference itself cannot be built here (no cargo/rustc, crates not vendored)" % lib.oracle_gmp_version().decode()},
-        "cpu_baseline": {"value": value, "unit": "modexp/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} modexps per step x {args.steps} steps, cpu={cpu_model()}"},
-        "e2e": {"value": value, "unit": "modexp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": config_dict(world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{2 * per_step} phases ({per_step} sessions) per step x {args.steps} steps of the same workload, persistent pool of {threads} threads, "
+                                   f"oracle/gg20_twin.c: the reference's scalar call sequence over GMP {twin.lib().oracle_gmp_version().decode()} mpz_powm/mpz_invert + OpenSSL "
+                                   f"secp256k1/SHA-256, redundant verifications kept; cpu={cpu_model()}; the Rust reference cannot be built here (no cargo/rustc, crates not vendored)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------- modexp block
+def modexp_inputs(count: int, seed: int):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 2**32, size=(count, K), dtype=np.uint32)
+    exp = rng.integers(0, 2**32, size=(count, EL), dtype=np.uint32)
+    mod = rng.integers(0, 2**32, size=(count, K), dtype=np.uint32)
+    mod[:, 0] |= 1
+    mod[:, K - 1] |= 0x80000000
+    exp[:, EL - 1] |= 0x80000000
+    return base, exp, mod
+
+
+def bench_modexp(eng, pkg, torch, rank, steps: int, threads: int, check: bool):
+    """configs[1]: 65 536 independent 2048-bit modexps with distinct moduli; every output compared with GMP mpz_powm."""
+    base, exp, mod = modexp_inputs(MODEXP_BATCH, MODEXP_SEED + rank)
+    d_base, d_exp, d_mod = (torch.from_numpy(x.view(np.int32)).cuda() for x in (base, exp, mod))
+    d_out = torch.empty((MODEXP_BATCH, K), dtype=torch.int32, device="cuda")
+    d_st = torch.empty(MODEXP_BATCH, dtype=torch.uint8, device="cuda")
+
+    def step():
+        eng.modexp_raw(2048, EL, d_base, d_exp, d_mod, d_out, d_st, mem=pkg.DEVICE)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    eng.work(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    macs = eng.work() / steps
+    out = {"metric": "2048-bit modexp/s", "value": MODEXP_BATCH / (ms * 1e-3), "unit": "modexp/s", "batch": MODEXP_BATCH, "steps": steps,
+           "ms_per_step": ms, "executed_mac32_per_modexp": macs / MODEXP_BATCH, "reference_mac32_per_modexp": W_MODEXP}
+    if check:
+        lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "libgg20_ref.so"))
+        lib.oracle_modexp_batch.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        want = np.zeros_like(base)
+        t0 = time.perf_counter()
+        lib.oracle_modexp_batch(base.ctypes.data, exp.ctypes.data, mod.ctypes.data, None, want.ctypes.data, MODEXP_BATCH, K, EL, threads)
+        dt = time.perf_counter() - t0
+        got = d_out.cpu().numpy().view(np.uint32)
+        out["outputs_compared_with_gmp"] = MODEXP_BATCH
+        out["parity_ok"] = bool(np.array_equal(got, want)) and bool((d_st == 0).all().item())
+        out["cpu_baseline"] = {"value": MODEXP_BATCH / dt, "unit": "modexp/s", "cores": threads, "kind": "port",
+                               "sample": f"all {MODEXP_BATCH} modexps of the batch, GMP mpz_powm on {threads} threads"}
+    return out, ms, macs
+
+
+# ------------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
+    ap.add_argument("--sessions", type=int, default=SESSIONS_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--offline-sessions", type=int, default=OFFLINE_SESSIONS, help="sessions per GPU for the offline-stage section (0 = skip)")
+    ap.add_argument("--no-modexp", action="store_true", help="skip the secondary modexp block")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -302,30 +266,45 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = entry.load_package()
+    from mpecdsa_b200 import gg20
     stream = torch.cuda.current_stream()
     eng = pkg.Engine(local_rank, stream.cuda_stream)
-    batch = args.batch
+    threads = host_threads()
 
-    # ---- inputs: rank-distinct synthetic operands, one device-resident copy, one pinned host copy
-    base, exp, mod = make_inputs(batch, SEED + rank)
-    h_base, h_exp, h_mod = (torch.from_numpy(x.view(np.int32)).pin_memory() for x in (base, exp, mod))
-    h_out = torch.empty((batch, K), dtype=torch.int32).pin_memory()
-    h_st = torch.empty(batch, dtype=torch.uint8).pin_memory()
-    d_base, d_exp, d_mod = (x.cuda(non_blocking=True) for x in (h_base, h_exp, h_mod))
-    d_out = torch.empty((batch, K), dtype=torch.int32, device="cuda")
-    d_st = torch.empty(batch, dtype=torch.uint8, device="cuda")
-    record = torch.zeros(8, dtype=torch.int64, device="cuda")            # per-rank result record
-    gathered = torch.zeros(8 * world, dtype=torch.int64, device="cuda")
+    # ---- the workload: this rank's block of sessions, one pinned host copy, one device-resident copy
+    n_sessions = args.sessions
+    U = 2 * n_sessions
+    keysets = load_keysets()
+    ks = gg20.KeySets(eng, keysets)
+    sess, rnd = make_batch(keysets, n_sessions, rank)
+    h_rnd = torch.from_numpy(rnd.view(np.int32)).pin_memory()
+    h_sess = torch.from_numpy(sess.view(np.int32)).pin_memory()
+    d_rnd, d_sess = h_rnd.cuda(), h_sess.cuda()
+    d_status = torch.empty(U, dtype=torch.uint8, device="cuda")
+    d_R = torch.empty((U, 16), dtype=torch.int32, device="cuda")
+    d_sigma = torch.empty((U, 8), dtype=torch.int32, device="cuda")
+    d_tvec = torch.empty((U, 32), dtype=torch.int32, device="cuda")
+    d_digest = torch.empty((U, 8), dtype=torch.int32, device="cuda")
+    d_rec = torch.empty((U, REC), dtype=torch.uint8, device="cuda")
+    d_all = torch.empty((world, U, REC), dtype=torch.uint8, device="cuda")
+    h_all = torch.empty((world, U, REC), dtype=torch.uint8).pin_memory()
+
+    # ---- the communicator of the single gather: id drawn by rank 0, handed round through torch.distributed
+    comm = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.from_numpy(eng.nccl_unique_id()))
+        dist.broadcast(idt, 0)
+        comm = eng.nccl_comm_create(idt.cpu().numpy(), world, rank)
 
     def step_device():
-        eng.modexp_raw(MOD_BITS, EL, d_base, d_exp, d_mod, d_out, d_st, mem=pkg.DEVICE)
-        if world > 1:
-            record[0] = d_st.sum()
-            record[1:5] = d_out[:, :4].to(torch.int64).sum(dim=0)
-            dist.all_gather_into_tensor(gathered, record)
+        gg20.offline_raw(eng, ks, d_sess, n_sessions, d_rnd, d_status, d_R, d_sigma, d_tvec, d_digest, pkg.DEVICE)
+        eng.pack_records(d_status, d_R, d_sigma, d_tvec, d_digest, d_rnd, U, d_rec)
+        eng.gather_results(comm, d_rec, U, d_all)                     # the single NCCL all-gather (identity copy on one rank)
 
-    def step_host():
-        eng.modexp_raw(MOD_BITS, EL, h_base, h_exp, h_mod, h_out, h_st, mem=pkg.HOST)
+    def step_e2e():
+        eng.offline_records(ks, comm, h_sess, n_sessions, h_rnd, h_all, pkg.HOST)
 
     def barrier():
         torch.cuda.synchronize()
@@ -333,133 +312,179 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident timing (value) + per-launch kernel time (roofline)
+    # ---- device-resident timing
     for _ in range(args.warmup):
         step_device()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    eng.work(reset=True)
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
-        kernel_ms.append(None)
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
-    # kernel-only duration of one launch (events recorded by the library around the kernel)
-    step_device(); torch.cuda.synchronize()
-    k_ms, k_launches = eng.last_kernel_ms()
+    macs_per_step = eng.work() / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    dev_records = d_all[rank].cpu().numpy().copy()
 
-    # ---- end-to-end timing through the C ABI with host buffers
-    for _ in range(2):
-        step_host()
+    # ---- per-launch durations of the job kernels (CUDA events around every launch, one extra step, single stream)
+    prof = eng.profile_step(step_device)
+
+    # ---- end to end: host buffers in, host records out, copies inside the timed region
+    step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_host()
+        step_e2e()
     barrier()
-    e2e_s = time.perf_counter() - t0
-
-    t = torch.tensor([dev_ms, e2e_s * 1e3, k_ms], dtype=torch.float64, device="cuda")
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, k_ms = (float(x) for x in t.tolist())
+    dev_ms, e2e_ms = (float(x) for x in t.tolist())
+    e2e_records = h_all.numpy()
 
-    # ---- parity spot check inside the bench (not timed): sample vs the GMP oracle
-    ok = bool((d_st == 0).all().item()) and bool((h_st == 0).all().item())
+    # ---- the online step for every session (device), statuses must be OK
+    msg, m_int = message_limbs(n_sessions)
+    d_k = torch.from_numpy(np.ascontiguousarray(rnd[:, 8:16]).view(np.int32)).cuda()
+    sig = gg20.sign_batch(eng, ks, sess, msg, d_R.cpu().numpy().view(np.uint32), d_sigma.cpu().numpy().view(np.uint32),
+                          d_k.cpu().numpy().view(np.uint32))
+    all_ok = bool((dev_records[:, 0] == 0).all()) and bool((sig["status"] == 0).all())
+    paths_agree = bool(np.array_equal(e2e_records[rank], dev_records))
+    gather_ok = True
+    if world > 1:
+        # every rank's block must have arrived identically on every rank: compare a digest of the gathered buffer
+        dg = torch.tensor([int.from_bytes(hashlib.sha256(e2e_records.tobytes()).digest()[:7], "big")], dtype=torch.int64, device="cuda")
+        lo, hi = dg.clone(), dg.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        gather_ok = bool((lo == hi).item()) and bool((e2e_records[:, :, 0] == 0).all())
+
+    parity = None
     if rank == 0:
-        lib = load_oracle_lib()
-        idx = np.linspace(0, batch - 1, 64).astype(np.int64)
-        want, _ = cpu_modexp(lib, np.ascontiguousarray(base[idx]), np.ascontiguousarray(exp[idx]),
-                             np.ascontiguousarray(mod[idx]), 4)
-        got_dev = d_out.cpu().numpy().view(np.uint32)[idx]
-        got_host = h_out.numpy().view(np.uint32)[idx]
-        ok = ok and np.array_equal(want, got_dev) and np.array_equal(want, got_host)
+        parity = parity_block(keysets, sess, rnd, dev_records, sig, m_int, threads)
 
-    offline = None
-    if args.offline_sessions > 0:
+    modexp = None
+    if not args.no_modexp:
         try:
-            offline = bench_offline(args, eng, pkg, torch, dist, rank, world, args.offline_sessions)
-        except Exception as exc:          # the secondary section must not take the headline line down with it
-            offline = {"error": f"{type(exc).__name__}: {exc}"}
+            modexp, _, _ = bench_modexp(eng, pkg, torch, rank, max(1, min(args.steps, 3)), threads, check=(rank == 0))
+        except Exception as exc:
+            modexp = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
+        if comm is not None:
+            eng.nccl_comm_destroy(comm)
         if world > 1:
             dist.destroy_process_group()
         return
 
-    total = batch * world
-    value = total * args.steps / (dev_ms * 1e-3)
-    e2e_value = total * args.steps / (e2e_ms * 1e-3)
-    peak_mac, peak_ms = eng.imad_peak()
-    achieved_mac = W_MODEXP * batch / (k_ms * 1e-3)
+    total_units = U * world
+    value = total_units * args.steps / (dev_ms * 1e-3)
+    e2e_value = total_units * args.steps / (e2e_ms * 1e-3)
+    step_ms = dev_ms / args.steps
+    peak_mac, _ = eng.imad_peak()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
-    hbm_achieved = BYTES_PER_MODEXP * batch / (k_ms * 1e-3) / 1e9
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
+    roofline = {"bound": "int32-mad", "unit": "TMAC32/s", "peak": peak_mac / 1e12,
+                "peak_source": "on-box IMAD.WIDE.U32 saturation micro-benchmark (tecdsa_imad_peak); MEASURED_PEAKS.json has no integer entry"}
+    if dom:
+        name, d = dom
+        ach = d["mac32"] / (d["ms"] * 1e-3)
+        roofline.update({"kernel": name, "achieved": ach / 1e12, "frac": ach / peak_mac, "kernel_ms_per_step": d["ms"], "launches_per_step": d["launches"],
+                         "work_per_step_mac32": d["mac32"], "work_source": "counted by the kernel (tecdsa_ctx_work), CUDA events around each launch",
+                         "share_of_step_kernel_time": d["ms"] / sum(x["ms"] for x in prof.values()), "traffic": None})
+    roofline["whole_step"] = {
+        "ms_per_step": step_ms, "executed_mac32_per_unit": macs_per_step / U,
+        "achieved_executed": macs_per_step / (step_ms * 1e-3) / 1e12, "frac_executed": macs_per_step / (step_ms * 1e-3) / peak_mac,
+        "reference_oplist_mac32_per_unit": W_UNIT,
+        "achieved_reference_oplist": W_UNIT * U / (step_ms * 1e-3) / 1e12, "frac_reference_oplist": W_UNIT * U / (step_ms * 1e-3) / peak_mac,
+        "note": "reference-oplist figures exceed the executed ones because of the declared value-preserving shortcuts (DESIGN.md section 4)"}
+    roofline["hbm"] = {"achieved": BYTES_PER_UNIT * U / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": BYTES_PER_UNIT * U / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                       "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"}
+    roofline["kernels"] = prof
 
     cpu = None
     if not args.no_cpu_baseline:
-        lib = load_oracle_lib()
-        threads = host_threads()
-        sample = max(threads * 48, 1024)                 # ~3 ms each -> 10-30 s of CPU work in total
-        sb, se, sm_ = make_inputs(sample, SEED + 999)
-        _, dt = cpu_modexp(lib, sb, se, sm_, threads)
-        _, dt1 = cpu_modexp(lib, sb[:64], se[:64], sm_[:64], 1)
-        cpu = {"value": sample / dt, "unit": "modexp/s", "cores": threads, "kind": "port",
-               "sample": f"{sample} modexps of the same shape on {threads} threads (GMP {lib.oracle_gmp_version().decode()} mpz_powm, "
-                         f"{cpu_model()}); single thread: {64 / dt1:.1f} modexp/s"}
+        from oracle import twin
+        n_cpu = max(threads * 16, 64)                 # 32 phases per thread, ~10 s of GMP work each
+        v, dt = cpu_phases(keysets, n_cpu, threads)
+        v1, dt1 = cpu_phases(keysets, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{2 * n_cpu} phases ({n_cpu} sessions) of the same workload in {dt:.1f} s on a persistent pool of {threads} threads (oracle/gg20_twin.c: the "
+                         f"reference's scalar call sequence, GMP {twin.lib().oracle_gmp_version().decode()} + OpenSSL, {cpu_model()}); single thread: {v1:.2f} phases/s"}
 
     line = {
-        "metric": "2048-bit modexp/s", "value": value, "unit": "modexp/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": batch, "mod_bits": MOD_BITS, "exp_bits": EXP_BITS,
-                   "distinct_moduli": True, "window_bits": 5, "parallelism": f"shard{world}",
-                   "cache": "per-step working set (48 MiB operands + 512 MiB window tables) exceeds the 126 MB L2",
-                   "parity_ok": ok},
-        "e2e": {"value": e2e_value, "unit": "modexp/s", "h2d_bytes_per_step": int(batch * (2 * K + EL) * 4),
-                "d2h_bytes_per_step": int(batch * (K * 4 + 1)), "ms_per_step": e2e_ms / args.steps},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": config_dict(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rnd.nbytes + sess.nbytes), "d2h_bytes_per_step": int(world * U * REC),
+                "ms_per_step": e2e_ms / args.steps, "call": "tecdsa_gg20_offline_records(TECDSA_HOST)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "int32-mad", "achieved": achieved_mac / 1e12, "peak": peak_mac / 1e12, "unit": "TMAC32/s",
-                     "frac": achieved_mac / peak_mac,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture of this kernel
-                     # (profiles/r01_ncu_modexp2048_summary.md): window tables written once and re-read; algorithmic bytes are 64 MiB
-                     "traffic": 1.863e9 if batch == BATCH else None,
-                     "kernel": "modexp_kernel<64,TPI>", "kernel_ms": k_ms, "launches_per_step": k_launches,
-                     "work_per_launch_mac32": W_MODEXP * batch,
-                     "peak_source": "on-box IMAD.WIDE.U32 saturation micro-benchmark (tecdsa_imad_peak); "
-                                    "MEASURED_PEAKS.json has no integer entry",
-                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                             "peak_source": hbm_src, "algorithmic_bytes_per_launch": BYTES_PER_MODEXP * batch}},
+        "sessions_per_s": value / 2,
+        "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "offline_stage": offline,
+        "parity": {"all_units_ok": all_ok, "host_and_device_paths_agree": paths_agree, "gather_consistent": gather_ok, **(parity or {})},
+        "modexp": modexp,
     }
-    if offline is not None and "error" not in offline:
-        offline["roofline_frac_reference_oplist"] = offline["work"]["achieved_reference_oplist_tmac32"] * 1e12 / peak_mac
-        offline["roofline_frac_executed"] = offline["work"]["achieved_executed_tmac32"] * 1e12 / peak_mac
-        if not args.no_cpu_baseline:
-            offline["cpu_baseline"] = cpu_unit_baseline(host_threads())
     print(json.dumps(line), flush=True)
+    if comm is not None:
+        eng.nccl_comm_destroy(comm)
     if world > 1:
         dist.destroy_process_group()
-    if not ok:
-        raise SystemExit("parity check against the oracle FAILED")
-    if offline is not None and "error" in offline:
-        raise SystemExit("offline stage section failed: " + offline["error"])
-    if offline is not None and not (offline["all_units_ok"] and offline["host_and_device_paths_agree"]):
-        raise SystemExit("offline stage: a unit failed or the host/device paths disagree")
+    p = line["parity"]
+    if not (p["all_units_ok"] and p["host_and_device_paths_agree"] and p["gather_consistent"] and p.get("units_match_cpu_twin") and p.get("signatures_verify")):
+        raise SystemExit("parity check FAILED: " + json.dumps(p))
+    if modexp is not None and ("error" in modexp or not modexp.get("parity_ok", True)):
+        raise SystemExit("modexp block failed: " + json.dumps(modexp))
+
+
+def parity_block(keysets, sess, rnd, records, sig, m_int, threads):
+    """256 units (128 sessions spread over the batch) against the oracle's C twin, and their signatures against OpenSSL."""
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec, utils
+    from oracle import gg20_oracle as o
+    from oracle import twin
+    n_sessions = sess.shape[0]
+    pick = np.unique(np.linspace(0, n_sessions - 1, min(128, n_sessions)).astype(np.int64))
+    units = np.stack([2 * pick, 2 * pick + 1], axis=1).reshape(-1)
+    res = twin.offline_batch(twin.KeyTables(keysets), sess[pick], rnd[units], threads)
+
+    def be(limbs):            # [n][8] little-endian limbs -> [n][32] big-endian bytes
+        return np.ascontiguousarray(limbs[:, ::-1]).astype(">u4").view(np.uint8).reshape(limbs.shape[0], 32)
+
+    got = records[units]
+    ok = bool((res.status == 0).all()) and bool((got[:, 0] == 0).all())
+    ok = ok and np.array_equal(got[:, 164:196], be(res.digest))
+    ok = ok and np.array_equal(got[:, 34:66], be(res.sigma)) and np.array_equal(got[:, 66:98], be(res.k))
+    ok = ok and np.array_equal(got[:, 2:34], be(res.R[:, :8])) and np.array_equal(got[:, 1], 2 + (res.R[:, 8] & 1).astype(np.uint8))
+    ok = ok and np.array_equal(got[:, 99:131], be(res.t_vec[:, :8])) and np.array_equal(got[:, 132:164], be(res.t_vec[:, 16:24]))
+    # signatures: (r, s) of every sampled session verifies under OpenSSL against the key set's public key y
+    sig_ok = True
+    digest = m_int.to_bytes(32, "big")
+    for s in pick:
+        y = keysets[int(sess[s, 0])][0].y_sum_s
+        pub = ec.EllipticCurvePublicNumbers(y[0], y[1], ec.SECP256K1()).public_key()
+        r = int.from_bytes(sig["r"][s].tobytes(), "little"); sv = int.from_bytes(sig["s"][s].tobytes(), "little")
+        try:
+            pub.verify(utils.encode_dss_signature(r, sv), digest, ec.ECDSA(utils.Prehashed(hashes.SHA256())))
+        except Exception:
+            sig_ok = False
+        sig_ok = sig_ok and o.ecdsa_verify(r, sv, y, m_int) and sv <= Q - sv
+    return {"units_compared_with_cpu_twin": int(len(units)), "units_match_cpu_twin": bool(ok), "signatures_checked": int(len(pick)),
+            "signatures_verify": bool(sig_ok), "checker": "oracle/gg20_twin.c (GMP + OpenSSL) bit-compare of status, R, sigma_i, k_i, t_vec, transcript digest; "
+                                                          "ECDSA verify under OpenSSL (`cryptography`) and the oracle's in-tree `verify`"}
 
 
 if __name__ == "__main__":

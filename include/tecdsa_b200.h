@@ -292,6 +292,51 @@ enum {
 int tecdsa_gg20_offline_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
                               const uint32_t* rnd, uint8_t* status, uint32_t* R, uint32_t* sigma, uint32_t* t_vec,
                               uint32_t* digest, int mem);
+/* ---- result records, their multi-GPU gather, and the end-to-end call ---------------------------------------------------
+ * One 256-byte record per unit = the fields of CompletedOfflineStage (sign/rounds.rs:647-654) in the
+ * reference's byte encodings: status byte, R and t_vec as `Point::to_bytes(true)` (33 bytes), sigma_i and k_i
+ * (`sign_keys.k_i`) as 32-byte big-endian scalars, and the 32-byte transcript digest; the rest is zero.                  */
+enum {
+    TECDSA_REC_BYTES = 256, TECDSA_REC_STATUS = 0, TECDSA_REC_R = 1, TECDSA_REC_SIGMA = 34, TECDSA_REC_K = 66,
+    TECDSA_REC_T0 = 98, TECDSA_REC_T1 = 131, TECDSA_REC_DIGEST = 164
+};
+/* records[u] from the per-unit outputs of tecdsa_gg20_offline_batch and the batch's randomness records (k_i); DEVICE pointers. */
+int tecdsa_gg20_pack_records(tecdsa_ctx* ctx, const uint8_t* status, const uint32_t* R, const uint32_t* sigma, const uint32_t* t_vec,
+                             const uint32_t* digest, const uint32_t* rnd, size_t n_units, uint8_t* records);
+/* The single collective of the path: all_records[rank][n_units][256] on every rank = ncclAllGather of each rank's
+ * records[n_units][256] on the context stream (DEVICE pointers; `nccl_comm` is an ncclComm_t; NULL = one rank, a copy).
+ * NCCL is bound at run time to the libnccl.so.2 already loaded in the process (no link-time dependency).                 */
+int tecdsa_gather_results(tecdsa_ctx* ctx, void* nccl_comm, const uint8_t* records, size_t n_units, uint8_t* all_records);
+/* Communicator plumbing for callers that do not already hold an ncclComm_t: rank 0 draws an id (`ncclGetUniqueId`) and
+ * distributes its 128 bytes out of band; every rank then creates its communicator for the context's device.             */
+enum { TECDSA_NCCL_ID_BYTES = 128 };
+int tecdsa_nccl_unique_id(uint8_t id[TECDSA_NCCL_ID_BYTES]);
+int tecdsa_nccl_comm_create(tecdsa_ctx* ctx, const uint8_t id[TECDSA_NCCL_ID_BYTES], int nranks, int rank, void** nccl_comm);
+int tecdsa_nccl_comm_destroy(void* nccl_comm);
+/* End to end: sessions / rnd as for tecdsa_gg20_offline_batch; H2D of the inputs -> Round0..6 -> pack -> gather -> D2H, all on
+ * the context stream.  all_records = [nranks][2*n_sessions][256] (nranks = 1 when nccl_comm == NULL); with TECDSA_HOST the
+ * call returns after the records have landed in host memory.                                                            */
+int tecdsa_gg20_offline_records(tecdsa_ctx* ctx, const tecdsa_keyset* ks, void* nccl_comm, const uint32_t* sessions, size_t n_sessions,
+                                const uint32_t* rnd, uint8_t* all_records, int mem);
+/* ---- online step (gg_2020/party_i.rs:850-936) for a batch of completed two-signer sessions ------------------------------
+ * message = [n_sessions][8] (the BigInt being signed, reduced mod q like `Scalar::from`), R / sigma / k = per-unit outputs of
+ * the offline stage ([2n][16], [2n][8], [2n][8]).  s_i (optional, [2n][8]) = `phase7_local_sig`: m k_i + r sigma_i;
+ * (sig_r, sig_s, recid) = `output_signature` over both signers' s_i (low-s normalised); status = TECDSA_ST_OK or
+ * TECDSA_ST_INVALID_SIG from the in-tree `verify` against the key set's y (Error::InvalidSig, party_i.rs:908,934).       */
+int tecdsa_gg20_sign_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions, const uint32_t* message,
+                           const uint32_t* R, const uint32_t* sigma, const uint32_t* k, uint32_t* s_i, uint32_t* sig_r, uint32_t* sig_s,
+                           uint8_t* recid, uint8_t* status, int mem);
+/* 32x32+64 multiply-accumulates executed by the big-integer kernels of this context since creation / the last reset:
+ * counted by the kernels themselves (one atomic add per job, from the loop trip counts of the products it ran) — the
+ * "ops actually executed" figure of SURVEY.md section 8(d).  EC / hashing glue and the shift-subtract inversions are not
+ * multiply-accumulate work and are not counted.                                                                          */
+int tecdsa_ctx_work(tecdsa_ctx* ctx, uint64_t* mac32, int reset);
+/* Per-launch profiling: while enabled, every kernel launch of this context is bracketed by CUDA events on the context stream
+ * and the executed-work counter is snapshotted after it (batches then run on the one stream, without the two-stream split).
+ * profile_read waits for the stream and returns up to `cap` launches in launch order; *n = how many were recorded.          */
+typedef struct { char kernel[48]; float ms; uint64_t mac32; } tecdsa_launch_info;
+int tecdsa_ctx_profile(tecdsa_ctx* ctx, int enable);
+int tecdsa_ctx_profile_read(tecdsa_ctx* ctx, tecdsa_launch_info* out, size_t cap, size_t* n);
 /* test access: copy one named per-unit field of the last batch (names in csrc/gg20_fields.h) */
 int tecdsa_gg20_debug_field(tecdsa_ctx* ctx, const char* name, uint32_t* out_host, size_t* limbs_per_unit);
 

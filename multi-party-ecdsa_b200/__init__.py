@@ -38,6 +38,8 @@ EXPORTS = [
     "tecdsa_heg_prove_batch", "tecdsa_heg_verify_batch", "tecdsa_sha256_bigints_batch", "tecdsa_hash_commitment_batch",
     "tecdsa_mta_message_a_batch", "tecdsa_mta_message_b_batch", "tecdsa_mta_get_alpha_batch",
     "tecdsa_correct_key_verify_batch", "tecdsa_composite_dlog_verify_batch", "tecdsa_vss_validate_share_batch",
+    "tecdsa_gg20_pack_records", "tecdsa_gather_results", "tecdsa_nccl_unique_id", "tecdsa_nccl_comm_create", "tecdsa_nccl_comm_destroy",
+    "tecdsa_gg20_offline_records", "tecdsa_gg20_sign_batch", "tecdsa_ctx_work", "tecdsa_ctx_profile", "tecdsa_ctx_profile_read",
     "tecdsa_correct_key_prove_batch", "tecdsa_composite_dlog_prove_batch", "tecdsa_vss_share_batch", "tecdsa_h1_h2_n_tilde_batch",
 ]
 
@@ -252,5 +254,94 @@ def _paillier_decrypt(self, keysets_handle, key_rows, c):
     return limbs_to_ints(out)
 
 
+# ----------------------------------------------------------------------------- records, gather, profiling
+REC_BYTES = 256
+REC = {"status": (0, 1), "R": (1, 33), "sigma": (34, 32), "k": (66, 32), "t0": (98, 33), "t1": (131, 33), "digest": (164, 32)}   # (offset, bytes)
+
+
+class _LaunchInfo(ctypes.Structure):
+    _fields_ = [("kernel", ctypes.c_char * 48), ("ms", ctypes.c_float), ("mac32", ctypes.c_uint64)]
+
+
+def _bind_rec(lib):
+    if getattr(lib, "_rec_bound", False):
+        return
+    V, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.tecdsa_gg20_pack_records.argtypes = [V] * 7 + [S, V]
+    lib.tecdsa_gather_results.argtypes = [V, V, V, S, V]
+    lib.tecdsa_nccl_unique_id.argtypes = [V]
+    lib.tecdsa_nccl_comm_create.argtypes = [V, V, I, I, ctypes.POINTER(V)]
+    lib.tecdsa_nccl_comm_destroy.argtypes = [V]
+    lib.tecdsa_gg20_offline_records.argtypes = [V, V, V, V, S, V, V, I]
+    lib.tecdsa_ctx_work.argtypes = [V, ctypes.POINTER(ctypes.c_uint64), I]
+    lib.tecdsa_ctx_profile.argtypes = [V, I]
+    lib.tecdsa_ctx_profile_read.argtypes = [V, ctypes.POINTER(_LaunchInfo), S, ctypes.POINTER(S)]
+    lib._rec_bound = True
+
+
+def _work(self, reset: bool = False) -> int:
+    """multiply-accumulates (32x32+64) executed by the big-integer kernels since the last reset (tecdsa_ctx_work)"""
+    _bind_rec(self.lib)
+    v = ctypes.c_uint64()
+    self._ck(self.lib.tecdsa_ctx_work(self._ctx, ctypes.byref(v), 1 if reset else 0), "ctx_work")
+    return int(v.value)
+
+
+def _pack_records(self, status, R, sigma, t_vec, digest, rnd, n_units, records):
+    _bind_rec(self.lib)
+    self._ck(self.lib.tecdsa_gg20_pack_records(self._ctx, _ptr(status), _ptr(R), _ptr(sigma), _ptr(t_vec), _ptr(digest), _ptr(rnd), n_units, _ptr(records)), "pack_records")
+
+
+def _gather_results(self, comm, records, n_units, all_records):
+    _bind_rec(self.lib)
+    self._ck(self.lib.tecdsa_gather_results(self._ctx, comm, _ptr(records), n_units, _ptr(all_records)), "gather_results")
+
+
+def _nccl_unique_id(self) -> np.ndarray:
+    _bind_rec(self.lib)
+    out = np.zeros(128, dtype=np.uint8)
+    self._ck(self.lib.tecdsa_nccl_unique_id(out.ctypes.data), "nccl_unique_id")
+    return out
+
+
+def _nccl_comm_create(self, uid: np.ndarray, nranks: int, rank: int):
+    _bind_rec(self.lib)
+    uid = np.ascontiguousarray(uid, dtype=np.uint8)
+    comm = ctypes.c_void_p()
+    self._ck(self.lib.tecdsa_nccl_comm_create(self._ctx, uid.ctypes.data, nranks, rank, ctypes.byref(comm)), "nccl_comm_create")
+    return comm
+
+
+def _nccl_comm_destroy(self, comm):
+    _bind_rec(self.lib)
+    self._ck(self.lib.tecdsa_nccl_comm_destroy(comm), "nccl_comm_destroy")
+
+
+def _offline_records(self, keys, comm, sessions, n_sessions, rnd, all_records, mem=HOST):
+    """tecdsa_gg20_offline_records: inputs -> Round0..6 -> 256-byte records -> gather -> (HOST) D2H, one call"""
+    _bind_rec(self.lib)
+    self._ck(self.lib.tecdsa_gg20_offline_records(self._ctx, keys.handle, comm, _ptr(sessions), n_sessions, _ptr(rnd), _ptr(all_records), mem), "gg20_offline_records")
+
+
+def _profile_step(self, fn):
+    """Run fn() once with per-launch CUDA-event profiling on -> {kernel: {"ms", "launches", "mac32"}}"""
+    _bind_rec(self.lib)
+    self._ck(self.lib.tecdsa_ctx_profile(self._ctx, 1), "ctx_profile")
+    try:
+        fn()
+        n = ctypes.c_size_t()
+        buf = (_LaunchInfo * 4096)()
+        self._ck(self.lib.tecdsa_ctx_profile_read(self._ctx, buf, 4096, ctypes.byref(n)), "ctx_profile_read")
+    finally:
+        self.lib.tecdsa_ctx_profile(self._ctx, 0)
+    out = {}
+    for i in range(min(n.value, 4096)):
+        e = out.setdefault(buf[i].kernel.decode(), {"ms": 0.0, "launches": 0, "mac32": 0})
+        e["ms"] += float(buf[i].ms); e["launches"] += 1; e["mac32"] += int(buf[i].mac32)
+    return out
+
+
+Engine.work, Engine.pack_records, Engine.gather_results, Engine.offline_records = _work, _pack_records, _gather_results, _offline_records
+Engine.nccl_unique_id, Engine.nccl_comm_create, Engine.nccl_comm_destroy, Engine.profile_step = _nccl_unique_id, _nccl_comm_create, _nccl_comm_destroy, _profile_step
 Engine.mod_mul, Engine.mod_inv, Engine.secp_mul = _mod_mul, _mod_inv, _secp_mul
 Engine.paillier_encrypt, Engine.paillier_mul, Engine.paillier_add, Engine.paillier_decrypt = _paillier_encrypt, _paillier_mul, _paillier_add, _paillier_decrypt

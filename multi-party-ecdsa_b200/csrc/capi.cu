@@ -63,10 +63,13 @@ extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
         int rc = tecdsa_internal_fb_points_init(device, c->stream, &fbp);
         if (rc == 0) rc = tecdsa_internal_fb_points_set_l12(fbp);
         if (rc == 0) rc = tecdsa_internal_fb_points_set_keygen(fbp);
+        if (rc == 0) rc = tecdsa_internal_fb_points_set_records(fbp);
         if (rc) { delete c; return rc; }
     }
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaMalloc(&c->d_work, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
     *out = c;
     return 0;
 }
@@ -81,11 +84,12 @@ extern "C" int tecdsa_ctx_destroy(tecdsa_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     // secrets may sit in every scratch buffer: wipe before release (the reference zeroizes its
     // proof round-1 secrets on drop, utilities/mta/range_proofs.rs:26-27)
-    char* bufs[3] = {c->ws, c->jobmem, c->arena};
-    size_t sizes[3] = {c->ws_bytes, c->jobmem_bytes, c->arena_bytes};
-    for (int i = 0; i < 3; i++) if (bufs[i]) cudaMemsetAsync(bufs[i], 0, sizes[i], c->stream);
+    char* bufs[4] = {c->ws, c->jobmem, c->arena, c->rec};
+    size_t sizes[4] = {c->ws_bytes, c->jobmem_bytes, c->arena_bytes, c->rec_bytes};
+    for (int i = 0; i < 4; i++) if (bufs[i]) cudaMemsetAsync(bufs[i], 0, sizes[i], c->stream);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 3; i++) if (bufs[i]) cudaFree(bufs[i]);
+    for (int i = 0; i < 4; i++) if (bufs[i]) cudaFree(bufs[i]);
+    if (c->d_work) cudaFree(c->d_work);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -117,15 +121,64 @@ extern "C" int tecdsa_ctx_last_kernel_ms(tecdsa_ctx* c, float* ms, int* launches
 }
 extern "C" uint64_t tecdsa_ctx_launch_count(tecdsa_ctx* c) { return c ? c->launches : 0; }
 
+// ------------------------------------------------------------------------------------ per-launch profiling
+void tecdsa_ctx::prof_begin(const char* name) {
+    if (!profiling || prof.size() >= prof_cap) return;
+    ProfEntry e{name, nullptr, nullptr};
+    if (cudaEventCreate(&e.e0) != cudaSuccess || cudaEventCreate(&e.e1) != cudaSuccess) return;
+    cudaEventRecord(e.e0, stream);
+    prof.push_back(e);
+}
+void tecdsa_ctx::prof_end() {
+    if (!profiling || prof.empty() || prof.size() > prof_cap) return;
+    cudaEventRecord(prof.back().e1, stream);
+    cudaMemcpyAsync(prof_work + prof.size() - 1, d_work, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+}
+extern "C" int tecdsa_ctx_profile(tecdsa_ctx* c, int enable) {
+    if (!c) return fail(TECDSA_E_ARG, "ctx_profile: null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& e : c->prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+    c->prof.clear();
+    if (enable && !c->prof_work) {
+        c->prof_cap = 4096;
+        CK(cudaMallocHost(&c->prof_work, c->prof_cap * sizeof(unsigned long long)));
+    }
+    if (enable) {
+        CK(cudaMemcpyAsync(&c->prof_work_base, c->d_work, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->profiling = enable != 0;
+    return 0;
+}
+extern "C" int tecdsa_ctx_profile_read(tecdsa_ctx* c, tecdsa_launch_info* out, size_t cap, size_t* n) {
+    if (!c || !n) return fail(TECDSA_E_ARG, "ctx_profile_read: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    *n = c->prof.size();
+    unsigned long long prev = 0;
+    for (size_t i = 0; i < c->prof.size() && out && i < cap; i++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->prof[i].e0, c->prof[i].e1));
+        memset(&out[i], 0, sizeof(out[i]));
+        strncpy(out[i].kernel, c->prof[i].name, sizeof(out[i].kernel) - 1);
+        out[i].ms = ms;
+        out[i].mac32 = i == 0 ? 0 : c->prof_work[i] - prev;
+        if (i == 0) out[i].mac32 = c->prof_work[0] - c->prof_work_base;
+        prev = c->prof_work[i];
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ modexp
 template <int K, int TPI>
 static cudaError_t launch_modexp(cudaStream_t s, const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
                                  const uint32_t* mod_idx, uint32_t* out, uint8_t* status, uint32_t* table,
-                                 int count, int exp_limbs) {
+                                 int count, int exp_limbs, unsigned long long* work) {
     constexpr int BLOCK = 128;
     constexpr int PER_BLOCK = BLOCK / TPI;
     int grid = (count + PER_BLOCK - 1) / PER_BLOCK;
-    modexp_kernel<K, TPI><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs);
+    modexp_kernel<K, TPI><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work);
     return cudaGetLastError();
 }
 
@@ -135,8 +188,8 @@ static int default_tpi(int mod_bits) { return mod_bits == 1024 ? 4 : mod_bits ==
 
 static cudaError_t dispatch_modexp(int mod_bits, int tpi, cudaStream_t s, const uint32_t* base, const uint32_t* exp,
                                    const uint32_t* mod, const uint32_t* mod_idx, uint32_t* out, uint8_t* status,
-                                   uint32_t* table, int count, int exp_limbs) {
-#define GO(K, T) return launch_modexp<K, T>(s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs)
+                                   uint32_t* table, int count, int exp_limbs, unsigned long long* work) {
+#define GO(K, T) return launch_modexp<K, T>(s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work)
     switch (mod_bits) {
     case 1024: switch (tpi) { case 4: GO(32, 4); case 8: GO(32, 8); case 16: GO(32, 16); default: return cudaErrorInvalidValue; }
     case 2048: switch (tpi) { case 4: GO(64, 4); case 8: GO(64, 8); case 16: GO(64, 16); case 32: GO(64, 32); default: return cudaErrorInvalidValue; }
@@ -202,7 +255,9 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
             ki = mod_idx ? mod_idx + off : nullptr; ko = out + off * K; ks = status ? status + off : nullptr;
         }
         if (first) { CK(cudaEventRecord(c->ev0, c->stream)); first = false; }
-        cudaError_t e = dispatch_modexp(mod_bits, tpi, c->stream, kb, ke, km, ki, ko, ks, d_table, (int)m, exp_limbs);
+        c->prof_begin("modexp_kernel");
+        cudaError_t e = dispatch_modexp(mod_bits, tpi, c->stream, kb, ke, km, ki, ko, ks, d_table, (int)m, exp_limbs, c->d_work);
+        c->prof_end();
         if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? TECDSA_E_UNSUPPORTED : TECDSA_E_CUDA, "modexp launch", e);
         launches++;
         CK(cudaEventRecord(c->ev1, c->stream));
@@ -325,9 +380,11 @@ int tecdsa_ctx::launch_exp(const ExpLaunch& l, int K) {
     char* d_desc; unsigned int* d_counter; uint32_t* d_tables;
     int rc = job_prepare(this, g.table_bytes, &l, sizeof(ExpLaunch), &d_desc, &d_counter, &d_tables);
     if (rc) return rc;
-    if (K == 32) exp_jobs_kernel<32, TPI_1024><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
-    else if (K == 64) exp_jobs_kernel<64, TPI_2048><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
-    else exp_jobs_kernel<128, TPI_4096><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
+    prof_begin(K == 32 ? "exp_jobs_kernel<32,4>" : K == 64 ? "exp_jobs_kernel<64,4>" : "exp_jobs_kernel<128,8>");
+    if (K == 32) exp_jobs_kernel<32, TPI_1024><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter, d_work);
+    else if (K == 64) exp_jobs_kernel<64, TPI_2048><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter, d_work);
+    else exp_jobs_kernel<128, TPI_4096><<<g.grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter, d_work);
+    prof_end();
     count_launch();
     CK(cudaGetLastError());
     return 0;
@@ -358,7 +415,9 @@ int launch_nadic_shape(tecdsa_ctx* c, const ExpLaunch& l) {
     char* d_desc; unsigned int* d_counter; uint32_t* d_tables;
     int rc = job_prepare(c, table_bytes, &l, sizeof(ExpLaunch), &d_desc, &d_counter, &d_tables);
     if (rc) return rc;
-    nadic_jobs_kernel<K, TPI, MINB><<<grid, JOB_BLOCK, 0, c->stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter);
+    c->prof_begin(K == 64 ? (TPI == 8 ? "nadic_jobs_kernel<64,8>" : "nadic_jobs_kernel<64,4>") : (TPI == 4 ? "nadic_jobs_kernel<32,4>" : "nadic_jobs_kernel<32,2>"));
+    nadic_jobs_kernel<K, TPI, MINB><<<grid, JOB_BLOCK, 0, c->stream>>>(reinterpret_cast<const ExpLaunch*>(d_desc), d_tables, d_counter, c->d_work);
+    c->prof_end();
     c->count_launch();
     CK(cudaGetLastError());
     return 0;
@@ -394,7 +453,9 @@ int tecdsa_ctx::launch_nadic_inv(const InvLaunch& l) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nadic_inv_kernel<64, TPI_NADIC_INV>, JOB_BLOCK, 0);
     if (per_sm < 1) per_sm = 1;
+    prof_begin("nadic_inv_kernel<64,8>");
     nadic_inv_kernel<64, TPI_NADIC_INV><<<sm_count * per_sm, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const InvLaunch*>(d_desc), d_counter);
+    prof_end();
     count_launch();
     CK(cudaGetLastError());
     return 0;
@@ -417,8 +478,10 @@ int tecdsa_ctx::launch_inv(const InvLaunch& l, int K) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inv_jobs_kernel<128, TPI_4096>, JOB_BLOCK, 0);
     if (per_sm < 1) per_sm = 1;
     const int grid = sm_count * per_sm;
+    prof_begin(K == 64 ? "inv_jobs_kernel<64,4>" : "inv_jobs_kernel<128,8>");
     if (K == 64) inv_jobs_kernel<64, TPI_2048><<<grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const InvLaunch*>(d_desc), d_counter);
     else inv_jobs_kernel<128, TPI_4096><<<grid, JOB_BLOCK, 0, stream>>>(reinterpret_cast<const InvLaunch*>(d_desc), d_counter);
+    prof_end();
     count_launch();
     CK(cudaGetLastError());
     return 0;

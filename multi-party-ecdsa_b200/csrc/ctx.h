@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 namespace tecdsa {
 struct ExpLaunch;
@@ -30,6 +31,11 @@ int tecdsa_fail(int code, const char* what, cudaError_t e = cudaSuccess);
 int tecdsa_internal_fb_points_init(int device, cudaStream_t stream, const uint32_t** table_out);   // gg20.cu
 int tecdsa_internal_fb_points_set_l12(const uint32_t* table);                                        // l12.cu
 int tecdsa_internal_fb_points_set_keygen(const uint32_t* table);                                     // keygen.cu
+int tecdsa_internal_fb_points_set_records(const uint32_t* table);                                    // records.cu
+
+// the offline stage with a HOST copy of the session descriptors; rnd / outputs live where `mem` says (gg20.cu)
+int tecdsa_internal_offline(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* h_sessions, size_t n_sessions, const uint32_t* rnd,
+                            uint8_t* status, uint32_t* R_out, uint32_t* sigma_out, uint32_t* tvec_out, uint32_t* digest_out, int mem);
 
 #define CK(call)                                                               \
     do {                                                                       \
@@ -57,6 +63,9 @@ struct tecdsa_ctx {
     char* jobmem = nullptr;        // job-list launches: descriptor ring, counters, window tables
     size_t jobmem_bytes = 0;
     int job_slot = 0;
+    char* rec = nullptr;           // staging of tecdsa_gg20_offline_records (inputs, per-unit outputs, packed records)
+    size_t rec_bytes = 0;
+    unsigned long long* d_work = nullptr;   // executed-work counter of the job kernels (MAC32), see tecdsa_ctx_work
     char* arena = nullptr;         // per-unit state of the last gg20 batch
     size_t arena_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -71,6 +80,17 @@ struct tecdsa_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     bool owns_stream = false;
     uint32_t last_off[tecdsa::F_COUNT] = {};
+
+    // per-launch profiling (tecdsa_ctx_profile): CUDA events around every kernel launch of this context + a snapshot of the
+    // executed-work counter after it; batches run unsplit (one stream) while it is on
+    struct ProfEntry { const char* name; cudaEvent_t e0, e1; };
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    unsigned long long* prof_work = nullptr;      // pinned host: d_work after launch i
+    size_t prof_cap = 0;
+    unsigned long long prof_work_base = 0;
+    void prof_begin(const char* name);
+    void prof_end();
 
     void count_launch() { launches++; }
     int reserve_arena(size_t bytes);

@@ -108,14 +108,18 @@ constexpr int GPW32 = 32 / TPI_1024, GPW64 = 32 / TPI_2048, GPWI128 = 32 / TPI_4
 
 template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A, int per_unit = 1) {
     int grid = (A.U * per_unit + 63) / 64;
+    c->prof_begin("gg20 glue (EC, hashing, checks)");
     kern<<<grid, 64, 0, c->stream>>>(A);
+    c->prof_end();
     c->count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "glue launch", e);
 }
 
 int glue_crt(tecdsa_ctx* c, const Arena& A, int first, int count) {
+    c->prof_begin("gg20_crt (CRT recombination)");
     gg20_crt<<<(A.U + 63) / 64, 64, 0, c->stream>>>(A, first, count);
+    c->prof_end();
     c->count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : tecdsa_fail(TECDSA_E_CUDA, "crt launch", e);
@@ -233,16 +237,14 @@ static int run_inv(tecdsa_ctx* c, InvLaunch& l, int K) {
 }
 
 // ------------------------------------------------------------------------------------------ offline stage
-static int offline_impl(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
+// `h_sess` is always a HOST copy of the session descriptors; `mem` says where rnd and the outputs live
+static int offline_impl(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* h_sess, size_t n_sessions,
                         const uint32_t* rnd, uint8_t* status, uint32_t* R_out, uint32_t* sigma_out,
                         uint32_t* tvec_out, uint32_t* digest_out, int mem) {
     CK(cudaSetDevice(c->device));
     const int U = (int)n_sessions * 2;
 
     // ---- host-side unit tables (who am I, who is my peer, which key rows)
-    std::vector<uint32_t> h_sess(n_sessions * 3);
-    if (mem == TECDSA_HOST) memcpy(h_sess.data(), sessions, h_sess.size() * 4);
-    else { CK(cudaMemcpyAsync(h_sess.data(), sessions, h_sess.size() * 4, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
     std::vector<uint32_t> idx((size_t)7 * U);
     uint32_t *row_own = idx.data(), *row_peer = row_own + U, *row_st = row_peer + U, *peer = row_st + 3 * (size_t)U, *kset = peer + U;
     for (size_t s = 0; s < n_sessions; s++) {
@@ -444,9 +446,22 @@ extern "C" int tecdsa_gg20_offline_batch(tecdsa_ctx* c, const tecdsa_keyset* ks,
     if (mem != TECDSA_HOST && mem != TECDSA_DEVICE) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: bad mem");
     if (n_sessions == 0) return 0;
     if (n_sessions > (1u << 22)) return tecdsa_fail(TECDSA_E_ARG, "gg20_offline: too many sessions");
-    if (n_sessions < split_min_sessions()) return offline_impl(c, ks, sessions, n_sessions, rnd, status, R_out, sigma_out, tvec_out, digest_out, mem);
-
     CK(cudaSetDevice(c->device));
+    std::vector<uint32_t> h_copy;
+    if (mem == TECDSA_DEVICE) {                     // the host builds the per-unit index tables from the descriptors
+        h_copy.resize(n_sessions * 3);
+        CK(cudaMemcpyAsync(h_copy.data(), sessions, h_copy.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        sessions = h_copy.data();
+    }
+    return tecdsa_internal_offline(c, ks, sessions, n_sessions, rnd, status, R_out, sigma_out, tvec_out, digest_out, mem);
+}
+
+int tecdsa_internal_offline(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* sessions, size_t n_sessions,
+                            const uint32_t* rnd, uint8_t* status, uint32_t* R_out, uint32_t* sigma_out,
+                            uint32_t* tvec_out, uint32_t* digest_out, int mem) {
+    if (n_sessions < split_min_sessions() || c->profiling) return offline_impl(c, ks, sessions, n_sessions, rnd, status, R_out, sigma_out, tvec_out, digest_out, mem);
+
     for (int h = 0; h < 2; h++) {
         if (c->child[h]) continue;
         cudaStream_t s = nullptr;

@@ -86,7 +86,8 @@ struct ExpLaunch {
 
 template <int K, int TPI>
 __global__ void __launch_bounds__(128)          // (128, 4) caps at 128 registers with spills: measured 2 % slower
-exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tables, unsigned int* __restrict__ counter) {
+exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tables, unsigned int* __restrict__ counter,
+                unsigned long long* __restrict__ work) {
     constexpr int L = K / TPI;
     constexpr int GPW = 32 / TPI;                 // groups per warp
     constexpr int TBL = 1 << WINDOW_BITS;
@@ -221,6 +222,21 @@ exp_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tab
             }
         }
         if (live) store_limbs<TPI, L>(c.out + (size_t)g * c.out_stride, acc);
+        if (live && gl == 0 && work) {
+            unsigned long long products = setup_products(K) + (c.nmul == 0 ? 1 : 1 + 2 * (c.nmul - 1));
+            if (c.fb) {
+                for (int b = 0; b < c.nbases; b++) products += (c.exp_limbs[b] * 32 + FB_WINDOW_BITS - 1) / FB_WINDOW_BITS;
+            } else if (c.nbases > 0) {
+                int nwmax = 0;
+                for (int b = 0; b < c.nbases; b++) {
+                    const int nwb = (c.exp_limbs[b] * 32 + WINDOW_BITS - 1) / WINDOW_BITS;
+                    products += 1 + (TBL - 2) + nwb + ((b == 0 && c.wide0) ? 3 : 0);
+                    nwmax = nwb > nwmax ? nwb : nwmax;
+                }
+                products += (unsigned long long)(nwmax - 1) * WINDOW_BITS;
+            }
+            atomicAdd(work, products * mac_mont(K));
+        }
         __syncwarp();
     }
 }

@@ -12,6 +12,11 @@ namespace tecdsa {
 
 static constexpr int WINDOW_BITS = 5;
 
+// Executed-work accounting (tecdsa_ctx_work): every job adds the 32x32+64 multiply-accumulates of the products it ran to a
+// device counter — one atomicAdd per job, counted from the loop trip counts of the kernel itself.
+__host__ __device__ constexpr unsigned long long mac_mont(int K) { return 2ull * K * K + K; }            // one Montgomery product (rows + quotient digits)
+__host__ __device__ constexpr int setup_products(int K) { int t = 0; for (unsigned v = 32u * K; v > 1; v >>= 1) t++; return t; }   // squarings of mont_setup
+
 // Everything a group needs to exponentiate modulo one modulus.
 template <int L> struct MontCtx {
     uint32_t n[L];
@@ -109,7 +114,7 @@ template <int K, int TPI>
 __global__ void __launch_bounds__(128)
 modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ exp, const uint32_t* __restrict__ mod,
               const uint32_t* __restrict__ mod_idx, uint32_t* __restrict__ out, uint8_t* __restrict__ status,
-              uint32_t* __restrict__ table, int count, int exp_limbs) {
+              uint32_t* __restrict__ table, int count, int exp_limbs, unsigned long long* __restrict__ work) {
     constexpr int L = K / TPI;
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
     const bool live = slot < count;
@@ -137,6 +142,11 @@ modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ex
     if (live && (n_low & 1u)) {
         store_limbs<TPI, L>(out + (size_t)idx * K, acc);
         if (group_lane<TPI>() == 0 && status) status[idx] = 0;
+        if (group_lane<TPI>() == 0 && work) {
+            const int nw = (exp_limbs * 32 + WINDOW_BITS - 1) / WINDOW_BITS;
+            const unsigned long long products = setup_products(K) + 1 + ((1 << WINDOW_BITS) - 2) + (unsigned long long)(nw - 1) * (WINDOW_BITS + 1) + 1;
+            atomicAdd(work, products * mac_mont(K));
+        }
     }
 }
 

@@ -220,7 +220,8 @@ __device__ __forceinline__ void to_nadic(Dig<L>& X, const Operand& o, int i, con
 // `mod` names N (K limbs) and `nadic` the per-key constants row.  K is the width of N.
 template <int K, int TPI, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tables, unsigned int* __restrict__ counter) {
+nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ tables, unsigned int* __restrict__ counter,
+                  unsigned long long* __restrict__ work) {
     constexpr int L = K / TPI;
     constexpr int GPW = 32 / TPI;
     constexpr int TBL = 1 << WINDOW_BITS;
@@ -328,6 +329,25 @@ nadic_jobs_kernel(const ExpLaunch* __restrict__ launch, uint32_t* __restrict__ t
             uint32_t* o = c.out + (size_t)g * c.out_stride;
             store_limbs<TPI, L>(o, lo);
             store_limbs<TPI, L>(o + K, hi);
+            if (gl == 0 && work) {
+                // nadic_mul: 4K^2 + 2K without the second cross product (lifts, squarings), 5K^2 + 2K with it
+                const unsigned long long m4 = 4ull * K * K + 2 * K, m5 = 5ull * K * K + 2 * K;
+                unsigned long long macs = (unsigned long long)K * K + m5;                                    // exit: times (1, 0), then d0 + d1 * N
+                int nwmax = 0;
+                for (int k = 0; k < c.nbases + c.nmul; k++) {
+                    const Operand& o2 = k < c.nbases ? c.base[k] : c.mul[k - c.nbases];
+                    int parts = ((int)o2.limbs + K - 1) / K;
+                    macs += (unsigned long long)(parts > 4 ? 4 : parts) * m4;
+                    if (k < c.nbases) {
+                        const int nwb = (c.exp_limbs[k] * 32 + WINDOW_BITS - 1) / WINDOW_BITS;
+                        macs += (unsigned long long)(TBL - 2 + nwb) * m5;
+                        nwmax = nwb > nwmax ? nwb : nwmax;
+                    } else macs += m5;
+                }
+                if (c.nmul > 0) macs += m5;
+                if (nwmax > 0) macs += (unsigned long long)(nwmax - 1) * WINDOW_BITS * m4;
+                atomicAdd(work, macs);
+            }
         }
         __syncwarp();
     }

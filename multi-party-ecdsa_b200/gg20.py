@@ -121,6 +121,31 @@ def offline_batch(eng: Engine, keys: KeySets, sessions: Sequence[Sequence[int]],
     return OfflineResult(status, R, sigma, tvec, digest)
 
 
+def offline_raw(eng: Engine, keys: KeySets, sessions, n_sessions: int, rnd, status, R, sigma, t_vec, digest, mem: int = HOST):
+    """tecdsa_gg20_offline_batch on caller buffers (numpy for HOST, torch CUDA tensors for DEVICE)"""
+    _bind(eng.lib)
+    eng._ck(eng.lib.tecdsa_gg20_offline_batch(eng._ctx, keys.handle, _ptr(sessions), n_sessions, _ptr(rnd), _ptr(status), _ptr(R), _ptr(sigma),
+                                              _ptr(t_vec), _ptr(digest), mem), "gg20_offline_batch")
+
+
+def sign_batch(eng: Engine, keys: KeySets, sessions: np.ndarray, message: np.ndarray, R: np.ndarray, sigma: np.ndarray, k: np.ndarray):
+    """The online step for a batch of completed sessions (`phase7_local_sig`, `output_signature`, `verify`; party_i.rs:850-936):
+    message [n][8], R [2n][16], sigma [2n][8], k [2n][8] (uint32 limbs) -> dict(s_i [2n][8], r [n][8], s [n][8], recid [n], status [n])"""
+    _bind(eng.lib)
+    lib = eng.lib
+    if not getattr(lib, "_sign_bound", False):
+        lib.tecdsa_gg20_sign_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 9 + [ctypes.c_int]
+        lib._sign_bound = True
+    sessions = np.ascontiguousarray(sessions, dtype=np.uint32).reshape(-1, 3)
+    n = sessions.shape[0]
+    ins = [np.ascontiguousarray(x, dtype=np.uint32) for x in (message, R, sigma, k)]
+    s_i, r, s = np.zeros((2 * n, 8), np.uint32), np.zeros((n, 8), np.uint32), np.zeros((n, 8), np.uint32)
+    recid, status = np.zeros(n, np.uint8), np.full(n, 255, np.uint8)
+    eng._ck(lib.tecdsa_gg20_sign_batch(eng._ctx, keys.handle, _ptr(sessions), n, *[_ptr(x) for x in ins], _ptr(s_i), _ptr(r), _ptr(s), _ptr(recid), _ptr(status), HOST),
+            "gg20_sign_batch")
+    return {"s_i": s_i, "r": r, "s": s, "recid": recid, "status": status}
+
+
 def debug_field(eng: Engine, name: str, units: int) -> np.ndarray:
     _bind(eng.lib)
     n = ctypes.c_size_t()

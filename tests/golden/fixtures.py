@@ -23,3 +23,12 @@ def load_keyset(index: int = 0):
                        dk=o.DecryptionKey(int(p["p"], 16), int(p["q"], 16)), pk_vec=pks, paillier_key_vec=eks,
                        h1_h2_n_tilde_vec=stmts, y_sum_s=y) for p in parties]
     return keys
+
+
+def n_keysets() -> int:
+    with open(os.path.join(HERE, "keys_t1n3.json")) as f:
+        return len(json.load(f)["keysets"])
+
+
+def load_all_keysets():
+    return [load_keyset(i) for i in range(n_keysets())]

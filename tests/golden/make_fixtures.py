@@ -51,8 +51,16 @@ def make_keyset(seed: int, n_parties: int = 3):
     return {"t": 1, "n": n_parties, "secret": hex(a0), "parties": parties}
 
 
+N_KEYSETS = 8          # "8 synthetic (t=1,n=3) key sets"
+
+
 if __name__ == "__main__":
-    sets = [make_keyset(0xB2000005 + s) for s in range(2)]
-    with open(os.path.join(HERE, "keys_t1n3.json"), "w") as f:
+    # the primes come from OpenSSL's RNG, so a regeneration would change every key: key sets already in the file are KEPT
+    # (the golden vectors of tests/golden/vectors_r01.json were produced with key sets 0 and 1) and only missing ones are added
+    path = os.path.join(HERE, "keys_t1n3.json")
+    sets = json.load(open(path))["keysets"] if os.path.exists(path) else []
+    for s in range(len(sets), N_KEYSETS):
+        sets.append(make_keyset(0xB2000005 + s))
+    with open(path, "w") as f:
         json.dump({"about": "synthetic GG20 t=1,n=3 key sets; see make_fixtures.py", "keysets": sets}, f, indent=1)
     print("wrote", len(sets), "key sets")

@@ -154,3 +154,89 @@ def test_offline_split_batch_equals_plain_batches(engine, pkg):
     assert big.status[6] != 0 or big.status[7] != 0
     assert not big.status[8:].any() and not big.status[:6].any()
     ks.free()
+
+
+def _be(limbs):
+    """[n][8] little-endian limbs -> [n][32] big-endian bytes"""
+    return np.ascontiguousarray(limbs[:, ::-1]).astype(">u4").view(np.uint8).reshape(limbs.shape[0], 32)
+
+
+def test_records_e2e_call_and_online_step(engine, pkg):
+    """tecdsa_gg20_offline_records (host buffers in, 256-byte records out) == the C twin of the oracle on every field of the
+    record, for 8 key sets; then the device online step (phase7_local_sig / output_signature / verify, party_i.rs:850-936)
+    against the oracle and OpenSSL; the kernels' own work counter and the per-launch profile are live."""
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec, utils
+    from mpecdsa_b200 import gg20
+    from oracle import twin
+    from tests.golden import fixtures
+    keysets = fixtures.load_all_keysets()
+    assert len(keysets) == 8
+    ks = gg20.KeySets(engine, keysets)
+    n = 48
+    sessions, rnd = gg20.synthetic_batch(keysets, n, 0xB2000005)
+    assert len(set(sessions[:, 0].tolist())) == 8
+    engine.work(reset=True)
+    rec = np.zeros((1, 2 * n, pkg.REC_BYTES), dtype=np.uint8)
+    engine.offline_records(ks, None, sessions, n, rnd, rec, pkg.HOST)
+    macs = engine.work()
+    assert 0.3e9 < macs / (2 * n) < 1.0e9                    # executed multiply-accumulates per unit, counted by the kernels
+    rec = rec[0]
+    want = twin.offline_batch(twin.KeyTables(keysets), sessions, rnd, 8)
+    assert not want.status.any() and not rec[:, 0].any()
+    assert np.array_equal(rec[:, 164:196], _be(want.digest))
+    assert np.array_equal(rec[:, 34:66], _be(want.sigma)) and np.array_equal(rec[:, 66:98], _be(want.k))
+    assert np.array_equal(rec[:, 2:34], _be(want.R[:, :8])) and np.array_equal(rec[:, 1], 2 + (want.R[:, 8] & 1).astype(np.uint8))
+    assert np.array_equal(rec[:, 99:131], _be(want.t_vec[:, :8])) and np.array_equal(rec[:, 132:164], _be(want.t_vec[:, 16:24]))
+    assert np.array_equal(rec[:, 98], 2 + (want.t_vec[:, 8] & 1).astype(np.uint8)) and not rec[:, 196:].any()
+    # the plain batch call gives the same per-unit outputs
+    res = gg20.offline_batch(engine, ks, sessions, rnd)
+    assert np.array_equal(res.R, want.R) and np.array_equal(res.sigma, want.sigma) and np.array_equal(res.digest, want.digest)
+    # online step
+    m = o.sha256_bigints([o.bn_from_bytes(b"ZenGo")])
+    msg = np.tile(np.frombuffer(m.to_bytes(32, "little"), dtype="<u4"), (n, 1))
+    sig = gg20.sign_batch(engine, ks, sessions, msg, res.R, res.sigma, want.k)
+    assert not sig["status"].any()
+    for s in range(n):
+        R = gg20.unpack_point(pkg.limbs_to_ints(res.R[2 * s:2 * s + 1])[0])
+        parts = [o.local_sig(pkg.limbs_to_ints(want.k[2 * s + p:2 * s + p + 1])[0], m, R, pkg.limbs_to_ints(res.sigma[2 * s + p:2 * s + p + 1])[0]) for p in range(2)]
+        assert pkg.limbs_to_ints(sig["s_i"][2 * s:2 * s + 2]) == parts
+        r_, s_, recid = o.output_signature(R, parts)
+        assert (pkg.limbs_to_ints(sig["r"][s:s + 1])[0], pkg.limbs_to_ints(sig["s"][s:s + 1])[0], int(sig["recid"][s])) == (r_, s_, recid)
+        y = keysets[int(sessions[s, 0])][0].y_sum_s
+        pub = ec.EllipticCurvePublicNumbers(y[0], y[1], ec.SECP256K1()).public_key()
+        pub.verify(utils.encode_dss_signature(r_, s_), m.to_bytes(32, "big"), ec.ECDSA(utils.Prehashed(hashes.SHA256())))
+    # a wrong sigma_i makes the in-tree verify fail for that session only (Error::InvalidSig)
+    bad = res.sigma.copy(); bad[5, 0] ^= 1
+    sig2 = gg20.sign_batch(engine, ks, sessions, msg, res.R, bad, want.k)
+    assert sig2["status"][2] == pkg.ST_INVALID_SIG and not np.delete(sig2["status"], 2).any()
+    # per-launch profile: every job-list kernel shows up with its counted work
+    prof = engine.profile_step(lambda: engine.offline_records(ks, None, sessions, n, rnd, np.zeros((1, 2 * n, 256), np.uint8), pkg.HOST))
+    assert any(k.startswith("nadic_jobs_kernel<64") for k in prof) and any(k.startswith("exp_jobs_kernel<64") for k in prof)
+    assert abs(sum(v["mac32"] for v in prof.values()) - macs) <= 1e-6 * macs
+    assert all(v["ms"] > 0 for v in prof.values())
+    ks.free()
+
+
+def test_config4_share_digest_sample_vs_cpu_twin(engine, pkg):
+    """BASELINE.json configs[4], the per-GPU share at full size: 8 192 sessions = 16 384 units over 8 key sets; every unit
+    completes, 2^8 sampled units are bit-compared with the oracle's C twin."""
+    from mpecdsa_b200 import gg20
+    from oracle import twin
+    from tests.golden import fixtures
+    keysets = fixtures.load_all_keysets()
+    ks = gg20.KeySets(engine, keysets)
+    n = 8192
+    sessions, rnd = gg20.synthetic_batch(keysets, n, 0xB2000005)
+    rec = np.zeros((1, 2 * n, pkg.REC_BYTES), dtype=np.uint8)
+    engine.offline_records(ks, None, sessions, n, rnd, rec, pkg.HOST)
+    rec = rec[0]
+    assert not rec[:, 0].any()
+    pick = np.unique(np.linspace(0, n - 1, 128).astype(np.int64))
+    units = np.stack([2 * pick, 2 * pick + 1], axis=1).reshape(-1)
+    want = twin.offline_batch(twin.KeyTables(keysets), sessions[pick], rnd[units], 32)
+    got = rec[units]
+    assert not want.status.any()
+    assert np.array_equal(got[:, 164:196], _be(want.digest)) and np.array_equal(got[:, 34:66], _be(want.sigma))
+    assert np.array_equal(got[:, 2:34], _be(want.R[:, :8]))
+    ks.free()

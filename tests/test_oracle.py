@@ -239,3 +239,50 @@ def test_tensor_core_montgomery_study_is_exact():
     R = 1 << bits
     assert got == [x * y * pow(R, -1, n) % n for x, y in zip(a, b)]
     assert peak < 1 << 24
+
+
+def test_c_twin_equals_python_restatement(keyset):
+    """oracle/gg20_twin.c (GMP + OpenSSL, the reference's scalar call sequence) and oracle/gg20_oracle.py agree on every output
+    of an offline session: two independent implementations of the restatement, one in C over the reference's own bignum
+    backend, pin each other."""
+    import numpy as np
+    from oracle import twin
+    from oracle.sampling import Drbg, sample_unit
+    from tests.golden import fixtures
+    keysets = [keyset, fixtures.load_keyset(5)]
+    drbg = Drbg(0xB2C7, "twin")
+    sess, rnds, want = [], [], []
+    for ks_i, a, b in ((0, 0, 2), (1, 1, 0)):
+        keys, s_l = [keysets[ks_i][a], keysets[ks_i][b]], [a + 1, b + 1]
+        r = [sample_unit(drbg, keys, s_l, p) for p in range(2)]
+        sess.append((ks_i, a, b)); rnds += r; want += o.offline_session(keys, s_l, r)
+    # the packing of the randomness record (include/tecdsa_b200.h TECDSA_RND_*), restated here so that the CPU suite does not
+    # depend on the product package
+    rnd = np.zeros((len(rnds), 1408), dtype=np.uint32)
+
+    def put(row, off, limbs, val):
+        rnd[row, off:off + limbs] = np.frombuffer(int(val).to_bytes(4 * limbs, "little"), dtype="<u4")
+
+    for u, r in enumerate(rnds):
+        for name, (off, limbs) in {"gamma_i": (0, 8), "k_i": (8, 8), "blind": (16, 8), "r_k": (24, 64), "beta_tag_gamma": (832, 64), "r_gamma": (896, 64),
+                                   "nonce_gamma_b": (960, 8), "nonce_gamma_beta": (968, 8), "beta_tag_w": (976, 64), "r_w": (1040, 64), "nonce_w_b": (1104, 8),
+                                   "nonce_w_beta": (1112, 8), "l": (1120, 8), "ped_s1": (1128, 8), "ped_s2": (1136, 8), "heg_s1": (1392, 8), "heg_s2": (1400, 8)}.items():
+            put(u, off, limbs, getattr(r, name))
+        for x in range(3):
+            for (o_, l_), v in zip(((0, 24), (24, 64), (88, 88), (176, 72)), r.alice[x]):
+                put(u, 88 + x * 248 + o_, l_, v)
+        for (o_, l_), v in zip(((1144, 24), (1168, 64), (1232, 72), (1304, 88)), r.pdl):
+            put(u, o_, l_, v)
+    res = twin.offline_batch(twin.KeyTables(keysets), np.array(sess, dtype=np.uint32), rnd, 2)
+    I = lambda row: int.from_bytes(row.tobytes(), "little")
+    for u, w in enumerate(want):
+        assert res.status[u] == w.status == 0
+        assert I(res.digest[u]).to_bytes(32, "big") == w.transcript
+        assert (I(res.R[u, :8]), I(res.R[u, 8:])) == w.R and I(res.sigma[u]) == w.sigma_i and I(res.k[u]) == w.k_i
+        assert [(I(res.t_vec[u, :8]), I(res.t_vec[u, 8:16])), (I(res.t_vec[u, 16:24]), I(res.t_vec[u, 24:]))] == w.t_vec
+    # a corrupted range-proof nonce: both implementations reject at the same place
+    bad = rnd.copy(); bad[0, 88 + 248:88 + 248 + 24] = 0xFFFFFFFF
+    r0 = list(rnds[:2]); import copy; r0[0] = copy.deepcopy(r0[0]); a = r0[0].alice[1]; r0[0].alice[1] = ((1 << 768) - 1, a[1], a[2], a[3])
+    w = o.offline_session([keysets[0][0], keysets[0][2]], [1, 3], r0)
+    res = twin.offline_batch(twin.KeyTables(keysets), np.array(sess[:1], dtype=np.uint32), bad[:2], 1)
+    assert [int(x) for x in res.status] == [x.status for x in w] == [0, 2]
