@@ -62,10 +62,28 @@ def config_dict(world: int) -> dict:
 
 
 def host_threads() -> int:
+    """Threads this process may actually run at once: the affinity mask capped by the cgroup CPU quota (a box whose container
+    is limited to a few CPUs' worth of time gains nothing from one thread per visible core)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
 
 
 def cpu_model() -> str:
@@ -130,6 +148,8 @@ def load_keysets():
 
 def make_batch(keysets, n_sessions: int, rank: int):
     """Sessions and randomness records of this rank's block (oracle-free: mpecdsa_b200.gg20.synthetic_batch)."""
+    import __graft_entry__ as entry
+    entry.load_package()                      # registers the package; the input generator needs neither the library nor a GPU
     from mpecdsa_b200 import gg20
     return gg20.synthetic_batch(keysets, n_sessions, SEED + 0x1000 * rank)
 
@@ -155,6 +175,14 @@ def cpu_phases(keysets, n_sessions: int, threads: int, seed_rank: int = 1000):
     return 2 * n_sessions / dt, dt
 
 
+def cpu_sample_sessions(keysets, threads: int, target_s: float):
+    """How many sessions keep `threads` host threads busy for about target_s: sized from a short probe, because the CPU time a
+    GPU box gives its container varies from box to box (round 1 saw 5x between two boxes of the same CPU model)."""
+    v1, _ = cpu_phases(keysets, 1, 1, seed_rank=900)
+    vt, _ = cpu_phases(keysets, max(threads // 2, 2), threads, seed_rank=901)
+    return max(int(vt * target_s / 2), 16), v1, vt
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path (scalar BigInt calls over GMP, secp256k1 on the CPU) on all
     host threads through a persistent thread pool; each step is a bounded sample of the workload."""
@@ -163,9 +191,7 @@ def run_reference(args):
     from oracle import twin
     threads = host_threads()
     keysets = load_keysets()
-    per_step = max(threads * 4, 16)                     # sessions per step: 8 units per thread (~2.7 s of GMP work per thread)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_phases(keysets, max(threads, 8), threads)
+    per_step, _, _ = cpu_sample_sessions(keysets, threads, 3.0)      # sessions per step: about 3 s of wall time on this box (also the warm-up)
     t, units = 0.0, 0
     for i in range(args.steps):
         v, dt = cpu_phases(keysets, per_step, threads, seed_rank=2000 + i)
@@ -417,9 +443,8 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import twin
-        n_cpu = max(threads * 16, 64)                 # 32 phases per thread, ~10 s of GMP work each
+        n_cpu, v1, _ = cpu_sample_sessions(keysets, threads, 12.0)      # about 12 s of wall time on this box
         v, dt = cpu_phases(keysets, n_cpu, threads)
-        v1, dt1 = cpu_phases(keysets, 2, 1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{2 * n_cpu} phases ({n_cpu} sessions) of the same workload in {dt:.1f} s on a persistent pool of {threads} threads (oracle/gg20_twin.c: the "
                          f"reference's scalar call sequence, GMP {twin.lib().oracle_gmp_version().decode()} + OpenSSL, {cpu_model()}); single thread: {v1:.2f} phases/s"}

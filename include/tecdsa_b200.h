@@ -5,7 +5,7 @@
  * `Paillier::*` and the in-tree proof structs.  Every entry point below is the BATCHED form
  * of one of those scalar calls and cites the reference call site it replaces (paths are
  * relative to /root/reference).  INTEGRATION.md shows the Rust `extern "C"` shim a maintainer
- * would add so that src/protocols/* links against this library.
+ * would add so that the protocol modules under src/protocols link against this library.
  *
  * Conventions
  *   - Big integers are little-endian arrays of uint32_t limbs, operand-major:
@@ -95,6 +95,36 @@ int tecdsa_modinv_batch(tecdsa_ctx* ctx, int mod_bits, const uint32_t* a, const 
  * means the generator (`Point::generator() * s`).  Points are affine x||y (16 limbs, all-zero = identity); scalars
  * are reduced mod q; a point that is not on the curve yields the identity.                                          */
 int tecdsa_secp_mul_batch(tecdsa_ctx* ctx, const uint32_t* points, const uint32_t* scalars, uint32_t* out, size_t count, int mem);
+
+/* ---- L0: the rest of the Scalar<Secp256k1> / Point<Secp256k1> / BigInt surface src/ calls between the heavy steps ----------
+ * Points are affine x||y (16 limbs, all-zero = identity), scalars 8 limbs reduced mod q on entry.
+ * secp_add / secp_sub: `Point + Point`, `Point - Point` (gg_2020/party_i.rs:771-772,839-840).
+ * secp_compress: `Point::to_bytes(true)` -> 33 bytes per point (party_i.rs:577-580; zk_pdl_with_slack/mod.rs:102-110); the
+ *   identity gives 33 zero bytes.  secp_decompress: `Point::from_bytes` of such an encoding; ok = 0 (and the identity) for a
+ *   malformed one (bad prefix, x >= p, x^3 + 7 a non-residue).
+ * secp_scalar_{mul,add,sub,inv}: `Scalar * + - invert()` (party_i.rs:599-617,635-640,857-863); inv: ok = 0 for zero.
+ * secp_scalar_from_bigint: `Scalar::from(&BigInt)` — a `limbs`-limb integer reduced mod q (mta/mod.rs:132,166).
+ * wide_muladd: a*b + c over the integers, no modulus (`e * a + alpha`, `e * rho + gamma`; mta/range_proofs.rs:87-88):
+ *   out_limbs >= a_limbs + b_limbs and > c_limbs.
+ * unit_mod_check: the acceptance test of `SampleFromMultiplicativeGroup::from_modulo / from_paillier_key`
+ *   (mta/range_proofs.rs:538-557): ok = 1 iff r < N and gcd(r, N) = 1 (odd N; mod_bits 2048 or 4096) — the caller's sampling
+ *   loop draws again where ok = 0, exactly as the reference's `while r.gcd(N) != 1`.
+ * sha256: SHA-256 of arbitrary byte strings, message i = bytes[offsets[i], offsets[i+1]) -> digests [count][32]
+ *   (TECDSA_HOST only: the offsets are read on the host).                                                                */
+int tecdsa_secp_add_batch(tecdsa_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, int mem);
+int tecdsa_secp_sub_batch(tecdsa_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, int mem);
+int tecdsa_secp_compress_batch(tecdsa_ctx* ctx, const uint32_t* points, uint8_t* out33, size_t count, int mem);
+int tecdsa_secp_decompress_batch(tecdsa_ctx* ctx, const uint8_t* in33, uint32_t* points, uint8_t* ok, size_t count, int mem);
+int tecdsa_secp_scalar_mul_batch(tecdsa_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, int mem);
+int tecdsa_secp_scalar_add_batch(tecdsa_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, int mem);
+int tecdsa_secp_scalar_sub_batch(tecdsa_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t count, int mem);
+int tecdsa_secp_scalar_inv_batch(tecdsa_ctx* ctx, const uint32_t* a, uint32_t* out, uint8_t* ok, size_t count, int mem);
+int tecdsa_secp_scalar_from_bigint_batch(tecdsa_ctx* ctx, const uint32_t* x, int limbs, uint32_t* out, size_t count, int mem);
+int tecdsa_wide_muladd_batch(tecdsa_ctx* ctx, const uint32_t* a, int a_limbs, const uint32_t* b, int b_limbs, const uint32_t* c, int c_limbs,
+                             uint32_t* out, int out_limbs, size_t count, int mem);
+int tecdsa_unit_mod_check_batch(tecdsa_ctx* ctx, int mod_bits, const uint32_t* r, const uint32_t* modulus, const uint32_t* mod_idx, size_t n_mod,
+                                uint8_t* ok, size_t count, int mem);
+int tecdsa_sha256_batch(tecdsa_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, uint8_t* digests, size_t count, int mem);
 
 /* ---- L1: Paillier (kzen-paillier 0.4.2 as called from src/utilities/mta/mod.rs:68,133,140,145,165) ----------------
  * n = [n_keys][64] public moduli, key_idx[i] selects the key of element i (NULL: element i uses row i).

@@ -40,6 +40,9 @@ EXPORTS = [
     "tecdsa_correct_key_verify_batch", "tecdsa_composite_dlog_verify_batch", "tecdsa_vss_validate_share_batch",
     "tecdsa_gg20_pack_records", "tecdsa_gather_results", "tecdsa_nccl_unique_id", "tecdsa_nccl_comm_create", "tecdsa_nccl_comm_destroy",
     "tecdsa_gg20_offline_records", "tecdsa_gg20_sign_batch", "tecdsa_ctx_work", "tecdsa_ctx_profile", "tecdsa_ctx_profile_read",
+    "tecdsa_secp_add_batch", "tecdsa_secp_sub_batch", "tecdsa_secp_compress_batch", "tecdsa_secp_decompress_batch", "tecdsa_secp_scalar_mul_batch",
+    "tecdsa_secp_scalar_add_batch", "tecdsa_secp_scalar_sub_batch", "tecdsa_secp_scalar_inv_batch", "tecdsa_secp_scalar_from_bigint_batch",
+    "tecdsa_wide_muladd_batch", "tecdsa_unit_mod_check_batch", "tecdsa_sha256_batch",
     "tecdsa_correct_key_prove_batch", "tecdsa_composite_dlog_prove_batch", "tecdsa_vss_share_batch", "tecdsa_h1_h2_n_tilde_batch",
 ]
 
@@ -343,5 +346,116 @@ def _profile_step(self, fn):
 
 Engine.work, Engine.pack_records, Engine.gather_results, Engine.offline_records = _work, _pack_records, _gather_results, _offline_records
 Engine.nccl_unique_id, Engine.nccl_comm_create, Engine.nccl_comm_destroy, Engine.profile_step = _nccl_unique_id, _nccl_comm_create, _nccl_comm_destroy, _profile_step
+# ----------------------------------------------------------------------------- Scalar / Point / BigInt helpers (L0)
+def _bind_ec(lib):
+    if getattr(lib, "_ec_bound", False):
+        return
+    V, S, I = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    for n in ("add", "sub"):
+        getattr(lib, f"tecdsa_secp_{n}_batch").argtypes = [V, V, V, V, S, I]
+    lib.tecdsa_secp_compress_batch.argtypes = [V, V, V, S, I]
+    lib.tecdsa_secp_decompress_batch.argtypes = [V, V, V, V, S, I]
+    for n in ("mul", "add", "sub"):
+        getattr(lib, f"tecdsa_secp_scalar_{n}_batch").argtypes = [V, V, V, V, S, I]
+    lib.tecdsa_secp_scalar_inv_batch.argtypes = [V, V, V, V, S, I]
+    lib.tecdsa_secp_scalar_from_bigint_batch.argtypes = [V, V, I, V, S, I]
+    lib.tecdsa_wide_muladd_batch.argtypes = [V, V, I, V, I, V, I, V, I, S, I]
+    lib.tecdsa_unit_mod_check_batch.argtypes = [V, I, V, V, V, S, V, S, I]
+    lib.tecdsa_sha256_batch.argtypes = [V, V, V, V, S, I]
+    lib._ec_bound = True
+
+
+def _pack_pts(points):
+    return ints_to_limbs([0 if p is None else p[0] | (p[1] << 256) for p in points], 16)
+
+
+def _unpack_pts(arr):
+    return [None if v == 0 else (v & ((1 << 256) - 1), v >> 256) for v in limbs_to_ints(arr)]
+
+
+def _point_add(self, a, b, subtract=False):
+    """Batched `Point + Point` / `Point - Point`; points are (x, y) tuples or None (identity)."""
+    _bind_ec(self.lib)
+    A, B = _pack_pts(a), _pack_pts(b)
+    out = np.zeros_like(A)
+    fn = self.lib.tecdsa_secp_sub_batch if subtract else self.lib.tecdsa_secp_add_batch
+    self._ck(fn(self._ctx, _ptr(A), _ptr(B), _ptr(out), len(a), HOST), "secp_add/sub")
+    return _unpack_pts(out)
+
+
+def _point_compress(self, points):
+    """Batched `Point::to_bytes(true)` -> list of 33-byte strings"""
+    _bind_ec(self.lib)
+    A = _pack_pts(points)
+    out = np.zeros((len(points), 33), dtype=np.uint8)
+    self._ck(self.lib.tecdsa_secp_compress_batch(self._ctx, _ptr(A), _ptr(out), len(points), HOST), "secp_compress")
+    return [bytes(r) for r in out]
+
+
+def _point_decompress(self, encodings):
+    """Batched `Point::from_bytes` of 33-byte compressed encodings -> list of (x, y) or None (malformed)"""
+    _bind_ec(self.lib)
+    n = len(encodings)
+    buf = np.frombuffer(b"".join(bytes(e).ljust(33, b"\0")[:33] for e in encodings), dtype=np.uint8).reshape(n, 33).copy()
+    out, ok = np.zeros((n, 16), dtype=np.uint32), np.zeros(n, dtype=np.uint8)
+    self._ck(self.lib.tecdsa_secp_decompress_batch(self._ctx, _ptr(buf), _ptr(out), _ptr(ok), n, HOST), "secp_decompress")
+    return [p if o else None for p, o in zip(_unpack_pts(out), ok)]
+
+
+def _scalar_op(self, op, a, b=None):
+    """Batched `Scalar` arithmetic mod q: op in {"mul", "add", "sub", "inv"}; inv returns None for zero"""
+    _bind_ec(self.lib)
+    A = ints_to_limbs(a, 8)
+    out = np.zeros_like(A)
+    if op == "inv":
+        ok = np.zeros(len(a), dtype=np.uint8)
+        self._ck(self.lib.tecdsa_secp_scalar_inv_batch(self._ctx, _ptr(A), _ptr(out), _ptr(ok), len(a), HOST), "secp_scalar_inv")
+        return [v if o else None for v, o in zip(limbs_to_ints(out), ok)]
+    B = ints_to_limbs(b, 8)
+    self._ck(getattr(self.lib, f"tecdsa_secp_scalar_{op}_batch")(self._ctx, _ptr(A), _ptr(B), _ptr(out), len(a), HOST), "secp_scalar_" + op)
+    return limbs_to_ints(out)
+
+
+def _scalar_from_bigint(self, x, limbs=64):
+    _bind_ec(self.lib)
+    X = ints_to_limbs(x, limbs)
+    out = np.zeros((len(x), 8), dtype=np.uint32)
+    self._ck(self.lib.tecdsa_secp_scalar_from_bigint_batch(self._ctx, _ptr(X), limbs, _ptr(out), len(x), HOST), "secp_scalar_from_bigint")
+    return limbs_to_ints(out)
+
+
+def _wide_muladd(self, a, b, c, a_limbs, b_limbs, c_limbs, out_limbs):
+    """Batched exact a*b + c (no modulus)"""
+    _bind_ec(self.lib)
+    A, B, C = ints_to_limbs(a, a_limbs), ints_to_limbs(b, b_limbs), ints_to_limbs(c, c_limbs)
+    out = np.zeros((len(a), out_limbs), dtype=np.uint32)
+    self._ck(self.lib.tecdsa_wide_muladd_batch(self._ctx, _ptr(A), a_limbs, _ptr(B), b_limbs, _ptr(C), c_limbs, _ptr(out), out_limbs, len(a), HOST), "wide_muladd")
+    return limbs_to_ints(out)
+
+
+def _unit_mod_check(self, r, modulus, mod_bits=2048):
+    """Batched acceptance test of `SampleFromMultiplicativeGroup`: r < N and gcd(r, N) == 1"""
+    _bind_ec(self.lib)
+    k = mod_bits // 32
+    R, M = ints_to_limbs(r, k), ints_to_limbs(modulus, k)
+    ok = np.zeros(len(r), dtype=np.uint8)
+    self._ck(self.lib.tecdsa_unit_mod_check_batch(self._ctx, mod_bits, _ptr(R), _ptr(M), None, 0, _ptr(ok), len(r), HOST), "unit_mod_check")
+    return [bool(x) for x in ok]
+
+
+def _sha256(self, messages):
+    """Batched SHA-256 of byte strings"""
+    _bind_ec(self.lib)
+    n = len(messages)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(m) for m in messages])
+    blob = np.frombuffer(b"".join(messages) or b"\0", dtype=np.uint8).copy()
+    out = np.zeros((n, 32), dtype=np.uint8)
+    self._ck(self.lib.tecdsa_sha256_batch(self._ctx, _ptr(blob), _ptr(offs), _ptr(out), n, HOST), "sha256")
+    return [bytes(r) for r in out]
+
+
+Engine.point_add, Engine.point_compress, Engine.point_decompress, Engine.scalar_op = _point_add, _point_compress, _point_decompress, _scalar_op
+Engine.scalar_from_bigint, Engine.wide_muladd, Engine.unit_mod_check, Engine.sha256 = _scalar_from_bigint, _wide_muladd, _unit_mod_check, _sha256
 Engine.mod_mul, Engine.mod_inv, Engine.secp_mul = _mod_mul, _mod_inv, _secp_mul
 Engine.paillier_encrypt, Engine.paillier_mul, Engine.paillier_add, Engine.paillier_decrypt = _paillier_encrypt, _paillier_mul, _paillier_add, _paillier_decrypt

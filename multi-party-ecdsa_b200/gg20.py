@@ -244,16 +244,43 @@ def alice_proof_generate(eng: Engine, keys: KeySets, ek_row, st_row, a, cipher, 
     return {k: limbs_to_ints(v) for k, v in outs.items()}
 
 
+class _Screen:
+    """Untrusted proof fields arrive as arbitrary integers; the ABI slots have fixed widths.  A field that is negative or wider
+    than its slot can never verify (the reference compares / hashes the full value: `s1 > q^3`, range_proofs.rs:118, or a
+    challenge mismatch), so it is replaced by 0 and that ONE proof is marked rejected after the call — it must not abort the
+    whole batch with an OverflowError in the limb packing."""
+
+    def __init__(self, n: int):
+        self.bad = np.zeros(n, dtype=bool)
+        self.range_bad = np.zeros(n, dtype=bool)
+
+    def limbs(self, vals, k: int, is_range_field: bool = False) -> np.ndarray:
+        out = []
+        for i, v in enumerate(vals):
+            v = int(v)
+            if v < 0 or v >> (32 * k):
+                (self.range_bad if is_range_field and v > 0 else self.bad)[i] = True
+                v = 0
+            out.append(v)
+        return ints_to_limbs(out, k)
+
+    def apply(self, status: np.ndarray, code: int, range_code: int = None) -> np.ndarray:
+        status[self.bad] = code
+        status[self.range_bad] = code if range_code is None else range_code
+        return status
+
+
 def alice_proof_verify(eng: Engine, keys: KeySets, ek_row, st_row, cipher, z, e, s, s1, s2) -> np.ndarray:
     """Batched `AliceProof::verify` (range_proofs.rs:105-156): status byte per proof (0 = accept)."""
     _bind_l2(eng.lib)
     n = len(z)
     er, sr = np.asarray(ek_row, dtype=np.uint32), np.asarray(st_row, dtype=np.uint32)
-    ins = [ints_to_limbs(cipher, 128), ints_to_limbs(z, 64), ints_to_limbs(e, 8), ints_to_limbs(s, 64), ints_to_limbs(s1, 28), ints_to_limbs(s2, 92)]
+    sc = _Screen(n)
+    ins = [sc.limbs(cipher, 128), sc.limbs(z, 64), sc.limbs(e, 8), sc.limbs(s, 64), sc.limbs(s1, 28, True), sc.limbs(s2, 92)]
     status = np.full(n, 255, dtype=np.uint8)
     eng._ck(eng.lib.tecdsa_alice_proof_verify_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), *[_ptr(x) for x in ins], _ptr(status), n, HOST),
             "alice_proof_verify")
-    return status
+    return sc.apply(status, 5, 3)            # TECDSA_ST_HASH_MISMATCH; an over-wide s1 is the `s1 > q^3` reject (TECDSA_ST_RANGE)
 
 
 # ----------------------------------------------------------------------------- L2: PDLwSlack and Bob proofs, batched
@@ -293,11 +320,12 @@ def pdl_prove(eng, keys, ek_row, st_row, x, r, cipher, Q, G, alpha, beta, rho, g
 def pdl_verify(eng, keys, ek_row, st_row, cipher, Q, G, z, u1, u2, u3, s1, s2, s3) -> np.ndarray:
     _bind_l2b(eng.lib)
     n = len(z)
-    ins = [_rows(ek_row), _rows(st_row), ints_to_limbs(cipher, 128), _pts(Q), _pts(G), ints_to_limbs(z, 64), _pts(u1), ints_to_limbs(u2, 128),
-           ints_to_limbs(u3, 64), ints_to_limbs(s1, 28), ints_to_limbs(s2, 64), ints_to_limbs(s3, 92)]
+    sc = _Screen(n)
+    ins = [_rows(ek_row), _rows(st_row), sc.limbs(cipher, 128), _pts(Q), _pts(G), sc.limbs(z, 64), _pts(u1), sc.limbs(u2, 128),
+           sc.limbs(u3, 64), sc.limbs(s1, 28), sc.limbs(s2, 64), sc.limbs(s3, 92)]
     status = np.full(n, 255, dtype=np.uint8)
     eng._ck(eng.lib.tecdsa_pdl_verify_batch(eng._ctx, keys.handle, *[_ptr(a) for a in ins], _ptr(status), n, HOST), "pdl_verify")
-    return status
+    return sc.apply(status, 6)               # TECDSA_ST_PDL_VERIFY
 
 
 def bob_proof_generate(eng, keys, ek_row, st_row, check, a_enc, mta_enc, b, beta_prim, r, alpha, beta, gamma, ro, ro_prim, sigma, tau):
@@ -321,14 +349,15 @@ def bob_proof_verify(eng, keys, ek_row, st_row, a_enc, mta_out, pf, X=None, u=No
     """Batched `BobProof::verify` (X is None) / `BobProofExt::verify` (X = G*b, u from the proof)."""
     _bind_l2b(eng.lib)
     n = len(pf["z"])
-    ins = [_rows(ek_row), _rows(st_row), ints_to_limbs(a_enc, 128), ints_to_limbs(mta_out, 128), ints_to_limbs(pf["t"], 64), ints_to_limbs(pf["z"], 64),
-           ints_to_limbs(pf["e"], 8), ints_to_limbs(pf["s"], 64), ints_to_limbs(pf["s1"], 28), ints_to_limbs(pf["s2"], 92), ints_to_limbs(pf["t1"], 84),
-           ints_to_limbs(pf["t2"], 92)]
+    sc = _Screen(n)
+    ins = [_rows(ek_row), _rows(st_row), sc.limbs(a_enc, 128), sc.limbs(mta_out, 128), sc.limbs(pf["t"], 64), sc.limbs(pf["z"], 64),
+           sc.limbs(pf["e"], 8), sc.limbs(pf["s"], 64), sc.limbs(pf["s1"], 28, True), sc.limbs(pf["s2"], 92), sc.limbs(pf["t1"], 84),
+           sc.limbs(pf["t2"], 92)]
     Xa = _pts(X) if X is not None else None
     Ua = _pts(u) if u is not None else None
     status = np.full(n, 255, dtype=np.uint8)
     eng._ck(eng.lib.tecdsa_bob_proof_verify_batch(eng._ctx, keys.handle, *[_ptr(a) for a in ins], _ptr(Xa), _ptr(Ua), _ptr(status), n, HOST), "bob_proof_verify")
-    return status
+    return sc.apply(status, 5, 3)
 
 
 # ----------------------------------------------------------------------------- curv sigma proofs / hashes, batched
@@ -450,13 +479,19 @@ def mta_message_b(eng, keys, ek_row, st_rows, b, c_a, proofs, randomness, beta_t
     n_st = len(st_rows[0]) if n else 0
     flat = {k: [v for inst in proofs[k] for v in inst] for k in ("z", "e", "s", "s1", "s2")}
     er, sr = _rows(ek_row), np.ascontiguousarray(np.asarray(st_rows, dtype=np.uint32).reshape(-1))
-    ins = [ints_to_limbs(b, 8), ints_to_limbs(c_a, 128), ints_to_limbs(flat["z"], 64), ints_to_limbs(flat["e"], 8), ints_to_limbs(flat["s"], 64),
-           ints_to_limbs(flat["s1"], 28), ints_to_limbs(flat["s2"], 92), ints_to_limbs(randomness, 64), ints_to_limbs(beta_tag, 64),
+    # the peer's MessageA is untrusted: an over-wide field of any of its range proofs makes that MessageB Err(InvalidKey)
+    scp, sca = _Screen(n * n_st), _Screen(n)
+    ins = [ints_to_limbs(b, 8), sca.limbs(c_a, 128), scp.limbs(flat["z"], 64), scp.limbs(flat["e"], 8), scp.limbs(flat["s"], 64),
+           scp.limbs(flat["s1"], 28), scp.limbs(flat["s2"], 92), ints_to_limbs(randomness, 64), ints_to_limbs(beta_tag, 64),
            ints_to_limbs(nonce_b, 8), ints_to_limbs(nonce_beta, 8)]
     c_b, bp, btp, beta = np.zeros((n, 128), np.uint32), np.zeros((n, 40), np.uint32), np.zeros((n, 40), np.uint32), np.zeros((n, 8), np.uint32)
     status = np.full(n, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_mta_message_b_batch(eng._ctx, keys.handle, _ptr(er), _ptr(sr), n_st, *[_ptr(x) for x in ins], _ptr(c_b), _ptr(bp), _ptr(btp),
                                                _ptr(beta), _ptr(status), n, HOST), "mta_message_b")
+    rejected = sca.bad | sca.range_bad
+    if n_st:
+        rejected |= (scp.bad | scp.range_bad).reshape(n, n_st).any(axis=1)
+    status[rejected] = 2                     # TECDSA_ST_INVALID_KEY (mta/mod.rs:120,130)
     return limbs_to_ints(c_b), bp, btp, limbs_to_ints(beta), status
 
 

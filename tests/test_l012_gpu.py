@@ -138,6 +138,12 @@ def test_alice_proof_generate_verify_batch(engine, pkg, keyset):
     bad_z = list(pf["z"]); bad_z[2] = 0
     st1 = gg20.alice_proof_verify(engine, ks, ek_row, st_row, bad_c, bad_z, pf["e"], pf["s"], bad_s1, pf["s2"])
     assert st1[0] == pkg.ST_HASH_MISMATCH and st1[1] == pkg.ST_RANGE and st1[2] == pkg.ST_NOT_INVERTIBLE and not st1[3:].any()
+    # fields wider than their ABI slot (or negative) reject THAT proof and leave the rest of the batch alone
+    wide_s1 = list(pf["s1"]); wide_s1[3] = 1 << 900
+    wide_s2 = list(pf["s2"]); wide_s2[4] = 1 << 2944
+    wide_z = list(pf["z"]); wide_z[5] = pf["z"][5] + (1 << 2048); wide_z[6] = -1
+    st2 = gg20.alice_proof_verify(engine, ks, ek_row, st_row, cph, wide_z, pf["e"], pf["s"], wide_s1, wide_s2)
+    assert st2[3] == pkg.ST_RANGE and list(st2[4:7]) == [pkg.ST_HASH_MISMATCH] * 3 and not st2[:3].any() and not st2[7:].any()
     ks.free()
 
 
@@ -323,3 +329,44 @@ def test_mta_messages_batch(engine, pkg, keyset):
     _, _, st4 = gg20.mta_get_alpha(engine, ks, ek_row, a_bad, c_b, bp, btp)
     assert st4[0] == pkg.ST_INVALID_KEY and not st4[1:].any()
     ks.free()
+
+
+def test_scalar_point_bigint_surface(engine, pkg):
+    """The rest of the Scalar / Point / BigInt surface the protocol code calls (include/tecdsa_b200.h L0), against Python
+    integers, the oracle's secp256k1 (itself pinned to OpenSSL) and hashlib."""
+    import hashlib
+    from math import gcd
+    rng = random.Random(0xB2E0)
+    Qn, Pn = o.Q, o.P
+    a = [rng.randrange(Qn) for _ in range(40)] + [0, 1, Qn - 1]
+    b = [rng.randrange(Qn) for _ in range(40)] + [Qn - 1, 0, Qn - 1]
+    assert engine.scalar_op("mul", a, b) == [x * y % Qn for x, y in zip(a, b)]
+    assert engine.scalar_op("add", a, b) == [(x + y) % Qn for x, y in zip(a, b)]
+    assert engine.scalar_op("sub", a, b) == [(x - y) % Qn for x, y in zip(a, b)]
+    assert engine.scalar_op("inv", a) == [pow(x, -1, Qn) if x else None for x in a]
+    big = [rng.getrandbits(2048) for _ in range(8)] + [Qn, Qn + 5, 0, (1 << 2048) - 1]
+    assert engine.scalar_from_bigint(big, 64) == [x % Qn for x in big]
+    pts = [o.pt_mul(o.G, rng.randrange(1, Qn)) for _ in range(12)]
+    A = pts + [None, pts[0], pts[1], None]
+    B = pts[1:] + pts[:1] + [pts[3], pts[0], o.pt_neg(pts[1]), None]
+    assert engine.point_add(A, B) == [o.pt_add(x, y) for x, y in zip(A, B)]
+    assert engine.point_add(A, B, subtract=True) == [o.pt_sub(x, y) for x, y in zip(A, B)]
+    enc = engine.point_compress(pts)
+    assert enc == [o.pt_compress(p) for p in pts]
+    assert engine.point_compress([None]) == [bytes(33)]
+    bad_x = next(x for x in range(2, 100) if pow((x ** 3 + 7) % Pn, (Pn - 1) // 2, Pn) != 1)
+    bogus = [b"\x04" + enc[0][1:], b"\x02" + Pn.to_bytes(32, "big"), b"\x02" + bad_x.to_bytes(32, "big")]
+    assert engine.point_decompress(enc + bogus) == pts + [None, None, None]
+    # e * a + alpha over the integers (range_proofs.rs:87-88)
+    e, x, al = [rng.getrandbits(256) for _ in range(6)], [rng.randrange(Qn) for _ in range(6)], [rng.randrange(Qn ** 3) for _ in range(6)]
+    assert engine.wide_muladd(e, x, al, 8, 8, 24, 28) == [p * q + r for p, q, r in zip(e, x, al)]
+    # SampleFromMultiplicativeGroup acceptance: r < N and gcd(r, N) == 1
+    p1, p2 = 0xFFFFFFFFFFFFFFC5, 2 ** 89 - 1
+    N = [((rng.getrandbits(2048) | (1 << 2047) | 1) // (p1 * p2)) * p1 * p2 | 0 for _ in range(6)]
+    N = [n if n & 1 else n + p1 * p2 for n in N]
+    r = [rng.randrange(N[0]), p1 * 12345, N[2] + 5, p2, 1, 0]
+    want = [x < n and gcd(x, n) == 1 for x, n in zip(r, N)]
+    assert want[1:4] == [False, False, False] and want[4] and not want[5]
+    assert engine.unit_mod_check(r, N) == want
+    msgs = [b"", b"abc", b"ZenGo", bytes(range(256)) * 5, b"x" * 55, b"y" * 56, b"z" * 64]
+    assert engine.sha256(msgs) == [hashlib.sha256(m).digest() for m in msgs]
