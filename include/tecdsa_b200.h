@@ -370,10 +370,12 @@ int tecdsa_ctx_profile_read(tecdsa_ctx* ctx, tecdsa_launch_info* out, size_t cap
 /* test access: copy one named per-unit field of the last batch (names in csrc/gg20_fields.h) */
 int tecdsa_gg20_debug_field(tecdsa_ctx* ctx, const char* name, uint32_t* out_host, size_t* limbs_per_unit);
 
-/* Saturation micro-benchmark of the integer multiply-add pipe (IMAD.WIDE.U32 with carry
- * chains shaped like the Montgomery rows): 32x32+64 MACs per second on this device.  This is
- * the roofline denominator for every kernel of this library. */
+/* Saturation micro-benchmarks of the integer multiply-add pipe, 32x32+64 MACs per second on this device — the roofline
+ * denominators of every kernel of this library.  imad_peak: carry-free IMAD.WIDE.U32 on 16 independent
+ * accumulators per thread, every product with its own operand pair; imad_peak_chained: IMAD.WIDE.U32.X in the carry chains of
+ * the Montgomery rows (two accumulator sets per thread).  Both at full occupancy; SASS in profiles/r02_imad_peak_sass.md.      */
 int tecdsa_imad_peak(tecdsa_ctx* ctx, double* mac32_per_s, float* ms);
+int tecdsa_imad_peak_chained(tecdsa_ctx* ctx, double* mac32_per_s, float* ms);
 
 #ifdef __cplusplus
 }

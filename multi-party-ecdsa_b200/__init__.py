@@ -29,7 +29,7 @@ ST_PDL_VERIFY, ST_PHASE5_BAD_SUM, ST_PHASE6, ST_INVALID_SIG, ST_PROOF, ST_COMMIT
 # every symbol include/tecdsa_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tecdsa_ctx_create", "tecdsa_ctx_destroy", "tecdsa_ctx_sync", "tecdsa_last_error", "tecdsa_ctx_set_tpi",
-    "tecdsa_ctx_last_kernel_ms", "tecdsa_ctx_launch_count", "tecdsa_modexp_batch", "tecdsa_imad_peak",
+    "tecdsa_ctx_last_kernel_ms", "tecdsa_ctx_launch_count", "tecdsa_modexp_batch", "tecdsa_imad_peak", "tecdsa_imad_peak_chained",
     "tecdsa_keys_upload", "tecdsa_keys_free", "tecdsa_keys_table", "tecdsa_gg20_offline_batch", "tecdsa_gg20_debug_field",
     "tecdsa_modmul_batch", "tecdsa_modinv_batch", "tecdsa_secp_mul_batch", "tecdsa_paillier_encrypt_batch", "tecdsa_paillier_mul_batch",
     "tecdsa_paillier_add_batch", "tecdsa_paillier_decrypt_batch", "tecdsa_alice_proof_generate_batch", "tecdsa_alice_proof_verify_batch",
@@ -139,10 +139,13 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.tecdsa_ctx_launch_count(self._ctx))
 
-    def imad_peak(self):
-        """(MAC32/s, ms) of the integer multiply-add saturation micro-benchmark."""
+    def imad_peak(self, chained: bool = False):
+        """(MAC32/s, ms) of the integer multiply-add saturation micro-benchmark: carry-free IMAD.WIDE.U32, or (chained) the
+        IMAD.WIDE.U32.X carry chains the Montgomery rows are made of."""
         v, ms = ctypes.c_double(), ctypes.c_float()
-        self._ck(self.lib.tecdsa_imad_peak(self._ctx, ctypes.byref(v), ctypes.byref(ms)), "imad_peak")
+        fn = self.lib.tecdsa_imad_peak_chained if chained else self.lib.tecdsa_imad_peak
+        fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
+        self._ck(fn(self._ctx, ctypes.byref(v), ctypes.byref(ms)), "imad_peak")
         return v.value, ms.value
 
     # ---- BigInt::mod_pow, batched -------------------------------------------------------

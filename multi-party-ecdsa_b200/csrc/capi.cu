@@ -275,61 +275,90 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
 }
 
 // ------------------------------------------------------------------------------------ IMAD peak
-// NACC independent 64-bit accumulators per thread, acc += a*b as IMAD.WIDE.U32 (the
-// instruction every Montgomery row is made of; the .X carry variant issues on the same
-// pipe at the same rate); few registers so the SM runs at full occupancy.
-template <int NACC>
+// Saturation micro-benchmarks of the integer multiply-add pipe — the roofline denominators.
+//  * carry-free: 16 independent 64-bit accumulators per thread, acc_j += a_j * b_u as IMAD.WIDE.U32 — every product of an
+//    iteration has its OWN operand pair (16 distinct a_j, a fresh b_u per step), so ptxas cannot share a product between two
+//    accumulators (the round-1 kernel reused operand pairs and ptxas turned half of its MACs into adds);
+//  * carry-chained: the instruction the Montgomery rows are made of, IMAD.WIDE.U32.X with carry in and out — the mad_even /
+//    mad_odd chains of bigint.cuh on two accumulator sets, exactly as mont_row issues them.
+// Both run at full occupancy with few registers; profiles/r02_imad_peak_sass.md holds the SASS of the two loops.
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
+    constexpr int NACC = 16;
     uint64_t acc[NACC];
-    uint32_t a[8];
+    uint32_t a[NACC];
 #pragma unroll
-    for (int j = 0; j < 8; j++) a[j] = (seed + j) * (threadIdx.x | 1u);
-#pragma unroll
-    for (int j = 0; j < NACC; j++) acc[j] = (uint64_t)seed * (j + 1) + threadIdx.x;
+    for (int j = 0; j < NACC; j++) { a[j] = (seed + 0x9e3779b9u * (j + 1)) ^ (threadIdx.x * 2654435761u); acc[j] = (uint64_t)seed * (j + 1) + threadIdx.x; }
     uint32_t b = seed ^ 0x85ebca6bu ^ threadIdx.x;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int u = 0; u < 32 / NACC; u++) {
-            const uint32_t bu = b ^ a[u];
+        for (int u = 0; u < 4; u++) {
+            const uint32_t bu = b + 0x01000193u * (u + 1);               // a fresh multiplier per step
 #pragma unroll
             for (int j = 0; j < NACC; j++)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[(j + u) & 7]), "r"(bu));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(bu));
         }
-        b = b * 5u + (uint32_t)acc[0];
+        b = b * 5u + 1u;
     }
     uint64_t x = 0;
 #pragma unroll
     for (int j = 0; j < NACC; j++) x ^= acc[j];
     if (x == 0x12345678u) sink[0] = (uint32_t)x;
 }
+__global__ void __launch_bounds__(256) imad_chain_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
+    constexpr int L = 16;
+    uint32_t E[L + 2], O[L + 2], a[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) a[j] = (seed + 0x9e3779b9u * (j + 1)) ^ (threadIdx.x * 2654435761u);
+#pragma unroll
+    for (int j = 0; j < L + 2; j++) { E[j] = seed + j; O[j] = seed ^ j; }
+    uint32_t b = seed ^ 0x85ebca6bu ^ threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t bu = b + 0x01000193u * (u + 1);
+            mad_even<L>(E, a, bu);                                       // 8 IMAD.WIDE.U32(.X) in one carry chain
+            mad_odd<L>(O, a, bu);                                        // 8 more on the second accumulator set
+        }
+        b = b * 5u + E[0];
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < L + 2; j++) x ^= E[j] ^ O[j];
+    if (x == 0x12345678u) sink[0] = x;
+}
 
-extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_out) {
-    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+static int imad_run(tecdsa_ctx* c, bool chained, double* mac32_per_s, float* ms_out) {
     CK(cudaSetDevice(c->device));
     int rc = ws_reserve(c, 4096);
     if (rc) return rc;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, c->device));
-    const int iters = 1 << 13, block = 256, grid = prop.multiProcessorCount * 16;
-    imad_peak_kernel<8><<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u, 64);   // warm-up
+    const int iters = 1 << 13, block = 256, grid = c->sm_count * 16;
+    const double macs_per_iter = chained ? 64.0 : 64.0;                   // 4 steps x 16 wide MACs per thread and iteration, both kernels
     float best = 1e30f;
-    for (int rep = 0; rep < 6; rep++) {
+    for (int rep = 0; rep < 4; rep++) {
         CK(cudaEventRecord(c->ev0, c->stream));
-        if (rep & 1) imad_peak_kernel<16><<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, iters);
-        else imad_peak_kernel<8><<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, iters);
+        if (chained) imad_chain_peak_kernel<<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, rep ? iters : 64);
+        else imad_peak_kernel<<<grid, block, 0, c->stream>>>((uint32_t*)c->ws, 12345u + rep, rep ? iters : 64);
         CK(cudaEventRecord(c->ev1, c->stream));
         CK(cudaEventSynchronize(c->ev1));
         float t;
         CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
-        if (t < best) best = t;
+        if (rep && t < best) best = t;                                   // rep 0 is the warm-up
     }
     CK(cudaGetLastError());
-    c->launches += 7;
-    double macs = (double)grid * block * (double)iters * 32.0;   // 4 x 8 wide MACs per iteration
-    if (mac32_per_s) *mac32_per_s = macs / (best * 1e-3);
+    c->launches += 4;
+    if (mac32_per_s) *mac32_per_s = (double)grid * block * (double)iters * macs_per_iter / (best * 1e-3);
     if (ms_out) *ms_out = best;
     return 0;
+}
+extern "C" int tecdsa_imad_peak(tecdsa_ctx* c, double* mac32_per_s, float* ms_out) {
+    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+    return imad_run(c, false, mac32_per_s, ms_out);
+}
+extern "C" int tecdsa_imad_peak_chained(tecdsa_ctx* c, double* mac32_per_s, float* ms_out) {
+    if (!c) return fail(TECDSA_E_ARG, "null ctx");
+    return imad_run(c, true, mac32_per_s, ms_out);
 }
 
 // ------------------------------------------------------------------------------------ job-list launches
