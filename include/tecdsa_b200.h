@@ -241,6 +241,20 @@ int tecdsa_vss_share_batch(tecdsa_ctx* ctx, int t, int n_shares, const uint32_t*
 int tecdsa_h1_h2_n_tilde_batch(tecdsa_ctx* ctx, const uint32_t* p_t, const uint32_t* q_t, const uint32_t* h1, const uint32_t* xhi,
                                uint32_t* n_tilde, uint32_t* h2, uint32_t* xhi_neg, uint32_t* xhi_inv_neg, uint8_t* status, size_t count, int mem);
 
+/* ---- identifiable abort (gg_2020/blame.rs) ------------------------------------------------
+ * paillier_open: `Paillier::open(dk, c)` (blame.rs:252-256) over an uploaded key set: m = Dec(c) [count][64] and the
+ *   randomness r [count][64] with c = (1 + m N) r^N mod N^2 (r = (c mod N)^(N^-1 mod phi(N)) mod N).
+ * ecddh_prove / ecddh_verify: curv `ECDDHProof` [R] for statements (g1, h1 = x g1, g2, h2 = x g2) (blame.rs:258-271,405-417):
+ *   proof = a1 16 | a2 16 | z 8 (40 limbs), nonce = the sampled s; status TECDSA_ST_OK / _PROOF.
+ * The blame procedures (`phase5_blame`, `phase6_blame`, `phase7_blame`) re-derive every opened value with these and the
+ * L0/L1 batch calls: multi-party-ecdsa_b200/blame.py.                                                                    */
+int tecdsa_paillier_open_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* key_row, const uint32_t* c, uint32_t* m, uint32_t* r,
+                               size_t count, int mem);
+int tecdsa_ecddh_prove_batch(tecdsa_ctx* ctx, const uint32_t* x, const uint32_t* g1, const uint32_t* h1, const uint32_t* g2, const uint32_t* h2,
+                             const uint32_t* nonce, uint32_t* proof, size_t count, int mem);
+int tecdsa_ecddh_verify_batch(tecdsa_ctx* ctx, const uint32_t* proof, const uint32_t* g1, const uint32_t* h1, const uint32_t* g2, const uint32_t* h2,
+                              uint8_t* status, size_t count, int mem);
+
 /* ---- curv-kzen sigma proofs and hashes used by the protocol (out-of-tree crate; call sites cited) ----------------
  * Scalars are 8 limbs (reduced mod q on entry), points affine x||y 16 limbs.  Verifiers write TECDSA_ST_OK or
  * TECDSA_ST_PROOF.  Encodings [R]: challenges hash 65-byte uncompressed points and reduce the digest mod q.

@@ -43,6 +43,7 @@ EXPORTS = [
     "tecdsa_secp_add_batch", "tecdsa_secp_sub_batch", "tecdsa_secp_compress_batch", "tecdsa_secp_decompress_batch", "tecdsa_secp_scalar_mul_batch",
     "tecdsa_secp_scalar_add_batch", "tecdsa_secp_scalar_sub_batch", "tecdsa_secp_scalar_inv_batch", "tecdsa_secp_scalar_from_bigint_batch",
     "tecdsa_wide_muladd_batch", "tecdsa_unit_mod_check_batch", "tecdsa_sha256_batch",
+    "tecdsa_paillier_open_batch", "tecdsa_ecddh_prove_batch", "tecdsa_ecddh_verify_batch",
     "tecdsa_correct_key_prove_batch", "tecdsa_composite_dlog_prove_batch", "tecdsa_vss_share_batch", "tecdsa_h1_h2_n_tilde_batch",
 ]
 

@@ -6,7 +6,7 @@
 // job-list launch per kind of modulus (1024-bit: p, q; 2048-bit: N_tilde, N; p-adic: p^2, q^2;
 // N-adic: N^2 — nadic.cuh), and, where the verifier needs `mod_inv`, an inversion launch.
 #include "ctx.h"
-#include "gg20_glue.cuh"
+#include "gg20_rounds.cuh"
 #include "modinv.cuh"
 
 #include <cstdlib>
@@ -103,12 +103,13 @@ struct Builder {
     }
 };
 
+#define glue(c, kern, ...) glue_named(c, kern, #kern, __VA_ARGS__)
 const Operand NONE = {nullptr, nullptr, 0, 0, 0};
 constexpr int GPW32 = 32 / TPI_1024, GPW64 = 32 / TPI_2048, GPWI128 = 32 / TPI_4096;
 
-template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A, int per_unit = 1) {
+template <typename Kern> int glue_named(tecdsa_ctx* c, Kern kern, const char* name, const Arena& A, int per_unit = 1) {
     int grid = (A.U * per_unit + 63) / 64;
-    c->prof_begin("gg20 glue (EC, hashing, checks)");
+    c->prof_begin(name);
     kern<<<grid, 64, 0, c->stream>>>(A);
     c->prof_end();
     c->count_launch();
@@ -117,7 +118,7 @@ template <typename Kern> int glue(tecdsa_ctx* c, Kern kern, const Arena& A, int 
 }
 
 int glue_crt(tecdsa_ctx* c, const Arena& A, int first, int count) {
-    c->prof_begin("gg20_crt (CRT recombination)");
+    c->prof_begin("gg20_crt");
     gg20_crt<<<(A.U + 63) / 64, 64, 0, c->stream>>>(A, first, count);
     c->prof_end();
     c->count_launch();

@@ -1,5 +1,11 @@
 // secp256k1 field / scalar / point arithmetic for sm_100a, one thread per operation.
 //
+// Structure (round 2): field operations, point doubling and addition are __forceinline__ and work on registers; the units of
+// non-inlined code are whole scalar multiplications (jac_mul: GLV split + signed fixed 5-bit windows over a table of 16 multiples;
+// jac_mul_fixed: 8-bit windows over precomputed affine tables of G and base_point2) and the field inversion (fixed addition
+// chain).  Verifiers compare a computed Jacobian point with a received affine point WITHOUT inverting (jac_eq_affine), provers
+// normalise all their output points with one shared inversion (jac_to_affine2/3).
+//
 // Replaces curv-kzen `Scalar<Secp256k1>` / `Point<Secp256k1>` (libsecp256k1 underneath) at the
 // call sites of the GG20 offline stage: /root/reference/src/protocols/multi_party_ecdsa/gg_2020/
 // party_i.rs:559-563,627-630,682-686,784, src/utilities/mta/mod.rs:168-169 and
@@ -33,6 +39,28 @@ __device__ __constant__ const uint32_t HX_LIMBS[8] = {0x0378B795u, 0xA8DC7BFAu, 
                                                       0x4BA80116u, 0x34DD4521u, 0xE3A7326Au, 0x08D13221u};
 __device__ __constant__ const uint32_t HY_LIMBS[8] = {0xF7C2BE88u, 0x8217E9F7u, 0xDF0DF07Au, 0x807BCBA1u,
                                                       0xBD565EA2u, 0x0848D50Du, 0x77614B5Cu, 0x5D41AC14u};
+
+// GLV endomorphism (x, y) -> (BETA x, y) = LAMBDA * (x, y) and the lattice constants of the scalar split k = k1 + k2 LAMBDA
+// with |k1|, |k2| < 2^128 (derivation and exhaustive bound check: tests/test_glue_host.py::test_glv_split):
+//   c1 = round(k G1 / 2^384), c2 = round(k G2 / 2^384), k2 = c1 (-b1) + c2 (-b2), k1 = k - k2 LAMBDA   (all mod q)
+__device__ __constant__ const uint32_t BETA_LIMBS[8] = {0x719501EEu, 0xC1396C28u, 0x12F58995u, 0x9CF04975u, 0xAC3434E9u, 0x6E64479Eu, 0x657C0710u, 0x7AE96A2Bu};
+__device__ __constant__ const uint32_t MINUS_LAMBDA_LIMBS[8] = {0xB51283CFu, 0xE0CFC810u, 0x8EC739C2u, 0xA880B9FCu, 0x77ED9BA4u, 0x5AD9E3FDu, 0x3FA3CF1Fu, 0xAC9C52B3u};
+__device__ __constant__ const uint32_t GLV_G1_LIMBS[8] = {0x45DBB031u, 0xE893209Au, 0x71E8CA7Fu, 0x3DAA8A14u, 0x9284EB15u, 0xE86C90E4u, 0xA7D46BCDu, 0x3086D221u};
+__device__ __constant__ const uint32_t GLV_G2_LIMBS[8] = {0x8AC47F71u, 0x1571B4AEu, 0x9DF506C6u, 0x221208ACu, 0x0ABFE4C4u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u};
+__device__ __constant__ const uint32_t GLV_MINUS_B1_LIMBS[8] = {0x0ABFE4C3u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u, 0u, 0u, 0u, 0u};
+__device__ __constant__ const uint32_t GLV_MINUS_B2_LIMBS[8] = {0x3DB1562Cu, 0xD765CDA8u, 0x0774346Du, 0x8A280AC5u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+// curv `VerifiableSS::map_share_to_new_params` [R] for two signers: lambda_own = x_peer / (x_peer - x_own) mod q with x = index + 1;
+// the six (own, peer) pairs of n = 3 (row own * 3 + peer; the diagonal is unused)
+__device__ __constant__ const uint32_t LAGRANGE2_LIMBS[9][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0},
+    {2, 0, 0, 0, 0, 0, 0, 0},
+    {0x681B20A2u, 0xDFE92F46u, 0x57A4501Du, 0x5D576E73u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu},
+    {0xD0364140u, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu},
+    {0, 0, 0, 0, 0, 0, 0, 0},
+    {3, 0, 0, 0, 0, 0, 0, 0},
+    {0x681B20A0u, 0xDFE92F46u, 0x57A4501Du, 0x5D576E73u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu},
+    {0xD036413Fu, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu},
+    {0, 0, 0, 0, 0, 0, 0, 0}};
 
 __device__ __forceinline__ U256 u256_zero() { U256 r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
 __device__ __forceinline__ U256 u256_one() { U256 r = u256_zero(); r.v[0] = 1; return r; }
@@ -139,29 +167,50 @@ __device__ __forceinline__ U256 fe_reduce512(const uint32_t (&t)[16]) {
 }
 __device__ __forceinline__ U256 fe_mul(const U256& a, const U256& b) { uint32_t t[16]; mul_256(t, a, b); return fe_reduce512(t); }
 __device__ __forceinline__ U256 fe_sqr(const U256& a) { return fe_mul(a, a); }
+// branch-free: the subtraction is always computed and selected by mask (data-dependent branches diverge inside a warp)
 __device__ __forceinline__ U256 fe_add(const U256& a, const U256& b) {
-    U256 r; uint32_t c = u256_add(r, a, b);
-    if (c || u256_ge(r, P_LIMBS)) { U256 s; u256_sub(s, r, P_LIMBS); r = s; }
+    U256 r, d;
+    const uint32_t c = u256_add(r, a, b);
+    const uint32_t bw = u256_sub(d, r, P_LIMBS);
+    const uint32_t take = (c | (bw ^ 1u)) ? 0xFFFFFFFFu : 0u;           // carry out, or r >= p
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = (d.v[i] & take) | (r.v[i] & ~take);
     return r;
 }
 __device__ __forceinline__ U256 fe_sub(const U256& a, const U256& b) {
-    U256 r; uint32_t bw = u256_sub(r, a, b.v);
-    if (bw) { U256 p = u256_load(P_LIMBS); U256 s; u256_add(s, r, p); r = s; }
+    U256 r;
+    const uint32_t bw = u256_sub(r, a, b.v);
+    const uint32_t m = bw ? 0xFFFFFFFFu : 0u;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)r.v[i] + (P_LIMBS[i] & m); r.v[i] = (uint32_t)c; c >>= 32; }
     return r;
 }
-__device__ __forceinline__ U256 fe_neg(const U256& a) { return u256_is_zero(a) ? a : fe_sub(u256_zero(), a); }
+__device__ __forceinline__ U256 fe_neg(const U256& a) { return fe_sub(u256_zero(), a); }      // 0 - 0 = 0: no special case
 __device__ __forceinline__ U256 fe_dbl(const U256& a) { return fe_add(a, a); }
-// a^(p-2)
+__device__ __forceinline__ U256 fe_sqr_n(U256 x, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) x = fe_sqr(x);
+    return x;
+}
+// a^(p-2) through a fixed addition chain: p - 2 has runs of 223, 22, 1, 2 and 1 ones — 255 squarings and 15 multiplications
+// (plain square-and-multiply costs ~250 multiplications because almost every bit of p - 2 is set)
 static __device__ __noinline__ U256 fe_inv(const U256& a) {
-    // p - 2 = 2^256 - 2^32 - 979: plain square-and-multiply over its bits (MSB first)
-    U256 r = u256_one();
-    for (int i = 255; i >= 0; i--) {
-        r = fe_sqr(r);
-        uint32_t limb = P_LIMBS[i >> 5];
-        if (i < 32) limb = 0xFFFFFC2Du;           // low limb of p-2
-        if ((limb >> (i & 31)) & 1u) r = fe_mul(r, a);
-    }
-    return r;
+    const U256 x2 = fe_mul(fe_sqr(a), a);
+    const U256 x3 = fe_mul(fe_sqr(x2), a);
+    const U256 x6 = fe_mul(fe_sqr_n(x3, 3), x3);
+    const U256 x9 = fe_mul(fe_sqr_n(x6, 3), x3);
+    const U256 x11 = fe_mul(fe_sqr_n(x9, 2), x2);
+    const U256 x22 = fe_mul(fe_sqr_n(x11, 11), x11);
+    const U256 x44 = fe_mul(fe_sqr_n(x22, 22), x22);
+    const U256 x88 = fe_mul(fe_sqr_n(x44, 44), x44);
+    const U256 x176 = fe_mul(fe_sqr_n(x88, 88), x88);
+    const U256 x220 = fe_mul(fe_sqr_n(x176, 44), x44);
+    const U256 x223 = fe_mul(fe_sqr_n(x220, 3), x3);
+    U256 t = fe_mul(fe_sqr_n(x223, 23), x22);
+    t = fe_mul(fe_sqr_n(t, 5), a);
+    t = fe_mul(fe_sqr_n(t, 3), x2);
+    return fe_mul(fe_sqr_n(t, 2), a);
 }
 
 // ------------------------------------------------------------------------------- scalars mod q
@@ -256,8 +305,8 @@ __device__ __forceinline__ Jac jac_from_affine(const Affine& a) {
 __device__ __forceinline__ Affine affine_G() { Affine a; a.x = u256_load(GX_LIMBS); a.y = u256_load(GY_LIMBS); a.inf = false; return a; }
 __device__ __forceinline__ Affine affine_H() { Affine a; a.x = u256_load(HX_LIMBS); a.y = u256_load(HY_LIMBS); a.inf = false; return a; }
 
-static __device__ __noinline__ Jac jac_dbl(const Jac& p) {
-    if (jac_is_inf(p) || u256_is_zero(p.y)) return jac_identity();
+// 2P, a = 0 (2M + 5S); the identity and points of order two (none on this curve) come out with z == 0
+__device__ __forceinline__ Jac jac_dbl(const Jac& p) {
     U256 A = fe_sqr(p.x), B = fe_sqr(p.y), C = fe_sqr(B);
     U256 t = fe_add(p.x, B);
     U256 D = fe_dbl(fe_sub(fe_sub(fe_sqr(t), A), C));
@@ -267,11 +316,13 @@ static __device__ __noinline__ Jac jac_dbl(const Jac& p) {
     r.x = fe_sub(F, fe_dbl(D));
     U256 c8 = fe_dbl(fe_dbl(fe_dbl(C)));
     r.y = fe_sub(fe_mul(E, fe_sub(D, r.x)), c8);
-    r.z = fe_dbl(fe_mul(p.y, p.z));
+    r.z = fe_dbl(fe_mul(p.y, p.z));                 // z == 0 stays 0
     return r;
 }
-// general Jacobian + Jacobian, all special cases handled
-static __device__ __noinline__ Jac jac_add(const Jac& p, const Jac& q) {
+// P + P reached through the addition formulas (equal inputs): rare, so it goes through a non-inlined copy of the doubling
+static __device__ __noinline__ Jac jac_dbl_rare(const Jac& p) { return jac_dbl(p); }
+// general Jacobian + Jacobian (12M + 4S), all special cases handled
+__device__ __forceinline__ Jac jac_add(const Jac& p, const Jac& q) {
     if (jac_is_inf(p)) return q;
     if (jac_is_inf(q)) return p;
     U256 z1z1 = fe_sqr(p.z), z2z2 = fe_sqr(q.z);
@@ -279,7 +330,7 @@ static __device__ __noinline__ Jac jac_add(const Jac& p, const Jac& q) {
     U256 s1 = fe_mul(fe_mul(p.y, q.z), z2z2), s2 = fe_mul(fe_mul(q.y, p.z), z1z1);
     U256 h = fe_sub(u2, u1), r = fe_sub(s2, s1);
     if (u256_is_zero(h)) {
-        if (u256_is_zero(r)) return jac_dbl(p);
+        if (u256_is_zero(r)) return jac_dbl_rare(p);
         return jac_identity();
     }
     U256 hh = fe_sqr(h), hhh = fe_mul(hh, h), v = fe_mul(u1, hh);
@@ -289,40 +340,16 @@ static __device__ __noinline__ Jac jac_add(const Jac& p, const Jac& q) {
     o.z = fe_mul(fe_mul(p.z, q.z), h);
     return o;
 }
-__device__ __forceinline__ Jac jac_add_affine(const Jac& p, const Affine& a) { return jac_add(p, jac_from_affine(a)); }
 __device__ __forceinline__ Jac jac_neg(const Jac& p) { Jac r = p; r.y = fe_neg(p.y); return r; }
-static __device__ __noinline__ Affine jac_to_affine(const Jac& p) {
-    Affine a;
-    if (jac_is_inf(p)) { a.inf = true; a.x = u256_zero(); a.y = u256_zero(); return a; }
-    U256 zi = fe_inv(p.z), zi2 = fe_sqr(zi);
-    a.x = fe_mul(p.x, zi2); a.y = fe_mul(p.y, fe_mul(zi2, zi)); a.inf = false;
-    return a;
-}
-// `Point * Scalar`: 4-bit fixed-window, table of 16 Jacobian multiples in local memory
-static __device__ __noinline__ Jac jac_mul(const Jac& base, const U256& k) {
-    Jac tbl[16];
-    tbl[0] = jac_identity();
-    tbl[1] = base;
-    for (int i = 2; i < 16; i++) tbl[i] = (i & 1) ? jac_add(tbl[i - 1], base) : jac_dbl(tbl[i >> 1]);
-    Jac r = jac_identity();
-    for (int w = 63; w >= 0; w--) {
-        if (w != 63) { r = jac_dbl(r); r = jac_dbl(r); r = jac_dbl(r); r = jac_dbl(r); }
-        uint32_t d = (k.v[w >> 3] >> ((w & 7) * 4)) & 15u;
-        if (d) r = jac_add(r, tbl[d]);
-    }
-    return r;
-}
-__device__ __forceinline__ Affine pt_mul(const Affine& p, const U256& k) { return jac_to_affine(jac_mul(jac_from_affine(p), k)); }
-
 // Jacobian + affine (8M + 3S), all special cases handled
-static __device__ __noinline__ Jac jac_madd(const Jac& p, const Affine& a) {
+__device__ __forceinline__ Jac jac_madd(const Jac& p, const Affine& a) {
     if (a.inf) return p;
     if (jac_is_inf(p)) return jac_from_affine(a);
     U256 z1z1 = fe_sqr(p.z);
     U256 u2 = fe_mul(a.x, z1z1), s2 = fe_mul(fe_mul(a.y, p.z), z1z1);
     U256 h = fe_sub(u2, p.x), r = fe_sub(s2, p.y);
     if (u256_is_zero(h)) {
-        if (u256_is_zero(r)) return jac_dbl(p);
+        if (u256_is_zero(r)) return jac_dbl_rare(p);
         return jac_identity();
     }
     U256 hh = fe_sqr(h), hhh = fe_mul(hh, h), v = fe_mul(p.x, hh);
@@ -332,18 +359,141 @@ static __device__ __noinline__ Jac jac_madd(const Jac& p, const Affine& a) {
     o.z = fe_mul(p.z, h);
     return o;
 }
+__device__ __forceinline__ Jac jac_add_affine(const Jac& p, const Affine& a) { return jac_madd(p, a); }
+static __device__ __noinline__ Jac jac_add_noinline(const Jac& p, const Jac& q) { return jac_add(p, q); }
 
-// Fixed-base tables for the two constant points of the protocol (the generator and curv's
-// base_point2): T[b][w][d-1] = d * 16^w * B_b, affine, w < 64, d = 1..15 (123 KB, built once per
-// context by fb_points_build).  k * B_b is then at most 64 mixed additions and no doubling.
-static constexpr int FBP_WINDOWS = 64, FBP_DIGITS = 15;
-static __device__ const uint32_t* g_fb_points = nullptr;      // set per translation unit, see set_fb_points()
+// (X : Y : Z) == (x, y) without an inversion: X == x Z^2 and Y == y Z^3 (4M + 1S).  Verifiers compare the point they computed
+// with the point they were sent this way.
+__device__ __forceinline__ bool jac_eq_affine(const Jac& p, const Affine& a) {
+    if (jac_is_inf(p) || a.inf) return jac_is_inf(p) && a.inf;
+    const U256 zz = fe_sqr(p.z);
+    return u256_eq(p.x, fe_mul(a.x, zz)) && u256_eq(p.y, fe_mul(a.y, fe_mul(zz, p.z)));
+}
+// two Jacobian points equal (cross-multiplied)
+__device__ __forceinline__ bool jac_eq(const Jac& p, const Jac& q) {
+    if (jac_is_inf(p) || jac_is_inf(q)) return jac_is_inf(p) && jac_is_inf(q);
+    const U256 z1 = fe_sqr(p.z), z2 = fe_sqr(q.z);
+    return u256_eq(fe_mul(p.x, z2), fe_mul(q.x, z1)) && u256_eq(fe_mul(p.y, fe_mul(z2, q.z)), fe_mul(q.y, fe_mul(z1, p.z)));
+}
+__device__ __forceinline__ Affine jac_scale(const Jac& p, const U256& zi) {
+    Affine a;
+    const U256 zi2 = fe_sqr(zi);
+    a.x = fe_mul(p.x, zi2); a.y = fe_mul(p.y, fe_mul(zi2, zi)); a.inf = false;
+    return a;
+}
+__device__ __forceinline__ Affine affine_inf() { Affine a; a.inf = true; a.x = u256_zero(); a.y = u256_zero(); return a; }
+static __device__ __noinline__ Affine jac_to_affine(const Jac& p) {
+    if (jac_is_inf(p)) return affine_inf();
+    return jac_scale(p, fe_inv(p.z));
+}
+// two / three points with ONE shared inversion (Montgomery's trick); an identity among them takes the place of z = 1
+static __device__ __noinline__ void jac_to_affine2(Affine& a, Affine& b, const Jac& p, const Jac& q) {
+    const bool ip = jac_is_inf(p), iq = jac_is_inf(q);
+    const U256 zp = ip ? u256_one() : p.z, zq = iq ? u256_one() : q.z;
+    const U256 inv = fe_inv(fe_mul(zp, zq));
+    a = ip ? affine_inf() : jac_scale(p, fe_mul(inv, zq));
+    b = iq ? affine_inf() : jac_scale(q, fe_mul(inv, zp));
+}
+static __device__ __noinline__ void jac_to_affine3(Affine& a, Affine& b, Affine& c, const Jac& p, const Jac& q, const Jac& r) {
+    const bool ip = jac_is_inf(p), iq = jac_is_inf(q), ir = jac_is_inf(r);
+    const U256 zp = ip ? u256_one() : p.z, zq = iq ? u256_one() : q.z, zr = ir ? u256_one() : r.z;
+    const U256 pq = fe_mul(zp, zq);
+    const U256 inv = fe_inv(fe_mul(pq, zr));
+    const U256 inv_pq = fe_mul(inv, zr);                    // (zp zq)^-1
+    a = ip ? affine_inf() : jac_scale(p, fe_mul(inv_pq, zq));
+    b = iq ? affine_inf() : jac_scale(q, fe_mul(inv_pq, zp));
+    c = ir ? affine_inf() : jac_scale(r, fe_mul(inv, pq));
+}
 
-__device__ __forceinline__ Jac jac_mul_fixed(int which, const U256& k) {
+// ---- `Point * Scalar` for an arbitrary point: GLV split + signed fixed windows --------------------------------------------------
+// high 128 bits (limbs 12..15) of a 512-bit product, rounded at bit 383: round(k g / 2^384)
+__device__ __forceinline__ U256 mul_shift384(const U256& k, const uint32_t* g) {
+    uint32_t t[16];
+    mul_256(t, k, u256_load(g));
+    U256 r = u256_zero();
+    uint64_t c = (t[11] >> 31) & 1u;
+    for (int i = 0; i < 4; i++) { c += t[12 + i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    r.v[4] = (uint32_t)c;
+    return r;
+}
+// k = k1 + k2 LAMBDA (mod q) with k1 = s1 * m1, k2 = s2 * m2, m1, m2 < 2^128, s = +-1 (neg1/neg2 set for -1)
+__device__ __forceinline__ void glv_split(const U256& k, U256& m1, bool& neg1, U256& m2, bool& neg2) {
+    const U256 c1 = mul_shift384(k, GLV_G1_LIMBS), c2 = mul_shift384(k, GLV_G2_LIMBS);
+    U256 k2 = sc_add(sc_mul(c1, u256_load(GLV_MINUS_B1_LIMBS)), sc_mul(c2, u256_load(GLV_MINUS_B2_LIMBS)));
+    U256 k1 = sc_add(sc_mul(k2, u256_load(MINUS_LAMBDA_LIMBS)), k);
+    // a value above 2^128 is the negative of a small one
+    neg1 = (k1.v[4] | k1.v[5] | k1.v[6] | k1.v[7]) != 0;
+    neg2 = (k2.v[4] | k2.v[5] | k2.v[6] | k2.v[7]) != 0;
+    m1 = neg1 ? sc_neg(k1) : k1;
+    m2 = neg2 ? sc_neg(k2) : k2;
+}
+// Signed fixed 5-bit windows of a value below 2^129: m = sum d[i] 32^i with d[i] in [-15, 16], i < 27.  FIXED windows, not a
+// sparse (NAF) form: the 32 lanes of a warp run in lock step, so an addition costs the warp its full time whenever ANY lane has a
+// non-zero digit — sparse digits buy nothing under SIMT, regular windows keep every lane doing useful work at every step.
+static constexpr int SW_DIGITS = 27;
+__device__ __forceinline__ void signed_windows5(int8_t* d, const U256& m) {
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < SW_DIGITS; i++) {
+        const int bit = 5 * i, limb = bit >> 5, off = bit & 31;
+        uint32_t v = limb < 5 ? m.v[limb] >> off : 0u;
+        if (off > 27 && limb + 1 < 5) v |= m.v[limb + 1] << (32 - off);
+        v = (v & 31u) + carry;
+        carry = v > 16u ? 1u : 0u;
+        d[i] = (int8_t)((int)v - (int)(carry << 5));
+    }
+}
+// k * base.  One non-inlined unit; doubling and the table addition are inlined once each in the main loop.  GLV: k = k1 + k2 LAMBDA
+// with 128-bit halves, so 130 doublings instead of 256; both halves share the table of 1..16 times the base (the second half
+// through the endomorphism x -> BETA x).
+static __device__ __noinline__ Jac jac_mul(const Jac& base, const U256& k) {
+    const U256 kr = sc_reduce_once(k, 0);
+    if (jac_is_inf(base) || u256_is_zero(kr)) return jac_identity();
+    Jac tbl[16];
+    tbl[0] = base;
+    tbl[1] = jac_dbl_rare(base);
+#pragma unroll 1
+    for (int i = 2; i < 16; i++) tbl[i] = jac_add_noinline(tbl[i - 1], base);
+    U256 m1, m2;
+    bool neg1, neg2;
+    glv_split(kr, m1, neg1, m2, neg2);
+    int8_t d1[SW_DIGITS], d2[SW_DIGITS];
+    signed_windows5(d1, m1);
+    signed_windows5(d2, m2);
+    const U256 beta = u256_load(BETA_LIMBS);
+    Jac r = jac_identity();
+#pragma unroll 1
+    for (int i = SW_DIGITS - 1; i >= 0; i--) {
+        if (i != SW_DIGITS - 1) {
+#pragma unroll 1
+            for (int s = 0; s < 5; s++) r = jac_dbl(r);
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int dg = h ? d2[i] : d1[i];
+            if (dg == 0) continue;
+            Jac t = tbl[(dg > 0 ? dg : -dg) - 1];
+            if (h) t.x = fe_mul(t.x, beta);
+            if ((dg < 0) != (h ? neg2 : neg1)) t.y = fe_neg(t.y);
+            r = jac_add(r, t);
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ Affine pt_mul(const Affine& p, const U256& k) { return jac_to_affine(jac_mul(jac_from_affine(p), k)); }
+
+// ---- fixed-base tables for the two constant points of the protocol (the generator and curv's base_point2) ---------------------
+// T[b][w][d-1] = d * 256^w * B_b, affine, w < 32, d = 1..255 (2 x 32 x 255 x 64 B = 1.04 MB, built once per device by
+// fb_points_build; L2-resident).  k * B_b is then at most 32 mixed additions and no doubling.
+static constexpr int FBP_WINDOWS = 32, FBP_DIGITS = 255;
+static __device__ const uint32_t* g_fb_points = nullptr;      // set per translation unit, see tecdsa_internal_fb_points_set_*
+
+static __device__ __noinline__ Jac jac_mul_fixed(int which, const U256& k) {
     const uint32_t* t = g_fb_points + (size_t)which * FBP_WINDOWS * FBP_DIGITS * 16;
     Jac r = jac_identity();
+#pragma unroll 1
     for (int w = 0; w < FBP_WINDOWS; w++) {
-        uint32_t d = (k.v[w >> 3] >> ((w & 7) * 4)) & 15u;
+        const uint32_t d = (k.v[w >> 2] >> ((w & 3) * 8)) & 255u;
         if (d) {
             Affine a;
             const uint32_t* e = t + ((size_t)w * FBP_DIGITS + (d - 1)) * 16;
@@ -353,27 +503,35 @@ __device__ __forceinline__ Jac jac_mul_fixed(int which, const U256& k) {
     }
     return r;
 }
-// one thread per (base, window)
+// one thread per (base, window): the 255 multiples of 256^w * B, normalised in groups with a shared inversion
 static __global__ void fb_points_build(uint32_t* tables) {
     int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= 2 * FBP_WINDOWS) return;
     const int which = id / FBP_WINDOWS, w = id % FBP_WINDOWS;
     Jac b = jac_from_affine(which ? affine_H() : affine_G());
-    for (int i = 0; i < 4 * w; i++) b = jac_dbl(b);
-    Jac acc = b;
+    for (int i = 0; i < 8 * w; i++) b = jac_dbl(b);
     uint32_t* out = tables + ((size_t)which * FBP_WINDOWS + w) * FBP_DIGITS * 16;
-    for (int d = 1; d <= FBP_DIGITS; d++) {
-        Affine a = jac_to_affine(acc);
-        u256_store(out + (size_t)(d - 1) * 16, a.x); u256_store(out + (size_t)(d - 1) * 16 + 8, a.y);
-        acc = jac_add(acc, b);
+    Jac acc = b;
+    for (int d = 1; d <= FBP_DIGITS; d += 3) {
+        Jac p1 = acc; acc = jac_add_noinline(acc, b);
+        Jac p2 = acc; acc = jac_add_noinline(acc, b);
+        Jac p3 = acc; acc = jac_add_noinline(acc, b);
+        Affine a1, a2, a3;
+        jac_to_affine3(a1, a2, a3, p1, p2, p3);
+        u256_store(out + (size_t)(d - 1) * 16, a1.x); u256_store(out + (size_t)(d - 1) * 16 + 8, a1.y);
+        u256_store(out + (size_t)d * 16, a2.x); u256_store(out + (size_t)d * 16 + 8, a2.y);
+        u256_store(out + (size_t)(d + 1) * 16, a3.x); u256_store(out + (size_t)(d + 1) * 16 + 8, a3.y);
     }
 }
 __device__ __forceinline__ bool affine_eq(const Affine& a, const Affine& b) {
     if (a.inf || b.inf) return a.inf && b.inf;
     return u256_eq(a.x, b.x) && u256_eq(a.y, b.y);
 }
+// y^2 == x^3 + 7 with canonical coordinates (x, y < p): curv's Point deserialisation rejects anything else, and a non-canonical
+// coordinate would also enter transcript hashes as different bytes
 __device__ __forceinline__ bool on_curve(const Affine& a) {
     if (a.inf) return true;
+    if (u256_ge(a.x, P_LIMBS) || u256_ge(a.y, P_LIMBS)) return false;
     U256 seven = u256_zero(); seven.v[0] = 7;
     return u256_eq(fe_sqr(a.y), fe_add(fe_mul(fe_sqr(a.x), a.x), seven));
 }

@@ -759,3 +759,33 @@ def ecdsa_verify(r: int, s: int, y: Point, message: int) -> bool:
     u2 = r * b % Q
     pt = pt_add(pt_mul(G, u1), pt_mul(y, u2))
     return pt is not None and r == pt[0] % Q
+
+
+# --------------------------------------------------------------------------- identifiable abort helpers (gg_2020/blame.rs)
+def paillier_open(dk: DecryptionKey, c: int) -> Tuple[int, int]:
+    """kzen-paillier `Paillier::open(dk, c)` [R] (call site gg_2020/blame.rs:252-256): the plaintext and the randomness r with
+    c = (1 + m n) r^n mod n^2.  r is the unique n-th root of c modulo n: r = (c mod n)^(n^-1 mod phi) mod n."""
+    n = dk.p * dk.q
+    phi = (dk.p - 1) * (dk.q - 1)
+    return paillier_decrypt(dk, c), pow(c % n, pow(n, -1, phi), n)
+
+
+@dataclass
+class ECDDHProof:
+    a1: Point
+    a2: Point
+    z: int
+
+
+def ecddh_prove(x: int, g1: Point, h1: Point, g2: Point, h2: Point, s: int) -> ECDDHProof:
+    """curv `ECDDHProof::prove(&w, &delta)` (sigma_ec_ddh.rs [R]; call site blame.rs:258-271): a1 = s g1, a2 = s g2,
+    e = H(g1, h1, g2, h2, a1, a2), z = s + e x"""
+    a1, a2 = pt_mul(g1, s), pt_mul(g2, s)
+    e = sha256_points_scalar([g1, h1, g2, h2, a1, a2])
+    return ECDDHProof(a1, a2, (s + e * x) % Q)
+
+
+def ecddh_verify(pf: ECDDHProof, g1: Point, h1: Point, g2: Point, h2: Point) -> bool:
+    """curv `ECDDHProof::verify(&delta)` [R] (call site blame.rs:410-413): z g1 == a1 + e h1 and z g2 == a2 + e h2"""
+    e = sha256_points_scalar([g1, h1, g2, h2, pf.a1, pf.a2])
+    return pt_mul(g1, pf.z) == pt_add(pf.a1, pt_mul(h1, e)) and pt_mul(g2, pf.z) == pt_add(pf.a2, pt_mul(h2, e))

@@ -13,7 +13,7 @@
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, int n) { n &= 31; return n ? (lo >> n) | (hi << (32 - n)) : lo; }
 struct Dim3 { unsigned x, y, z; };
 static Dim3 blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, threadIdx = {0, 0, 0};
-#include "gg20_glue.cuh"
+#include "gg20_rounds.cuh"
 using namespace tecdsa;
 
 static uint32_t g_host_fb[2 * secp::FBP_WINDOWS * secp::FBP_DIGITS * 16];
@@ -57,6 +57,29 @@ int h_dlog_verify(const uint32_t* in40) { return dlog_verify(in40) ? 1 : 0; }
 int h_pedersen_verify(const uint32_t* ped64, const uint32_t* com16) { return pedersen_verify(ped64, affine_load(com16)) ? 1 : 0; }
 int h_heg_verify(const uint32_t* heg48, const uint32_t* R16, const uint32_t* D16, const uint32_t* E16) {
     return heg_verify(heg48, affine_load(R16), affine_load(D16), affine_load(E16)) ? 1 : 0;
+}
+void h_fe_inv(uint32_t* out8, const uint32_t* a) { U256 r = secp::fe_inv(u256_load(a)); memcpy(out8, r.v, 32); }
+// GLV split: m1, m2 (8 limbs each, < 2^128) and the two sign flags
+void h_glv_split(uint32_t* m1, uint32_t* m2, int* neg, const uint32_t* k8) {
+    U256 a, b; bool n1, n2;
+    secp::glv_split(u256_load(k8), a, n1, b, n2);
+    memcpy(m1, a.v, 32); memcpy(m2, b.v, 32); neg[0] = n1; neg[1] = n2;
+}
+void h_signed_windows5(signed char* digits, const uint32_t* m8) { secp::signed_windows5((int8_t*)digits, u256_load(m8)); }
+// projective comparison against an affine point after scaling the Jacobian representation by z (a random non-trivial z)
+int h_jac_eq_affine(const uint32_t* p16, const uint32_t* z8, const uint32_t* q16) {
+    Affine P = affine_load(p16), Qp = affine_load(q16);
+    Jac J = jac_from_affine(P);
+    if (!P.inf) { U256 z = u256_load(z8), zz = fe_sqr(z); J.x = fe_mul(J.x, zz); J.y = fe_mul(J.y, fe_mul(zz, z)); J.z = z; }
+    Jac K = jac_from_affine(Qp);
+    return (secp::jac_eq_affine(J, Qp) ? 1 : 0) | (secp::jac_eq(J, K) ? 2 : 0);
+}
+void h_to_affine3(uint32_t* out48, const uint32_t* p16, const uint32_t* q16, const uint32_t* r16, const uint32_t* k8) {
+    // three multiples k*P, k*Q, k*R normalised with one inversion
+    Affine a, b, c;
+    U256 k = u256_load(k8);
+    secp::jac_to_affine3(a, b, c, jac_mul(jac_from_affine(affine_load(p16)), k), jac_mul(jac_from_affine(affine_load(q16)), k), jac_mul(jac_from_affine(affine_load(r16)), k));
+    affine_store(out48, a); affine_store(out48 + 16, b); affine_store(out48 + 32, c);
 }
 void h_mul_add(uint32_t* d, int nd, const uint32_t* a, int na, const uint32_t* b, int nb, const uint32_t* c, int nc) { st::mul_add(d, nd, a, na, b, nb, c, nc); }
 }

@@ -177,3 +177,61 @@ def test_plain_integer_responses(h):
         d = np.zeros(92, np.uint32)
         h.h_mul_add(P(d), 92, P(L(e, 8)), 8, P(L(ro, 72)), 72, P(L(gamma, 88)), 88)
         assert I(d) == e * ro + gamma
+
+
+LAMBDA = 0x5363ad4cc05c30e0a5261c028812645a122e22ea20816678df02967c1b23bd72
+
+
+def test_glv_split_wnaf_and_scalar_mul(h):
+    """round-2 EC layer: GLV split k = k1 + k2*lambda with |k_i| < 2^128 for edge and random scalars, signed fixed 5-bit windows, and
+    the resulting `Point * Scalar` against the oracle's double-and-add (itself pinned to OpenSSL)"""
+    rng = random.Random(0xEC)
+    m1, m2, neg = np.zeros(8, np.uint32), np.zeros(8, np.uint32), (ctypes.c_int * 2)()
+    edge = [1, 2, 3, o.Q - 1, o.Q - 2, LAMBDA, o.Q - LAMBDA, (o.Q + 1) // 2, (o.Q - 1) // 2, 1 << 255, 1 << 128, (1 << 128) - 1, (1 << 127) + 1, 0xFFFFFFFF]
+    for k in edge + [rng.randrange(1, o.Q) for _ in range(3000)]:
+        h.h_glv_split(P(m1), P(m2), neg, P(L(k, 8)))
+        a, b = I(m1), I(m2)
+        assert a < 1 << 128 and b < 1 << 128
+        assert ((-a if neg[0] else a) + (-b if neg[1] else b) * LAMBDA) % o.Q == k
+    digits = (ctypes.c_byte * 27)()
+    for m in [0, 1, 15, 16, 17, 31, 32, (1 << 128) - 1, 1 << 127, 1 << 128, (1 << 129) - 1] + [rng.getrandbits(128) for _ in range(300)]:
+        h.h_signed_windows5(digits, P(L(m, 8)))
+        d = [digits[i] for i in range(27)]
+        assert sum(v << (5 * i) for i, v in enumerate(d)) == m and all(-15 <= v <= 16 for v in d)
+    out = np.zeros(16, np.uint32)
+    pts = [o.G, o.H2, o.pt_mul(o.G, 0xDEADBEEF)]
+    for k in edge + [rng.randrange(1, o.Q) for _ in range(60)]:
+        pt = pts[k % 3]
+        h.h_pt_mul(P(out), P(PT(pt)), P(L(k, 8)))
+        assert UNPT(out) == o.pt_mul(pt, k), hex(k)
+    h.h_pt_mul(P(out), P(PT(o.G)), P(L(0, 8))); assert UNPT(out) is None
+    h.h_pt_mul(P(out), P(PT(o.G)), P(L(o.Q, 8))); assert UNPT(out) is None           # un-reduced scalar = 0
+    h.h_pt_mul(P(out), P(PT(None)), P(L(5, 8))); assert UNPT(out) is None
+
+
+def test_fixed_base_tables_inversion_chain_and_projective_compare(h):
+    rng = random.Random(0xEC2)
+    out = np.zeros(16, np.uint32)
+    for which, base in ((0, o.G), (1, o.H2)):
+        for k in [1, 255, 256, 257, o.Q - 1, 1 << 248, (1 << 256) - 1 - (1 << 255)] + [rng.randrange(1, o.Q) for _ in range(40)]:
+            h.h_mul_fixed(P(out), which, P(L(k % o.Q, 8)))
+            assert UNPT(out) == o.pt_mul(base, k % o.Q)
+    o8 = np.zeros(8, np.uint32)
+    for a in [1, 2, o.P - 1, 977] + [rng.randrange(1, o.P) for _ in range(100)]:
+        h.h_fe_inv(P(o8), P(L(a, 8))); assert I(o8) == pow(a, -1, o.P)
+    A, B = o.pt_mul(o.G, 77), o.pt_mul(o.G, 78)
+    for _ in range(20):
+        z = rng.randrange(2, o.P)
+        assert h.h_jac_eq_affine(P(PT(A)), P(L(z, 8)), P(PT(A))) == 3
+        assert h.h_jac_eq_affine(P(PT(A)), P(L(z, 8)), P(PT(B))) == 0
+        assert h.h_jac_eq_affine(P(PT(A)), P(L(z, 8)), P(PT(o.pt_neg(A)))) == 0
+    assert h.h_jac_eq_affine(P(PT(None)), P(L(1, 8)), P(PT(None))) == 3 and h.h_jac_eq_affine(P(PT(A)), P(L(5, 8)), P(PT(None))) == 0
+    out48 = np.zeros(48, np.uint32)
+    k = rng.randrange(1, o.Q)
+    h.h_to_affine3(P(out48), P(PT(A)), P(PT(None)), P(PT(B)), P(L(k, 8)))
+    assert [UNPT(out48[0:16]), UNPT(out48[16:32]), UNPT(out48[32:48])] == [o.pt_mul(A, k), None, o.pt_mul(B, k)]
+    # lagrange constants for every signer pair of n = 3
+    for own in range(3):
+        for peer in range(3):
+            if own != peer:
+                h.h_lagrange2(P(o8), own, peer); assert I(o8) == o.lagrange_at_zero(own, [own, peer])
