@@ -413,7 +413,14 @@ def main():
     value = total_units * args.steps / (dev_ms * 1e-3)
     e2e_value = total_units * args.steps / (e2e_ms * 1e-3)
     step_ms = dev_ms / args.steps
-    peak_mac, _ = eng.imad_peak()
+    # roofline denominator: the better of the two on-box saturation micro-benchmarks (carry-free IMAD.WIDE.U32, and the
+    # IMAD.WIDE.U32.X carry chains of the Montgomery rows); the architectural ceiling of the pipe (32 wide MACs per clock and SM,
+    # profiles/r02_imad_peak_sass.md) at the sampled SM clock is reported beside it
+    peak_free, _ = eng.imad_peak()
+    peak_chain, _ = eng.imad_peak(chained=True)
+    peak_mac = max(peak_free, peak_chain)
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    pipe_ceiling = sm_count * 32 * (clocks["sm_mhz"] or 0) * 1e6 if clocks else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -422,7 +429,11 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
     roofline = {"bound": "int32-mad", "unit": "TMAC32/s", "peak": peak_mac / 1e12,
-                "peak_source": "on-box IMAD.WIDE.U32 saturation micro-benchmark (tecdsa_imad_peak); MEASURED_PEAKS.json has no integer entry"}
+                "peak_source": "on-box saturation micro-benchmarks (tecdsa_imad_peak / tecdsa_imad_peak_chained), the better of the two; "
+                               "MEASURED_PEAKS.json has no integer entry",
+                "peak_carry_free": peak_free / 1e12, "peak_carry_chained": peak_chain / 1e12,
+                "pipe_ceiling": pipe_ceiling / 1e12 if pipe_ceiling else None,
+                "pipe_ceiling_source": f"{sm_count} SMs x 32 IMAD.WIDE.U32 per clock x sampled SM clock"}
     if dom:
         name, d = dom
         ach = d["mac32"] / (d["ms"] * 1e-3)

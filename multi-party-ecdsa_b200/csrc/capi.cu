@@ -285,26 +285,28 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
 // Both run at full occupancy with few registers; profiles/r02_imad_peak_sass.md holds the SASS of the two loops.
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
     constexpr int NACC = 16;
-    uint64_t acc[NACC];
-    uint32_t a[NACC];
+    uint32_t acc[2 * NACC], a[NACC];                 // accumulator j = the register pair (acc[2j], acc[2j+1])
 #pragma unroll
-    for (int j = 0; j < NACC; j++) { a[j] = (seed + 0x9e3779b9u * (j + 1)) ^ (threadIdx.x * 2654435761u); acc[j] = (uint64_t)seed * (j + 1) + threadIdx.x; }
+    for (int j = 0; j < NACC; j++) { a[j] = (seed + 0x9e3779b9u * (j + 1)) ^ (threadIdx.x * 2654435761u); acc[2 * j] = seed * (j + 1) + threadIdx.x; acc[2 * j + 1] = seed ^ j; }
     uint32_t b = seed ^ 0x85ebca6bu ^ threadIdx.x;
+    // every multiply-accumulate is written as the lo/hi pair the Montgomery rows use (mad.lo.cc / madc.hi on neighbouring array
+    // elements): the accumulator sits on an aligned register pair and the pair fuses into ONE IMAD.WIDE.U32 with accumulate; the
+    // carry-flag dependence inside each pair also keeps ptxas from re-associating two products of one accumulator into two
+    // multiplies and a three-input add (what it does to plain 64-bit mad.wide sequences)
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const uint32_t bu = b + 0x01000193u * (u + 1);               // a fresh multiplier per step
 #pragma unroll
             for (int j = 0; j < NACC; j++)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(bu));
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(acc[2 * j]), "+r"(acc[2 * j + 1]) : "r"(a[j]), "r"(b));
+            b += 0x01000193u;                                            // a fresh multiplier per step
         }
-        b = b * 5u + 1u;
     }
-    uint64_t x = 0;
+    uint32_t x = 0;
 #pragma unroll
-    for (int j = 0; j < NACC; j++) x ^= acc[j];
-    if (x == 0x12345678u) sink[0] = (uint32_t)x;
+    for (int j = 0; j < 2 * NACC; j++) x ^= acc[j];
+    if (x == 0x12345678u) sink[0] = x;
 }
 __global__ void __launch_bounds__(256) imad_chain_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
     constexpr int L = 16;

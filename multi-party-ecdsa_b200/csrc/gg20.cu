@@ -153,8 +153,19 @@ extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_ke
         return tecdsa_fail(TECDSA_E_ARG, "keys_upload: missing table");
     CK(cudaSetDevice(c->device));
     const int rows = (int)k->n_keysets * 3;
+    // every modulus must be odd (Montgomery domain): checked on the host copy BEFORE anything is allocated or launched
+    for (int r = 0; r < rows; r++)
+        if (!(k->paillier_p[(size_t)r * 32] & 1) || !(k->paillier_q[(size_t)r * 32] & 1) || !(k->n_tilde[(size_t)r * 64] & 1))
+            return tecdsa_fail(TECDSA_E_ARG, "keys_upload: even modulus");
     tecdsa_keyset* ks = new tecdsa_keyset();
     ks->n_keysets = (int)k->n_keysets;
+    // from here on every failure releases the partially built key set
+#undef CK
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t _e = (call);                                                                             \
+        if (_e != cudaSuccess) { int _rc = tecdsa_fail(TECDSA_E_CUDA, #call, _e); tecdsa_keys_free(c, ks); return _rc; } \
+    } while (0)
     size_t total = 0;
     size_t offs[KT_COUNT];
     for (int t = 0; t < KT_COUNT; t++) { offs[t] = total; total += (size_t)rows * KEY_SIZE[t]; total = (total + 63) & ~size_t(63); }
@@ -195,13 +206,12 @@ extern "C" int tecdsa_keys_upload(tecdsa_ctx* c, const tecdsa_keys* k, tecdsa_ke
         if (rc) { tecdsa_keys_free(c, ks); return rc; }
     }
     CK(cudaStreamSynchronize(c->stream));
-    // parity bits of the uploaded moduli are validated on the host copy of the inputs only
-    for (int r = 0; r < rows; r++) {
-        if (!(k->paillier_p[(size_t)r * 32] & 1) || !(k->paillier_q[(size_t)r * 32] & 1) || !(k->n_tilde[(size_t)r * 64] & 1)) {
-            cudaFree(ks->mem); cudaFree(ks->fb); cudaFree(ks->nadic); cudaFree(ks->nadic_p); cudaFree(ks->nadic_q); delete ks;
-            return tecdsa_fail(TECDSA_E_ARG, "keys_upload: even modulus");
-        }
-    }
+#undef CK
+#define CK(call)                                                               \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return tecdsa_fail(TECDSA_E_CUDA, #call, _e);   \
+    } while (0)
     *out = ks;
     return 0;
 }
@@ -466,11 +476,16 @@ int tecdsa_internal_offline(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32
     for (int h = 0; h < 2; h++) {
         if (c->child[h]) continue;
         cudaStream_t s = nullptr;
-        CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        int rc = tecdsa_ctx_create(&c->child[h], c->device, s);
-        if (rc) { cudaStreamDestroy(s); return rc; }
-        c->child[h]->owns_stream = true;
-        CK(cudaEventCreateWithFlags(&c->ev_join[h], cudaEventDisableTiming));
+        cudaEvent_t ev = nullptr;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));           // the join event exists before the child context is published
+        cudaError_t se = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { cudaEventDestroy(ev); return tecdsa_fail(TECDSA_E_CUDA, "gg20_offline: stream for a half-batch", se); }
+        tecdsa_ctx* child = nullptr;
+        int rc = tecdsa_ctx_create(&child, c->device, s);
+        if (rc) { cudaStreamDestroy(s); cudaEventDestroy(ev); return rc; }
+        child->owns_stream = true;
+        c->ev_join[h] = ev;
+        c->child[h] = child;
     }
     if (!c->ev_fork) CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     // fork: both halves start after everything already queued on the caller's stream (device-resident inputs)
