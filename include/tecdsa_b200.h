@@ -65,6 +65,9 @@ const char* tecdsa_last_error(void);
 /* Lane-group width (4, 8, 16 or 32 lanes per operand; 32 = one warp per operand) used for
  * `mod_bits`-wide moduli.  0 restores the tuned default. */
 int tecdsa_ctx_set_tpi(tecdsa_ctx* ctx, int mod_bits, int tpi);
+/* Named tuning options (results never depend on them).  "sqr" = 1: tecdsa_modexp_batch squares through the block-partitioned
+ * Montgomery squaring of csrc/sqr.cuh (fewer multiply-accumulates, measured slower on B200: off by default).              */
+int tecdsa_ctx_set_option(tecdsa_ctx* ctx, const char* name, int value);
 /* Device time (ms, CUDA events on the context stream) of the kernels of the last call and
  * how many kernels that call launched. */
 int tecdsa_ctx_last_kernel_ms(tecdsa_ctx* ctx, float* ms, int* launches);

@@ -28,7 +28,7 @@ ST_PDL_VERIFY, ST_PHASE5_BAD_SUM, ST_PHASE6, ST_INVALID_SIG, ST_PROOF, ST_COMMIT
 
 # every symbol include/tecdsa_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "tecdsa_ctx_create", "tecdsa_ctx_destroy", "tecdsa_ctx_sync", "tecdsa_last_error", "tecdsa_ctx_set_tpi",
+    "tecdsa_ctx_create", "tecdsa_ctx_destroy", "tecdsa_ctx_sync", "tecdsa_last_error", "tecdsa_ctx_set_tpi", "tecdsa_ctx_set_option",
     "tecdsa_ctx_last_kernel_ms", "tecdsa_ctx_launch_count", "tecdsa_modexp_batch", "tecdsa_imad_peak", "tecdsa_imad_peak_chained",
     "tecdsa_keys_upload", "tecdsa_keys_free", "tecdsa_keys_table", "tecdsa_gg20_offline_batch", "tecdsa_gg20_debug_field",
     "tecdsa_modmul_batch", "tecdsa_modinv_batch", "tecdsa_secp_mul_batch", "tecdsa_paillier_encrypt_batch", "tecdsa_paillier_mul_batch",
@@ -131,6 +131,10 @@ class Engine:
 
     def set_tpi(self, mod_bits: int, tpi: int):
         self._ck(self.lib.tecdsa_ctx_set_tpi(self._ctx, mod_bits, tpi), "set_tpi")
+
+    def set_option(self, name: str, value: int):
+        self.lib.tecdsa_ctx_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        self._ck(self.lib.tecdsa_ctx_set_option(self._ctx, name.encode(), value), "set_option")
 
     def last_kernel_ms(self):
         ms, n = ctypes.c_float(), ctypes.c_int()

@@ -56,6 +56,7 @@ extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->opt_sqr = default_sqr();
     // the glue kernels call non-inlined EC / hash routines with multi-KB frames
     CK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
     {
@@ -110,6 +111,11 @@ extern "C" int tecdsa_ctx_set_tpi(tecdsa_ctx* c, int mod_bits, int tpi) {
     if (tpi != 0 && tpi != 4 && tpi != 8 && tpi != 16 && tpi != 32) return fail(TECDSA_E_ARG, "set_tpi: tpi must be 0/4/8/16/32");
     c->tpi[slot] = tpi;
     return 0;
+}
+extern "C" int tecdsa_ctx_set_option(tecdsa_ctx* c, const char* name, int value) {
+    if (!c || !name) return fail(TECDSA_E_ARG, "ctx_set_option: null argument");
+    if (strcmp(name, "sqr") == 0) { c->opt_sqr = value != 0; return 0; }
+    return fail(TECDSA_E_ARG, "ctx_set_option: unknown option");
 }
 extern "C" int tecdsa_ctx_last_kernel_ms(tecdsa_ctx* c, float* ms, int* launches) {
     if (!c) return fail(TECDSA_E_ARG, "null ctx");
@@ -173,14 +179,24 @@ extern "C" int tecdsa_ctx_profile_read(tecdsa_ctx* c, tecdsa_launch_info* out, s
 }
 
 // ------------------------------------------------------------------------------------ modexp
+// Squarings of tecdsa_modexp_batch through the block-partitioned mont_sqr (sqr.cuh) instead of mont_mul(a, a): bit-identical,
+// 12.5-19 % fewer multiply-accumulates, but MEASURED SLOWER on B200 (profiles/r02_sqr_ab.md: 2048-bit, 65 536 operands: 263 ms
+// vs 167 ms with 4 lanes, 222 vs 179 ms with 8) — the shuffles and in-lane accumulation that re-balance the triangle across
+// lock-stepped lanes cost more issue slots than the saved IMAD.WIDE pipe time.  Kept selectable (tecdsa_ctx_set_option "sqr",
+// TECDSA_SQR=1) so that the parity test covers it and the measurement can be repeated; off by default.
+static bool default_sqr() {
+    static const bool on = [] { const char* e = getenv("TECDSA_SQR"); return e && atoi(e) != 0; }();
+    return on;
+}
 template <int K, int TPI>
-static cudaError_t launch_modexp(cudaStream_t s, const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
+static cudaError_t launch_modexp(bool sqr, cudaStream_t s, const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
                                  const uint32_t* mod_idx, uint32_t* out, uint8_t* status, uint32_t* table,
                                  int count, int exp_limbs, unsigned long long* work) {
     constexpr int BLOCK = 128;
     constexpr int PER_BLOCK = BLOCK / TPI;
     int grid = (count + PER_BLOCK - 1) / PER_BLOCK;
-    modexp_kernel<K, TPI><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work);
+    if (sqr) modexp_kernel<K, TPI, true><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work);
+    else modexp_kernel<K, TPI, false><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work);
     return cudaGetLastError();
 }
 
@@ -188,10 +204,10 @@ static cudaError_t launch_modexp(cudaStream_t s, const uint32_t* base, const uin
 // 4096-bit 99k/91k/78k for TPI 8/16/32; 1024-bit 2.73M/2.43M/1.79M for TPI 4/8/16
 static int default_tpi(int mod_bits) { return mod_bits == 1024 ? 4 : mod_bits == 2048 ? 4 : 8; }
 
-static cudaError_t dispatch_modexp(int mod_bits, int tpi, cudaStream_t s, const uint32_t* base, const uint32_t* exp,
+static cudaError_t dispatch_modexp(bool sqr, int mod_bits, int tpi, cudaStream_t s, const uint32_t* base, const uint32_t* exp,
                                    const uint32_t* mod, const uint32_t* mod_idx, uint32_t* out, uint8_t* status,
                                    uint32_t* table, int count, int exp_limbs, unsigned long long* work) {
-#define GO(K, T) return launch_modexp<K, T>(s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work)
+#define GO(K, T) return launch_modexp<K, T>(sqr, s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work)
     switch (mod_bits) {
     case 1024: switch (tpi) { case 4: GO(32, 4); case 8: GO(32, 8); case 16: GO(32, 16); default: return cudaErrorInvalidValue; }
     case 2048: switch (tpi) { case 4: GO(64, 4); case 8: GO(64, 8); case 16: GO(64, 16); case 32: GO(64, 32); default: return cudaErrorInvalidValue; }
@@ -258,7 +274,7 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
         }
         if (first) { CK(cudaEventRecord(c->ev0, c->stream)); first = false; }
         c->prof_begin("modexp_kernel");
-        cudaError_t e = dispatch_modexp(mod_bits, tpi, c->stream, kb, ke, km, ki, ko, ks, d_table, (int)m, exp_limbs, c->d_work);
+        cudaError_t e = dispatch_modexp(c->opt_sqr, mod_bits, tpi, c->stream, kb, ke, km, ki, ko, ks, d_table, (int)m, exp_limbs, c->d_work);
         c->prof_end();
         if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? TECDSA_E_UNSUPPORTED : TECDSA_E_CUDA, "modexp launch", e);
         launches++;

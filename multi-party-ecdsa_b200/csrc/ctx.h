@@ -75,6 +75,7 @@ struct tecdsa_ctx {
     int last_launches = 0;
     uint64_t launches = 0;
     int tpi[3] = {0, 0, 0};        // modexp_batch override for 1024, 2048, 4096
+    bool opt_sqr = false;          // modexp_batch: squarings through mont_sqr (sqr.cuh); see tecdsa_ctx_set_option
     int last_U = 0;
     // large gg20 batches run as two half-batches on two private streams (gg20.cu): the tail of one half's persistent
     // launch and its latency-bound glue kernels overlap the other half's job lists

@@ -7,6 +7,7 @@
 // [0, modulus), identical to GMP mpz_powm for odd moduli.
 #pragma once
 #include "bigint.cuh"
+#include "sqr.cuh"
 
 namespace tecdsa {
 
@@ -15,6 +16,7 @@ static constexpr int WINDOW_BITS = 5;
 // Executed-work accounting (tecdsa_ctx_work): every job adds the 32x32+64 multiply-accumulates of the products it ran to a
 // device counter — one atomicAdd per job, counted from the loop trip counts of the kernel itself.
 __host__ __device__ constexpr unsigned long long mac_mont(int K) { return 2ull * K * K + K; }            // one Montgomery product (rows + quotient digits)
+__host__ __device__ constexpr unsigned long long mac_sqr(int K, int TPI) { return (unsigned long long)(TPI / 2 + 1) * (K / TPI) * K + (unsigned long long)K * K + K; }   // mont_sqr (sqr.cuh): blocks + reduction rows
 __host__ __device__ constexpr int setup_products(int K) { int t = 0; for (unsigned v = 32u * K; v > 1; v >>= 1) t++; return t; }   // squarings of mont_setup
 
 // Everything a group needs to exponentiate modulo one modulus.
@@ -74,7 +76,7 @@ __device__ __forceinline__ uint32_t exp_window(const uint32_t* __restrict__ e, i
 
 // acc = base^exp in Montgomery form.  `tbl` is this group's private window table
 // (2^WINDOW_BITS entries of K limbs, operand-major) in global memory.
-template <int TPI, int L>
+template <int TPI, int L, bool SQR>
 __device__ __forceinline__ void mont_pow(uint32_t (&acc)[L], const uint32_t (&base)[L], const uint32_t* __restrict__ e,
                                          int exp_limbs, const MontCtx<L>& c, uint32_t* __restrict__ tbl) {
     constexpr int K = TPI * L;
@@ -101,16 +103,20 @@ __device__ __forceinline__ void mont_pow(uint32_t (&acc)[L], const uint32_t (&ba
         if (s == WINDOW_BITS) {
             load_limbs<TPI, L>(bb, tbl + exp_window(e, exp_limbs, w) * K);
             w--; s = 0;
+            mont_mul<TPI, L>(acc, acc, bb, c.n, c.n0inv);
         } else {
-#pragma unroll
-            for (int j = 0; j < L; j++) bb[j] = acc[j];
             s++;
+            if (SQR) mont_sqr<TPI, L>(acc, acc, c.n, c.n0inv);       // dedicated squaring (sqr.cuh): fewer multiply-accumulates
+            else {
+#pragma unroll
+                for (int j = 0; j < L; j++) bb[j] = acc[j];
+                mont_mul<TPI, L>(acc, acc, bb, c.n, c.n0inv);
+            }
         }
-        mont_mul<TPI, L>(acc, acc, bb, c.n, c.n0inv);
     }
 }
 
-template <int K, int TPI>
+template <int K, int TPI, bool SQR>
 __global__ void __launch_bounds__(128)
 modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ exp, const uint32_t* __restrict__ mod,
               const uint32_t* __restrict__ mod_idx, uint32_t* __restrict__ out, uint8_t* __restrict__ status,
@@ -136,7 +142,7 @@ modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ex
         c.n[0] |= (group_lane<TPI>() == 0) ? 1u : 0u;
     }
     mont_setup<TPI, L>(c);
-    mont_pow<TPI, L>(acc, b, exp + (size_t)idx * exp_limbs, exp_limbs, c,
+    mont_pow<TPI, L, SQR>(acc, b, exp + (size_t)idx * exp_limbs, exp_limbs, c,
                      table + (size_t)slot * (K << WINDOW_BITS));
     mont_to_plain<TPI, L>(acc, c);
     if (live && (n_low & 1u)) {
@@ -144,8 +150,9 @@ modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ex
         if (group_lane<TPI>() == 0 && status) status[idx] = 0;
         if (group_lane<TPI>() == 0 && work) {
             const int nw = (exp_limbs * 32 + WINDOW_BITS - 1) / WINDOW_BITS;
-            const unsigned long long products = setup_products(K) + 1 + ((1 << WINDOW_BITS) - 2) + (unsigned long long)(nw - 1) * (WINDOW_BITS + 1) + 1;
-            atomicAdd(work, products * mac_mont(K));
+            const unsigned long long mults = setup_products(K) + 1 + ((1 << WINDOW_BITS) - 2) + (unsigned long long)(nw - 1) + 1;
+            const unsigned long long sqrs = (unsigned long long)(nw - 1) * WINDOW_BITS;
+            atomicAdd(work, mults * mac_mont(K) + sqrs * (SQR ? mac_sqr(K, TPI) : mac_mont(K)));
         }
     }
 }

@@ -50,16 +50,22 @@ __device__ __forceinline__ void mul(uint32_t* d, const uint32_t* a, int na, cons
         d[i + nb] = (uint32_t)c;
     }
 }
-// d (nd limbs, nd >= na+nb) = a*b + c  (c has nc <= nd limbs); exact, no modulus
+// d (nd limbs, nd >= na+nb) = a*b + c  (c has nc <= nd limbs); exact, no modulus.  The running sum lives in a thread-private
+// buffer (L1-resident local memory) and is written to `d` once: `d` is usually a global arena row, and a read-modify-write of
+// global memory in the inner loop is what made the plain-integer glue kernels slow.
 __device__ __forceinline__ void mul_add(uint32_t* d, int nd, const uint32_t* a, int na, const uint32_t* b, int nb,
                                         const uint32_t* c, int nc) {
-    for (int i = 0; i < nd; i++) d[i] = i < nc ? c[i] : 0;
+    constexpr int CAP = 132;
+    uint32_t t[CAP];
+    uint32_t* w = nd <= CAP ? t : d;
+    for (int i = 0; i < nd; i++) w[i] = i < nc ? c[i] : 0;
     for (int i = 0; i < na; i++) {
         uint64_t cy = 0;
-        uint32_t ai = a[i];
-        for (int j = 0; j < nb; j++) { cy += (uint64_t)ai * b[j] + d[i + j]; d[i + j] = (uint32_t)cy; cy >>= 32; }
-        for (int k = i + nb; cy && k < nd; k++) { cy += d[k]; d[k] = (uint32_t)cy; cy >>= 32; }
+        const uint32_t ai = a[i];
+        for (int j = 0; j < nb; j++) { cy += (uint64_t)ai * b[j] + w[i + j]; w[i + j] = (uint32_t)cy; cy >>= 32; }
+        for (int k = i + nb; cy && k < nd; k++) { cy += w[k]; w[k] = (uint32_t)cy; cy >>= 32; }
     }
+    if (w != d) for (int i = 0; i < nd; i++) d[i] = w[i];
 }
 // low n limbs of a*b (both n limbs)
 __device__ __forceinline__ void mul_low(uint32_t* d, const uint32_t* a, const uint32_t* b, int n) {

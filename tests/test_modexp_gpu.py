@@ -149,3 +149,25 @@ def test_modexp_ten_thousand_random_cases_vs_gmp(engine, pkg, oracle_lib):
         oracle_lib.oracle_modexp_batch(base.ctypes.data_as(ctypes.c_void_p), exp.ctypes.data_as(ctypes.c_void_p), mod.ctypes.data_as(ctypes.c_void_p),
                                        None, want.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(count), k, k, threads)
         assert np.array_equal(out, want), bits
+
+
+def test_block_partitioned_squaring_is_bit_identical(engine, pkg):
+    """csrc/sqr.cuh (opt-in: fewer multiply-accumulates, measured slower on B200): same residues as the mont_mul(a, a) path and
+    as Python integers, for every lane-group width the batch entry point offers, including moduli with leading zero limbs"""
+    rng = random.Random(0x5A5A)
+    try:
+        for bits, tpis in ((2048, (4, 8, 16, 32)), (1024, (4, 8, 16)), (4096, (8, 16, 32))):
+            mods = [rng.getrandbits(bits) | (1 << (bits - 1)) | 1 for _ in range(40)] + [(1 << 700) + 1, 3, (1 << bits) - 1]
+            bases = [rng.getrandbits(bits) % m for m in mods]
+            exps = [rng.getrandbits(600) for _ in mods]
+            want = [pow(b, e, m) for b, e, m in zip(bases, exps, mods)]
+            for tpi in tpis:
+                engine.set_tpi(bits, tpi)
+                for sqr in (1, 0):
+                    engine.set_option("sqr", sqr)
+                    got, st = engine.mod_pow(bases, exps, mods, mod_bits=bits)
+                    assert not st.any() and got == want, (bits, tpi, sqr)
+    finally:
+        engine.set_option("sqr", 0)
+        for bits in (1024, 2048, 4096):
+            engine.set_tpi(bits, 0)
