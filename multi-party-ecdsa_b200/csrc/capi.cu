@@ -43,6 +43,7 @@ struct Bump {
     }
 };
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+static bool default_sqr();
 
 extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
     if (!out) return fail(TECDSA_E_ARG, "ctx_create: null out");
