@@ -189,27 +189,17 @@ static bool default_sqr() {
     static const bool on = [] { const char* e = getenv("TECDSA_SQR"); return e && atoi(e) != 0; }();
     return on;
 }
-// Persistent grid of the modexp kernel: every SM filled to the occupancy the register budget allows, never more blocks than
-// the operands need.  The window tables are per RESIDENT lane group (grid x groups-per-block slots), not per operand.
+// One block per 128/TPI operands, window table per operand.  A persistent variant (grid = 3 blocks x 148 SMs, one table slot per
+// resident lane group, operands walked with the grid stride) was measured and rejected: DRAM traffic fell from 1.42 GB to 0.87 GB
+// per 65 536-operand launch (0.9 % -> 0.5 % of HBM bandwidth, never a limiter) but the launch took 196.8 ms instead of 166.3 ms —
+// the hardware block scheduler back-fills the last partial wave better than a fixed stride does (profiles/r02_modexp_persistent.md).
 template <int K, int TPI>
-static int modexp_grid(bool sqr, int device, size_t count) {
-    constexpr int BLOCK = 128;
-    constexpr int PER_BLOCK = BLOCK / TPI;
-    int per_sm = 0, sms = 0;
-    if (sqr) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, modexp_kernel<K, TPI, true>, BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, modexp_kernel<K, TPI, false>, BLOCK, 0);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (per_sm < 1) per_sm = 1;
-    if (sms < 1) sms = 1;
-    const size_t want = (count + PER_BLOCK - 1) / PER_BLOCK;
-    const size_t full = (size_t)per_sm * sms;
-    return (int)(want < full ? want : full);
-}
-template <int K, int TPI>
-static cudaError_t launch_modexp(bool sqr, int grid, cudaStream_t s, const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
+static cudaError_t launch_modexp(bool sqr, cudaStream_t s, const uint32_t* base, const uint32_t* exp, const uint32_t* mod,
                                  const uint32_t* mod_idx, uint32_t* out, uint8_t* status, uint32_t* table,
                                  int count, int exp_limbs, unsigned long long* work) {
     constexpr int BLOCK = 128;
+    constexpr int PER_BLOCK = BLOCK / TPI;
+    int grid = (count + PER_BLOCK - 1) / PER_BLOCK;
     if (sqr) modexp_kernel<K, TPI, true><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work);
     else modexp_kernel<K, TPI, false><<<grid, BLOCK, 0, s>>>(base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work);
     return cudaGetLastError();
@@ -219,12 +209,10 @@ static cudaError_t launch_modexp(bool sqr, int grid, cudaStream_t s, const uint3
 // 4096-bit 99k/91k/78k for TPI 8/16/32; 1024-bit 2.73M/2.43M/1.79M for TPI 4/8/16
 static int default_tpi(int mod_bits) { return mod_bits == 1024 ? 4 : mod_bits == 2048 ? 4 : 8; }
 
-// grid < 0: only compute the grid for (mod_bits, tpi, count) and return it through *grid_out
-static cudaError_t dispatch_modexp(bool sqr, int mod_bits, int tpi, int device, int* grid_io, cudaStream_t s, const uint32_t* base,
-                                   const uint32_t* exp, const uint32_t* mod, const uint32_t* mod_idx, uint32_t* out, uint8_t* status,
+static cudaError_t dispatch_modexp(bool sqr, int mod_bits, int tpi, cudaStream_t s, const uint32_t* base, const uint32_t* exp,
+                                   const uint32_t* mod, const uint32_t* mod_idx, uint32_t* out, uint8_t* status,
                                    uint32_t* table, int count, int exp_limbs, unsigned long long* work) {
-#define GO(K, T) do { if (*grid_io <= 0) { *grid_io = modexp_grid<K, T>(sqr, device, (size_t)count); return cudaSuccess; } \
-                      return launch_modexp<K, T>(sqr, *grid_io, s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work); } while (0)
+#define GO(K, T) return launch_modexp<K, T>(sqr, s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work)
     switch (mod_bits) {
     case 1024: switch (tpi) { case 4: GO(32, 4); case 8: GO(32, 8); case 16: GO(32, 16); default: return cudaErrorInvalidValue; }
     case 2048: switch (tpi) { case 4: GO(64, 4); case 8: GO(64, 8); case 16: GO(64, 16); case 32: GO(64, 32); default: return cudaErrorInvalidValue; }
@@ -251,14 +239,10 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
     if (!mod_idx) n_mod = count;
     if (n_mod == 0) return fail(TECDSA_E_ARG, "modexp: n_mod == 0");
 
-    const size_t CHUNK = 1 << 17;                                // operands per launch (bounds the host staging buffers)
+    const size_t CHUNK = 1 << 17;                                // operands per launch (bounds the table)
     const size_t chunk = count < CHUNK ? count : CHUNK;
     const size_t per_block = 128 / tpi;
-    int grid = 0;                                                // persistent grid; the tables are per resident lane group
-    if (dispatch_modexp(c->opt_sqr, mod_bits, tpi, c->device, &grid, c->stream, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                        nullptr, (int)chunk, exp_limbs, nullptr) != cudaSuccess || grid <= 0)
-        return fail(TECDSA_E_UNSUPPORTED, "modexp: unsupported lane-group width for this modulus size");
-    const size_t slots = (size_t)grid * per_block;
+    const size_t slots = ((chunk + per_block - 1) / per_block) * per_block;
     const size_t table_words = slots * ((size_t)K << WINDOW_BITS);
     size_t need = al(table_words * 4);
     if (mem == TECDSA_HOST)
@@ -295,8 +279,7 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
         }
         if (first) { CK(cudaEventRecord(c->ev0, c->stream)); first = false; }
         c->prof_begin("modexp_kernel");
-        int g = grid;                                            // a short last chunk still fits the tables of the full grid
-        cudaError_t e = dispatch_modexp(c->opt_sqr, mod_bits, tpi, c->device, &g, c->stream, kb, ke, km, ki, ko, ks, d_table, (int)m, exp_limbs, c->d_work);
+        cudaError_t e = dispatch_modexp(c->opt_sqr, mod_bits, tpi, c->stream, kb, ke, km, ki, ko, ks, d_table, (int)m, exp_limbs, c->d_work);
         c->prof_end();
         if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? TECDSA_E_UNSUPPORTED : TECDSA_E_CUDA, "modexp launch", e);
         launches++;

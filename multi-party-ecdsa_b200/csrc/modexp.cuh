@@ -122,14 +122,7 @@ modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ex
               const uint32_t* __restrict__ mod_idx, uint32_t* __restrict__ out, uint8_t* __restrict__ status,
               uint32_t* __restrict__ table, int count, int exp_limbs, unsigned long long* __restrict__ work) {
     constexpr int L = K / TPI;
-    // persistent: a lane group walks the operand list with the stride of the whole grid and keeps ONE window-table slot for all of
-    // its operands, so the tables of a launch (resident groups x 32 entries) stay L2-sized instead of growing with the batch
-    const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
-    const int stride = (gridDim.x * blockDim.x) / TPI;
-    const int trips = (count + stride - 1) / stride;          // uniform over the grid: the shuffles need converged warps
-    uint32_t* my_table = table + (size_t)gid * (K << WINDOW_BITS);
-    for (int trip = 0; trip < trips; trip++) {
-    const int slot = gid + trip * stride;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
     const bool live = slot < count;
     const int idx = live ? slot : count - 1;
     MontCtx<L> c;
@@ -149,7 +142,8 @@ modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ex
         c.n[0] |= (group_lane<TPI>() == 0) ? 1u : 0u;
     }
     mont_setup<TPI, L>(c);
-    mont_pow<TPI, L, SQR>(acc, b, exp + (size_t)idx * exp_limbs, exp_limbs, c, my_table);
+    mont_pow<TPI, L, SQR>(acc, b, exp + (size_t)idx * exp_limbs, exp_limbs, c,
+                     table + (size_t)slot * (K << WINDOW_BITS));
     mont_to_plain<TPI, L>(acc, c);
     if (live && (n_low & 1u)) {
         store_limbs<TPI, L>(out + (size_t)idx * K, acc);
@@ -160,8 +154,6 @@ modexp_kernel(const uint32_t* __restrict__ base, const uint32_t* __restrict__ ex
             const unsigned long long sqrs = (unsigned long long)(nw - 1) * WINDOW_BITS;
             atomicAdd(work, mults * mac_mont(K) + sqrs * (SQR ? mac_sqr(K, TPI) : mac_mont(K)));
         }
-    }
-    __syncwarp();                            // the next operand's table overwrites this one's
     }
 }
 
