@@ -413,14 +413,16 @@ def main():
     value = total_units * args.steps / (dev_ms * 1e-3)
     e2e_value = total_units * args.steps / (e2e_ms * 1e-3)
     step_ms = dev_ms / args.steps
-    # roofline denominator: the better of the two on-box saturation micro-benchmarks (carry-free IMAD.WIDE.U32, and the
-    # IMAD.WIDE.U32.X carry chains of the Montgomery rows); the architectural ceiling of the pipe (32 wide MACs per clock and SM,
-    # profiles/r02_imad_peak_sass.md) at the sampled SM clock is reported beside it
+    # roofline denominator: the issue ceiling of the FMA-heavy pipe, 32 IMAD.WIDE.U32 per clock and SM (one warp instruction per
+    # 4 cycles and sub-partition; confirmed by ncu: useful MACs x 4 cycles = the pipe-busy share, profiles/r02_ncu_*_summary.md) at the
+    # SM clock sampled during the timed region.  The two on-box saturation micro-benchmarks (carry-free IMAD.WIDE.U32 and the
+    # IMAD.WIDE.U32.X carry chains of the Montgomery rows) reach 78-87 % of it — their loops carry register moves on the same pipe
+    # (profiles/r02_sass_mix.md) — and are reported beside it; the LARGER figure is the denominator so that `frac` is never flattered.
     peak_free, _ = eng.imad_peak()
     peak_chain, _ = eng.imad_peak(chained=True)
-    peak_mac = max(peak_free, peak_chain)
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     pipe_ceiling = sm_count * 32 * (clocks["sm_mhz"] or 0) * 1e6 if clocks else None
+    peak_mac = max(peak_free, peak_chain, pipe_ceiling or 0.0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -429,8 +431,8 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
     roofline = {"bound": "int32-mad", "unit": "TMAC32/s", "peak": peak_mac / 1e12,
-                "peak_source": "on-box saturation micro-benchmarks (tecdsa_imad_peak / tecdsa_imad_peak_chained), the better of the two; "
-                               "MEASURED_PEAKS.json has no integer entry",
+                "peak_source": "max(pipe issue ceiling = SMs x 32 IMAD.WIDE.U32 per clock x sampled SM clock, on-box saturation micro-benchmarks "
+                               "tecdsa_imad_peak / tecdsa_imad_peak_chained); MEASURED_PEAKS.json has no integer entry",
                 "peak_carry_free": peak_free / 1e12, "peak_carry_chained": peak_chain / 1e12,
                 "pipe_ceiling": pipe_ceiling / 1e12 if pipe_ceiling else None,
                 "pipe_ceiling_source": f"{sm_count} SMs x 32 IMAD.WIDE.U32 per clock x sampled SM clock"}
@@ -439,7 +441,15 @@ def main():
         ach = d["mac32"] / (d["ms"] * 1e-3)
         roofline.update({"kernel": name, "achieved": ach / 1e12, "frac": ach / peak_mac, "kernel_ms_per_step": d["ms"], "launches_per_step": d["launches"],
                          "work_per_step_mac32": d["mac32"], "work_source": "counted by the kernel (tecdsa_ctx_work), CUDA events around each launch",
-                         "share_of_step_kernel_time": d["ms"] / sum(x["ms"] for x in prof.values()), "traffic": None})
+                         "share_of_step_kernel_time": d["ms"] / sum(x["ms"] for x in prof.values()),
+                         "frac_of_measured_microbenchmark": ach / max(peak_free, peak_chain), "traffic": None})
+        try:        # dram__bytes_read + dram__bytes_write of this kernel's largest launch, from the committed ncu --set full capture
+            t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if t["kernel"].split("<")[0] == name.split("<")[0]:
+                roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+                roofline["traffic_note"] = "bytes of ONE launch (" + t["launch"] + "), " + t["source"]
+        except Exception:
+            pass
     roofline["whole_step"] = {
         "ms_per_step": step_ms, "executed_mac32_per_unit": macs_per_step / U,
         "achieved_executed": macs_per_step / (step_ms * 1e-3) / 1e12, "frac_executed": macs_per_step / (step_ms * 1e-3) / peak_mac,

@@ -284,6 +284,85 @@ int tecdsa_sha256_bigints_batch(tecdsa_ctx* ctx, const uint32_t* data, const int
  * (gg_2020/party_i.rs:577-580,654-659): blind 8 limbs, commitment 8 limbs.                                           */
 int tecdsa_hash_commitment_batch(tecdsa_ctx* ctx, const uint32_t* points, const uint32_t* blind, uint32_t* com, size_t count, int mem);
 
+/* ---- other protocols on the same primitives -------------------------------------------------
+ * Lindell-2017 two-party ECDSA (src/protocols/two_party_ecdsa/lindell_2017/{party_one,party_two}.rs).  Key generation is a
+ * composition of calls above (DLogProof, hash commitments, NiCorrectKeyProof, PDL-with-slack, CompositeDLogProof):
+ * multi-party-ecdsa_b200/lindell17.py.  Entry points of the signing path, all randomness explicit:
+ * l17_eph_create: `party_one::EphKeyGenFirstMsg::create` (party_one.rs:403-433) when the four commitment buffers are NULL,
+ *   `party_two::EphKeyGenFirstMsg::create_commitments` (party_two.rs:314-371) when given: public_share = k G, c = k base_point2,
+ *   ECDDHProof (a1 16 | a2 16 | z 8, nonce = its sampled s), pk_commitment = commit(compressed public_share; pk_blind),
+ *   zk_pok_commitment = commit(H(a1, a2); zk_pok_blind).  secret_share and nonce must be non-zero mod q (Scalar::random()).
+ * l17_eph_verify: `party_one::EphKeyGenSecondMsg::verify_commitments_and_dlog_proof` (party_one.rs:436-482) with the
+ *   commitment buffers, `party_two::EphKeyGenSecondMsg::verify_and_decommit` (party_two.rs:374-387) without; status
+ *   TECDSA_ST_OK / _COMMITMENT / _PROOF.
+ * l17_partial_sig: `party_two::PartialSig::compute` (party_two.rs:390-424): n [n_keys][64] (key_idx as in paillier_encrypt),
+ *   c_key = encrypted_secret_share [count][128], x2, k2 8 limbs, eph_other_public 16, message 8 (reduced mod q), rho 16
+ *   (< q^2), randomness 64 (the r of `Paillier::encrypt`) -> c3 [count][128] = c_key^v * Enc(rho q + k2^-1 m) mod N^2 as ONE
+ *   job modulo N^2 per element; status _NOT_INVERTIBLE for k2 = 0 (the reference panics), _INVALID_KEY for a bad point.
+ * l17_sign: `party_one::Signature::compute_with_recid` (party_one.rs:519-564; `compute` :486-517 returns the same r, s) under
+ *   the Paillier key row `key_row` of an uploaded key set; status as above.
+ * l17_verify: `party_one::verify` (party_one.rs:567-592): r must equal the UNREDUCED x coordinate of u1 G + u2 Y and s < q - s;
+ *   status TECDSA_ST_OK / _INVALID_SIG.                                                                                      */
+int tecdsa_l17_eph_create_batch(tecdsa_ctx* ctx, const uint32_t* secret_share, const uint32_t* nonce, const uint32_t* pk_blind,
+                                const uint32_t* zk_pok_blind, uint32_t* public_share, uint32_t* c_point, uint32_t* proof,
+                                uint32_t* pk_commitment, uint32_t* zk_pok_commitment, size_t count, int mem);
+int tecdsa_l17_eph_verify_batch(tecdsa_ctx* ctx, const uint32_t* public_share, const uint32_t* c_point, const uint32_t* proof,
+                                const uint32_t* pk_blind, const uint32_t* zk_pok_blind, const uint32_t* pk_commitment,
+                                const uint32_t* zk_pok_commitment, uint8_t* status, size_t count, int mem);
+int tecdsa_l17_partial_sig_batch(tecdsa_ctx* ctx, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* c_key,
+                                 const uint32_t* x2, const uint32_t* k2, const uint32_t* eph_other_public, const uint32_t* message,
+                                 const uint32_t* rho, const uint32_t* randomness, uint32_t* c3, uint8_t* status, size_t count, int mem);
+int tecdsa_l17_sign_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* key_row, const uint32_t* c3, const uint32_t* k1,
+                          const uint32_t* eph_other_public, uint32_t* sig_r, uint32_t* sig_s, uint8_t* recid, uint8_t* status,
+                          size_t count, int mem);
+int tecdsa_l17_verify_batch(tecdsa_ctx* ctx, const uint32_t* sig_r, const uint32_t* sig_s, const uint32_t* pubkey, const uint32_t* message,
+                            uint8_t* status, size_t count, int mem);
+/* The interactive PDL proof of src/utilities/zk_pdl/mod.rs WITHOUT its `RangeProofNi` (zk-paillier, out of tree, not restated):
+ * verifier_message1 (:111-148): a 8 limbs (< q), b 16 (< q^2), randomness 64 (of `Paillier::encrypt(b)`), blindness 8 ->
+ *   c_tag [128] = c^a * Enc(b) mod N^2 (one job), c_tag_tag [8] = commit(a + (b << bit_length(a)); blindness), q_tag = a Q + b G;
+ * prover_message1 (:191-215): alpha [64] = Dec(c_tag) under key row `key_row`, q_hat = (alpha mod q) G, c_hat = commit(compressed
+ *   q_hat; blindness);  prover_message2 (:217-243): status _OK iff a x1 + b == alpha over the integers and c_tag_tag reopens,
+ *   else _PDL_VERIFY;  verifier_finalize (:170-187): c_hat reopens and q_hat == q_tag, else _PDL_VERIFY.                        */
+int tecdsa_zkpdl_verifier_message1_batch(tecdsa_ctx* ctx, const uint32_t* n, const uint32_t* key_idx, size_t n_keys, const uint32_t* ciphertext,
+                                         const uint32_t* Q, const uint32_t* a, const uint32_t* b, const uint32_t* randomness,
+                                         const uint32_t* blindness, uint32_t* c_tag, uint32_t* c_tag_tag, uint32_t* q_tag, uint8_t* status,
+                                         size_t count, int mem);
+int tecdsa_zkpdl_prover_message1_batch(tecdsa_ctx* ctx, const tecdsa_keyset* ks, const uint32_t* key_row, const uint32_t* c_tag,
+                                       const uint32_t* blindness, uint32_t* c_hat, uint32_t* q_hat, uint32_t* alpha, uint8_t* status,
+                                       size_t count, int mem);
+int tecdsa_zkpdl_prover_message2_batch(tecdsa_ctx* ctx, const uint32_t* x1, const uint32_t* alpha, const uint32_t* c_tag_tag, const uint32_t* a,
+                                       const uint32_t* b, const uint32_t* blindness, uint8_t* status, size_t count, int mem);
+int tecdsa_zkpdl_verifier_finalize_batch(tecdsa_ctx* ctx, const uint32_t* c_hat, const uint32_t* q_hat, const uint32_t* blindness,
+                                         const uint32_t* q_tag, uint8_t* status, size_t count, int mem);
+/* GG18 signing, the phases GG20 replaced (src/protocols/multi_party_ecdsa/gg_2018/party_i.rs:455-730); phases 1-3 are the MtA
+ * calls above with n_st = 0 plus scalar sums.  A batch is `sessions` signing sessions of `parties` signers; element
+ * u = session * parties + party, every array element-major, "the other signers" = the other elements of the session.
+ * phase4 (:455-485): b_proof_pk [count][parties][16] (entry j = pk of the DLogProof received from signer j; own entry = own
+ *   g^gamma), g_gamma 16, blind 8, com 8 per element -> R = delta_inv * sum g_gamma; status _OK / _INVALID_KEY.
+ * local_sig (:489-511): s_i = m k_i + r sigma_i.
+ * phase5a (:513-558): -> com 8, decom = V 16 | A 16 | B 16, HomoELGamalProof (T 16 | A3 16 | z1 8 | z2 8) for the statement
+ *   (G = A, H = R, Y = generator, D = V, E = B), DLogProof of rho (40 limbs); every scalar input non-zero mod q.
+ * phase5c (:560-629): checks the OTHER signers' phase-5a messages (commitment, ElGamal proof, DLog proof) -> com2 8,
+ *   decom2 = u_i 16 | t_i 16; status _OK / _COMMITMENT (Err(InvalidCom)) / _INVALID_SIG (identity point in a transcript).
+ * phase5d (:631-665) over all signers' second messages: status _OK / _COMMITMENT / _INVALID_KEY.
+ * output_signature (:666-703) + `verify` (:706-730): every element derives (r, s, recid) of its session; _OK / _INVALID_SIG.      */
+int tecdsa_gg18_phase4_batch(tecdsa_ctx* ctx, int parties, const uint32_t* delta_inv, const uint32_t* b_proof_pk, const uint32_t* g_gamma,
+                             const uint32_t* blind, const uint32_t* com, uint32_t* R, uint8_t* status, size_t sessions, int mem);
+int tecdsa_gg18_local_sig_batch(tecdsa_ctx* ctx, const uint32_t* message, const uint32_t* R, const uint32_t* k_i, const uint32_t* sigma_i,
+                                uint32_t* s_i, size_t count, int mem);
+int tecdsa_gg18_phase5a_batch(tecdsa_ctx* ctx, const uint32_t* R, const uint32_t* s_i, const uint32_t* l_i, const uint32_t* rho_i,
+                              const uint32_t* blind, const uint32_t* heg_s1, const uint32_t* heg_s2, const uint32_t* dlog_nonce,
+                              uint32_t* com, uint32_t* decom, uint32_t* heg_proof, uint32_t* dlog_proof, uint8_t* status, size_t count, int mem);
+int tecdsa_gg18_phase5c_batch(tecdsa_ctx* ctx, int parties, const uint32_t* R, const uint32_t* y, const uint32_t* message, const uint32_t* rho_i,
+                              const uint32_t* l_i, const uint32_t* blind2, const uint32_t* com, const uint32_t* decom, const uint32_t* blind,
+                              const uint32_t* heg_proof, const uint32_t* dlog_proof, uint32_t* com2, uint32_t* decom2, uint8_t* status,
+                              size_t sessions, int mem);
+int tecdsa_gg18_phase5d_batch(tecdsa_ctx* ctx, int parties, const uint32_t* decom2, const uint32_t* blind2, const uint32_t* com2,
+                              const uint32_t* decom, uint8_t* status, size_t sessions, int mem);
+int tecdsa_gg18_output_signature_batch(tecdsa_ctx* ctx, int parties, const uint32_t* R, const uint32_t* y, const uint32_t* message,
+                                       const uint32_t* s_i, uint32_t* sig_r, uint32_t* sig_s, uint8_t* recid, uint8_t* status,
+                                       size_t sessions, int mem);
+
 /* ---- L3: the batched GG20 offline-signing stage ----------------------------------------
  * One "unit" = one party's OfflineStage Round0..Round6
  *   (src/protocols/multi_party_ecdsa/gg_2020/state_machine/sign/rounds.rs:68-636,

@@ -20,7 +20,8 @@ from typing import Iterable, List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtecdsa_b200.so")
+# TECDSA_B200_LIB names another build of the same library (A/B measurements of kernel variants, tools/gpu_variants.sh)
+LIB_PATH = os.environ.get("TECDSA_B200_LIB") or os.path.join(_HERE, "libtecdsa_b200.so")
 
 HOST, DEVICE = 0, 1
 ST_OK, ST_EVEN_MODULUS, ST_INVALID_KEY, ST_RANGE, ST_NOT_INVERTIBLE, ST_HASH_MISMATCH = 0, 1, 2, 3, 4, 5
@@ -45,6 +46,11 @@ EXPORTS = [
     "tecdsa_wide_muladd_batch", "tecdsa_unit_mod_check_batch", "tecdsa_sha256_batch",
     "tecdsa_paillier_open_batch", "tecdsa_ecddh_prove_batch", "tecdsa_ecddh_verify_batch",
     "tecdsa_correct_key_prove_batch", "tecdsa_composite_dlog_prove_batch", "tecdsa_vss_share_batch", "tecdsa_h1_h2_n_tilde_batch",
+    "tecdsa_l17_eph_create_batch", "tecdsa_l17_eph_verify_batch", "tecdsa_l17_partial_sig_batch", "tecdsa_l17_sign_batch", "tecdsa_l17_verify_batch",
+    "tecdsa_zkpdl_verifier_message1_batch", "tecdsa_zkpdl_prover_message1_batch", "tecdsa_zkpdl_prover_message2_batch",
+    "tecdsa_zkpdl_verifier_finalize_batch",
+    "tecdsa_gg18_phase4_batch", "tecdsa_gg18_local_sig_batch", "tecdsa_gg18_phase5a_batch", "tecdsa_gg18_phase5c_batch", "tecdsa_gg18_phase5d_batch",
+    "tecdsa_gg18_output_signature_batch",
 ]
 
 

@@ -68,6 +68,8 @@ extern "C" int tecdsa_ctx_create(tecdsa_ctx** out, int device, void* stream) {
         if (rc == 0) rc = tecdsa_internal_fb_points_set_records(fbp);
         if (rc == 0) rc = tecdsa_internal_fb_points_set_ecops(fbp);
         if (rc == 0) rc = tecdsa_internal_fb_points_set_blame(fbp);
+        if (rc == 0) rc = tecdsa_internal_fb_points_set_lindell17(fbp);
+        if (rc == 0) rc = tecdsa_internal_fb_points_set_gg18(fbp);
         if (rc) { delete c; return rc; }
     }
     CK(cudaEventCreate(&c->ev0));

@@ -34,6 +34,8 @@ int tecdsa_internal_fb_points_set_keygen(const uint32_t* table);                
 int tecdsa_internal_fb_points_set_records(const uint32_t* table);                                    // records.cu
 int tecdsa_internal_fb_points_set_ecops(const uint32_t* table);                                      // ecops.cu
 int tecdsa_internal_fb_points_set_blame(const uint32_t* table);                                      // blame.cu
+int tecdsa_internal_fb_points_set_lindell17(const uint32_t* table);                                  // lindell17.cu
+int tecdsa_internal_fb_points_set_gg18(const uint32_t* table);                                       // gg18.cu
 
 // the offline stage with a HOST copy of the session descriptors; rnd / outputs live where `mem` says (gg20.cu)
 int tecdsa_internal_offline(tecdsa_ctx* c, const tecdsa_keyset* ks, const uint32_t* h_sessions, size_t n_sessions, const uint32_t* rnd,

@@ -106,6 +106,17 @@ __device__ __forceinline__ void hash_commit_point(uint32_t* out8, const Affine& 
     h.finish(out8);
 }
 
+// commit(Sha256::new().chain_points(pts).result_bigint(); blind): the inner digest re-enters as a minimal-length BigInt
+static __device__ __noinline__ void commit_points(uint32_t* out8, const Affine* pts, int n, const uint32_t* blind8) {
+    Sha256 h; h.init();
+    for (int i = 0; i < n; i++) put_point_uncompressed(h, pts[i]);
+    uint32_t d[8];
+    h.finish(d);
+    Sha256 g; g.init();
+    g.put_bigint(d, 8);
+    g.put_bigint(blind8, 8);
+    g.finish(out8);
+}
 // e = H(N | N+1 | c | z | u | w); s1 = e*a + alpha; s2 = e*ro + gamma (range_proofs.rs:174-182,87-88)
 static __device__ __noinline__ void alice_hash(uint32_t* e8, const uint32_t* N, const uint32_t* c, const uint32_t* z,
                                         const uint32_t* uu, const uint32_t* w) {

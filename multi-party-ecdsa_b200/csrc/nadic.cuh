@@ -19,6 +19,15 @@
 #pragma once
 #include "jobs.cuh"
 
+// The row loop of a pass walks the TPI lanes of a group; its body (L rows) ends with the accumulator pairs rotated, which costs
+// 2 L + 1 register moves per trip on the FMA-heavy pipe (ptxas emits IMAD.MOV; 7 % of the executed instructions,
+// profiles/r02_ncu_nadic_summary.md).  Unrolling two lanes per trip halves the moves but MEASURED no faster on B200 (1190 vs
+// 1190 ms per 8192-session batch), four lanes 6 % slower (instruction cache): profiles/r02_nadic_unroll_ab.md.  Default 1.
+#ifndef NADIC_GROUP_UNROLL
+#define NADIC_GROUP_UNROLL 1
+#endif
+constexpr int kNadicGroupUnroll = NADIC_GROUP_UNROLL;
+
 namespace tecdsa {
 
 template <int L> struct Dig { uint32_t d0[L], d1[L]; };
@@ -79,7 +88,7 @@ __device__ __forceinline__ uint32_t nadic_pass(uint32_t (&T)[L], uint32_t (&E)[L
                                                uint32_t n0inv, uint32_t (&m)[L]) {
     const int gl = group_lane<TPI>();
     uint32_t inc = 0;
-#pragma unroll 1
+#pragma unroll kNadicGroupUnroll
     for (int gi = 0; gi < TPI; gi++) {
         const bool rec = gi == gl;
 #pragma unroll

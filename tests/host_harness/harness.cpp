@@ -11,10 +11,20 @@
 #define __constant__
 #define __global__
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, int n) { n &= 31; return n ? (lo >> n) | (hi << (32 - n)) : lo; }
+static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 struct Dim3 { unsigned x, y, z; };
 static Dim3 blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, threadIdx = {0, 0, 0};
 #include "gg20_rounds.cuh"
+#include "lindell17_kernels.cuh"
+#include "gg18_kernels.cuh"
 using namespace tecdsa;
+
+// run a one-thread-per-element kernel for elements 0..count-1
+template <class F> static void each_thread(int count, F f) {
+    blockIdx.x = 0; blockDim.x = (unsigned)count;
+    for (int t = 0; t < count; t++) { threadIdx.x = (unsigned)t; f(); }
+    threadIdx.x = 0; blockDim.x = 1;
+}
 
 static uint32_t g_host_fb[2 * secp::FBP_WINDOWS * secp::FBP_DIGITS * 16];
 extern "C" {
@@ -82,4 +92,43 @@ void h_to_affine3(uint32_t* out48, const uint32_t* p16, const uint32_t* q16, con
     affine_store(out48, a); affine_store(out48 + 16, b); affine_store(out48 + 32, c);
 }
 void h_mul_add(uint32_t* d, int nd, const uint32_t* a, int na, const uint32_t* b, int nb, const uint32_t* c, int nc) { st::mul_add(d, nd, a, na, b, nb, c, nc); }
+
+// ---- Lindell-2017 / zk_pdl / GG18 per-element kernels (csrc/lindell17_kernels.cuh, gg18_kernels.cuh) ----------------------------
+typedef const uint32_t* CU;
+typedef uint32_t* MU;
+void h_l17_p2_pre(CU n_tab, CU key_idx, CU x2, CU k2, CU R1, CU msg, CU rho16, MU v8, MU lin128, uint8_t* st, int count) {
+    each_thread(count, [&] { l17::k_l17_p2_pre(n_tab, key_idx, x2, k2, R1, msg, rho16, v8, lin128, st, count); });
+}
+void h_l17_p1_post(CU s_tag64, CU k1, CU R2, MU r, MU s, uint8_t* recid, uint8_t* st, int count) {
+    each_thread(count, [&] { l17::k_l17_p1_post(s_tag64, k1, R2, r, s, recid, st, count); });
+}
+void h_l17_verify(CU r, CU s, CU pub, CU msg, uint8_t* st, int count) { each_thread(count, [&] { l17::k_l17_verify(r, s, pub, msg, st, count); }); }
+void h_l17_eph_create(CU k, CU nonce, CU b1, CU b2, MU pub, MU c, MU proof, MU com1, MU com2, int count) {
+    each_thread(count, [&] { l17::k_l17_eph_create(k, nonce, b1, b2, pub, c, proof, com1, com2, count); });
+}
+void h_l17_eph_verify(CU pub, CU c, CU proof, CU b1, CU b2, CU com1, CU com2, uint8_t* st, int count) {
+    each_thread(count, [&] { l17::k_l17_eph_verify(pub, c, proof, b1, b2, com1, com2, st, count); });
+}
+void h_zkpdl_v1_pre(CU n_tab, CU key_idx, CU Q, CU a, CU b, CU blind, MU lin, MU ctt, MU qtag, uint8_t* st, int count) {
+    each_thread(count, [&] { l17::k_zkpdl_v1_pre(n_tab, key_idx, Q, a, b, blind, lin, ctt, qtag, st, count); });
+}
+void h_zkpdl_p1_post(CU alpha, CU blind, MU chat, MU qhat, uint8_t* st, int count) { each_thread(count, [&] { l17::k_zkpdl_p1_post(alpha, blind, chat, qhat, st, count); }); }
+void h_zkpdl_p2(CU x1, CU alpha, CU ctt, CU a, CU b, CU blind, uint8_t* st, int count) { each_thread(count, [&] { l17::k_zkpdl_p2(x1, alpha, ctt, a, b, blind, st, count); }); }
+void h_zkpdl_finalize(CU chat, CU qhat, CU blind, CU qtag, uint8_t* st, int count) { each_thread(count, [&] { l17::k_zkpdl_finalize(chat, qhat, blind, qtag, st, count); }); }
+void h_gg18_phase4(int parties, CU dinv, CU pk, CU gg, CU blind, CU com, MU R, uint8_t* st, int count) {
+    each_thread(count, [&] { gg18::k_gg18_phase4(parties, dinv, pk, gg, blind, com, R, st, count); });
+}
+void h_gg18_phase5a(CU R, CU s, CU l, CU rho, CU blind, CU hs1, CU hs2, CU dn, MU com, MU vab, MU heg, MU dlog, uint8_t* st, int count) {
+    each_thread(count, [&] { gg18::k_gg18_phase5a(R, s, l, rho, blind, hs1, hs2, dn, com, vab, heg, dlog, st, count); });
+}
+void h_gg18_phase5c(int parties, CU R, CU y, CU msg, CU rho, CU l, CU blind2, CU com, CU vab, CU blind1, CU heg, CU dlog, MU com2, MU ut, uint8_t* st, int count) {
+    each_thread(count, [&] { gg18::k_gg18_phase5c(parties, R, y, msg, rho, l, blind2, com, vab, blind1, heg, dlog, com2, ut, st, count); });
+}
+void h_gg18_phase5d(int parties, CU ut, CU blind2, CU com2, CU vab, uint8_t* st, int count) {
+    each_thread(count, [&] { gg18::k_gg18_phase5d(parties, ut, blind2, com2, vab, st, count); });
+}
+void h_gg18_local_sig(CU msg, CU R, CU k, CU sigma, MU s, int count) { each_thread(count, [&] { gg18::k_gg18_local_sig(msg, R, k, sigma, s, count); }); }
+void h_gg18_output(int parties, CU R, CU y, CU msg, CU s, MU sr, MU ss, uint8_t* recid, uint8_t* st, int count) {
+    each_thread(count, [&] { gg18::k_gg18_output(parties, R, y, msg, s, sr, ss, recid, st, count); });
+}
 }

@@ -5,9 +5,7 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-python tools/prof_modexp.py 2048 4 65536 3 2>&1 | tail -3 > $O/r02_modexp_reverted.log
-cat $O/r02_modexp_reverted.log
-TECDSA_SPLIT=0 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:nadic_jobs_kernel<64' -s 8 -c 1 \
+TECDSA_SPLIT=0 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:nadic_jobs_kernel<.int.64' -s 8 -c 1 \
     -o $O/r02_nadic64 -f python tools/offline_throughput.py 4096 > $O/r02_ncu_nadic64.log 2>&1
 tail -3 $O/r02_ncu_nadic64.log
 ls -la $O/r02_nadic64.ncu-rep
