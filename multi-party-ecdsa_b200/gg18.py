@@ -101,3 +101,86 @@ def output_signature(eng: Engine, parties: int, R, y, message, s_i):
     eng._ck(eng.lib.tecdsa_gg18_output_signature_batch(eng._ctx, parties, *[_ptr(a) for a in ins], _ptr(r), _ptr(s), _ptr(rec), _ptr(st), count // parties, HOST),
             "gg18_output_signature")
     return limbs_to_ints(r), limbs_to_ints(s), rec, st
+
+
+# ----------------------------------------------------------------------------- whole signing protocol over the batch calls
+def sign_batch(eng: Engine, keys, parties: int, key_rows, w, y, message, rnd):
+    """GG18 signing (gg_2018/test.rs `sign`: phases 1-5 + output_signature) for `sessions` sessions of `parties` signers, element
+    u = session * parties + party, as a sequence of batch calls.  key_rows[u] = the element's Paillier key row in `keys`, w[u] its
+    Lagrange-weighted share w_i = lambda_i x_i, y[u] the public key, message[u] the hashed message; rnd = dict of per-element
+    lists k, gamma, blind (phase-1 commitment), r_a (MessageA randomness), l, rho, blind5, blind5c, heg_s1, heg_s2, dlog_nonce, and
+    per ordered pair (alice u, bob v != u of the same session; pair index u * (parties - 1) + j) lists r_b_gamma, beta_tag_gamma,
+    r_b_w, beta_tag_w, and the four DLogProof nonces nb_gamma, nbt_gamma, nb_w, nbt_w.
+    -> dict(r, s, recid, status) per element; status is the first failing phase's code."""
+    from . import gg20
+    _bind(eng.lib)
+    U = len(key_rows)
+    P1 = parties - 1
+    k, gamma = list(rnd["k"]), list(rnd["gamma"])
+    status = np.zeros(U, np.uint8)
+
+    def first_fail(st, idx=None):
+        for t, code in enumerate(st):
+            u = t if idx is None else idx[t]
+            if code and not status[u]:
+                status[u] = code
+
+    # phase 1: commit to g^gamma, MessageA = Enc_i(k_i) (no range proofs in GG18: MessageA::a(&k_i, &ek, &[]))
+    g_gamma = eng.secp_mul(None, gamma)
+    com = gg20.hash_commitment(eng, g_gamma, rnd["blind"])
+    c_a, _ = gg20.mta_message_a(eng, keys, list(key_rows), [[] for _ in range(U)], k, rnd["r_a"], [[] for _ in range(U)])
+    # phase 2: every ordered pair runs MtA twice (b = gamma_j and b = w_j) under Alice's key
+    alice = [u for u in range(U) for _ in range(P1)]
+    bob = [u // parties * parties + (j if j < u % parties else j + 1) for u in range(U) for j in range(P1)]
+    none = [[] for _ in alice]
+    empty = {f: none for f in ("z", "e", "s", "s1", "s2")}
+    a_rows, a_ca = [key_rows[u] for u in alice], [c_a[u] for u in alice]
+    cb_g, bp_g, btp_g, beta_g, st = gg20.mta_message_b(eng, keys, a_rows, none, [gamma[v] for v in bob], a_ca, empty, rnd["r_b_gamma"], rnd["beta_tag_gamma"],
+                                                        rnd["nb_gamma"], rnd["nbt_gamma"])
+    first_fail(st, bob)
+    cb_w, bp_w, btp_w, beta_w, st = gg20.mta_message_b(eng, keys, a_rows, none, [w[v] for v in bob], a_ca, empty, rnd["r_b_w"], rnd["beta_tag_w"],
+                                                        rnd["nb_w"], rnd["nbt_w"])
+    first_fail(st, bob)
+    alpha_g, _, st = gg20.mta_get_alpha(eng, keys, a_rows, [k[u] for u in alice], cb_g, bp_g, btp_g)
+    first_fail(st, alice)
+    alpha_w, _, st = gg20.mta_get_alpha(eng, keys, a_rows, [k[u] for u in alice], cb_w, bp_w, btp_w)
+    first_fail(st, alice)
+    # delta_i = k_i gamma_i + sum_j alpha_ij + sum_j beta_ji ; sigma_i likewise with w (party_i.rs:427-445)
+    delta = eng.scalar_op("mul", k, gamma)
+    sigma = eng.scalar_op("mul", k, w)
+    for j in range(P1):
+        delta = eng.scalar_op("add", delta, [alpha_g[u * P1 + j] for u in range(U)])
+        sigma = eng.scalar_op("add", sigma, [alpha_w[u * P1 + j] for u in range(U)])
+    as_bob = {v: [] for v in range(U)}
+    for t, v in enumerate(bob):
+        as_bob[v].append(t)
+    for j in range(P1):
+        delta = eng.scalar_op("add", delta, [beta_g[as_bob[v][j]] for v in range(U)])
+        sigma = eng.scalar_op("add", sigma, [beta_w[as_bob[v][j]] for v in range(U)])
+    # phase 3: delta^-1 of the session sum
+    tot = [0] * U
+    for j in range(parties):
+        tot = eng.scalar_op("add", tot, [delta[u // parties * parties + j] for u in range(U)])
+    dinv = eng.scalar_op("inv", tot)
+    for u in range(U):
+        if dinv[u] is None and not status[u]:
+            status[u] = 4
+    dinv = [d or 0 for d in dinv]
+    # phase 4: R; the public key of the MessageB proof element u received from signer v is g^gamma_v as v proved it
+    pk_of = {}
+    for t, (u, v) in enumerate(zip(alice, bob)):
+        pk_of[(u, v)] = unpack_point(limbs_to_ints(bp_g[t:t + 1, :16])[0])
+    pks = [[g_gamma[u] if (u // parties * parties + j) == u else pk_of[(u, u // parties * parties + j)] for j in range(parties)] for u in range(U)]
+    R, st = phase4(eng, parties, dinv, pks, g_gamma, rnd["blind"], com)
+    first_fail(st)
+    Rs = [p if p is not None else (0, 0) for p in R]
+    # phase 5
+    s_i = local_sig(eng, message, Rs, k, sigma)
+    a5 = phase5a(eng, Rs, s_i, rnd["l"], rnd["rho"], rnd["blind5"], rnd["heg_s1"], rnd["heg_s2"], rnd["dlog_nonce"])
+    first_fail(a5["status"])
+    c5 = phase5c(eng, parties, Rs, y, message, rnd["rho"], rnd["l"], rnd["blind5c"], a5["com"], a5["decom"], rnd["blind5"], a5["heg"], a5["dlog"])
+    first_fail(c5["status"])
+    first_fail(phase5d(eng, parties, c5["decom2"], rnd["blind5c"], c5["com2"], a5["decom"]))
+    r, s, rec, st = output_signature(eng, parties, Rs, y, message, s_i)
+    first_fail(st)
+    return {"r": r, "s": s, "recid": rec, "status": status, "R": R, "s_i": s_i}

@@ -509,3 +509,46 @@ def test_gg18_phases_on_gpu_match_oracle(engine, pkg):
             want = e18.phase4(dinv[u], pks[u], [(bl[v], gg[v]) for v in range(s0, s0 + parties)], coms[s0:s0 + parties])
             assert (int(st4[u]) == 0) == (want is not None) and (want is None or R4[u] == want)
         assert int(st4[1]) == pkg.ST_INVALID_KEY and int(st4[0]) == 0
+
+
+@pytest.mark.gpu
+def test_gg18_whole_signing_on_gpu(engine, pkg, keyset):
+    """gg_2018/test.rs `sign` as batch calls: two- and three-signer sessions over the (t=1, n=3) key set, phases 1-5; the signature
+    verifies under OpenSSL and equals k^-1 (m + r x) computed from the opened secrets; a wrong share is caught in phase 5d"""
+    from mpecdsa_b200 import gg18, gg20
+    ks = gg20.KeySets(engine, [keyset])
+    y = keyset[0].y_sum_s
+    rng = random.Random(0x6718)
+    for signers_list in ([[0, 1], [0, 2], [1, 2], [2, 0]], [[0, 1, 2], [2, 1, 0]]):
+        parties = len(signers_list[0])
+        U = parties * len(signers_list)
+        P1 = parties - 1
+        rows = [p for s in signers_list for p in s]
+        w = [o.lagrange_at_zero(p, s) * keyset[p].x_i % Q for s in signers_list for p in s]
+        msg = [m for s in signers_list for m in [rng.getrandbits(256)] * parties]
+        sc = lambda n_: [rng.randrange(1, Q) for _ in range(n_)]
+        nmod = lambda elems: [rng.randrange(1, keyset[rows[u]].dk.p * keyset[rows[u]].dk.q) for u in elems]
+        alice = [u for u in range(U) for _ in range(P1)]
+        rnd = dict(k=sc(U), gamma=sc(U), blind=[rng.getrandbits(256) for _ in range(U)], r_a=nmod(range(U)), l=sc(U), rho=sc(U),
+                   blind5=[rng.getrandbits(256) for _ in range(U)], blind5c=[rng.getrandbits(256) for _ in range(U)], heg_s1=sc(U), heg_s2=sc(U), dlog_nonce=sc(U),
+                   r_b_gamma=nmod(alice), r_b_w=nmod(alice), nb_gamma=sc(U * P1), nbt_gamma=sc(U * P1), nb_w=sc(U * P1), nbt_w=sc(U * P1),
+                   beta_tag_gamma=[rng.randrange(keyset[rows[u]].dk.p * keyset[rows[u]].dk.q >> 1) for u in alice],
+                   beta_tag_w=[rng.randrange(keyset[rows[u]].dk.p * keyset[rows[u]].dk.q >> 1) for u in alice])
+        out = gg18.sign_batch(engine, ks, parties, rows, w, [y] * U, msg, rnd)
+        assert list(out["status"]) == [0] * U
+        x = sum(o.lagrange_at_zero(p, [0, 1]) * keyset[p].x_i for p in (0, 1)) % Q
+        assert o.pt_mul(G, x) == y
+        for si in range(len(signers_list)):
+            u0 = si * parties
+            kk = sum(rnd["k"][u0:u0 + parties]) % Q
+            gam = sum(rnd["gamma"][u0:u0 + parties]) % Q
+            R = o.pt_mul(G, pow(kk, -1, Q))                         # R = (k gamma)^-1 * gamma G
+            assert all(out["R"][u] == R for u in range(u0, u0 + parties)) and gam != 0
+            s = kk * (msg[u0] + (R[0] % Q) * x) % Q
+            s = min(s, Q - s)
+            assert all((out["r"][u], out["s"][u]) == (R[0] % Q, s) for u in range(u0, u0 + parties))
+            assert _ecdsa_ok(out["r"][u0], out["s"][u0], y, msg[u0])
+        bad_w = list(w); bad_w[0] = (bad_w[0] + 1) % Q
+        out = gg18.sign_batch(engine, ks, parties, rows, bad_w, [y] * U, msg, rnd)
+        assert list(out["status"][:parties]) == [pkg.ST_INVALID_KEY] * parties and list(out["status"][parties:]) == [0] * (U - parties)
+    ks.free()
