@@ -223,24 +223,6 @@ def test_offline_stage_detects_corruption(keyset):
     assert res[1].status == o.ST_INVALID_KEY
 
 
-def test_tensor_core_montgomery_study_is_exact():
-    """tools/tc_montgomery_study.py ("next"): a Montgomery product whose two constant-operand
-    products run as u8 x u8 -> s32 digit GEMMs equals Python integer arithmetic, accumulators below 2^24."""
-    import importlib.util, os, random
-    spec = importlib.util.spec_from_file_location("tc_study", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "tc_montgomery_study.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    rng = random.Random(5)
-    bits = 1024
-    n = rng.getrandbits(bits) | 1 | (1 << (bits - 1))
-    a = [rng.randrange(n) for _ in range(4)] + [n - 1]
-    b = [rng.randrange(n) for _ in range(4)] + [n - 1]
-    got, peak = mod.mont_mul_tc(a, b, n, bits)
-    R = 1 << bits
-    assert got == [x * y * pow(R, -1, n) % n for x, y in zip(a, b)]
-    assert peak < 1 << 24
-
-
 def test_c_twin_equals_python_restatement(keyset):
     """oracle/gg20_twin.c (GMP + OpenSSL, the reference's scalar call sequence) and oracle/gg20_oracle.py agree on every output
     of an offline session: two independent implementations of the restatement, one in C over the reference's own bignum
