@@ -552,3 +552,28 @@ def test_gg18_whole_signing_on_gpu(engine, pkg, keyset):
         out = gg18.sign_batch(engine, ks, parties, rows, bad_w, [y] * U, msg, rnd)
         assert list(out["status"][:parties]) == [pkg.ST_INVALID_KEY] * parties and list(out["status"][parties:]) == [0] * (U - parties)
     ks.free()
+
+
+@pytest.mark.gpu
+def test_other_protocol_entry_points_reject_bad_arguments(engine, pkg):
+    """API-level errors never reach a kernel: empty batches return 0, NULL buffers and out-of-range signer counts return TECDSA_E_ARG"""
+    import ctypes
+    from mpecdsa_b200 import gg18, lindell17
+    gg18._bind(engine.lib); lindell17._bind(engine.lib)
+    lib, ctx = engine.lib, engine._ctx
+    z8, z16, z40, z48 = (np.zeros((1, k), np.uint32) for k in (8, 16, 40, 48))
+    st = np.zeros(1, np.uint8)
+    P = lambda a: a.ctypes.data
+    assert lib.tecdsa_l17_verify_batch(ctx, P(z8), P(z8), P(z16), P(z8), P(st), 0, pkg.HOST) == 0
+    assert lib.tecdsa_l17_verify_batch(ctx, None, P(z8), P(z16), P(z8), P(st), 1, pkg.HOST) == -1
+    assert lib.tecdsa_l17_eph_create_batch(ctx, P(z8), P(z8), P(z8), None, P(z16), P(z16), P(z40), None, None, 1, pkg.HOST) == -1     # half of the commitment buffers
+    assert b"come together" in lib.tecdsa_last_error()
+    assert lib.tecdsa_gg18_phase5d_batch(ctx, 1, P(z16), P(z8), P(z8), P(z48), P(st), 1, pkg.HOST) == -1                               # one signer is not a session
+    assert lib.tecdsa_gg18_phase5d_batch(ctx, 65, P(z16), P(z8), P(z8), P(z48), P(st), 1, pkg.HOST) == -1
+    assert lib.tecdsa_gg18_phase5d_batch(ctx, 2, P(z16), P(z8), P(z8), P(z48), P(st), 0, pkg.HOST) == 0
+    assert lib.tecdsa_zkpdl_verifier_finalize_batch(ctx, P(z8), P(z16), P(z8), None, P(st), 1, pkg.HOST) == -1
+    # points that are not on the curve are a per-element status, not an API error
+    bad = np.ones((2, 16), np.uint32)
+    st2 = np.full(2, 255, np.uint8)
+    assert lib.tecdsa_l17_verify_batch(ctx, P(np.ones((2, 8), np.uint32)), P(np.ones((2, 8), np.uint32)), P(bad), P(np.ones((2, 8), np.uint32)), P(st2), 2, pkg.HOST) == 0
+    assert list(st2) == [pkg.ST_INVALID_SIG] * 2
