@@ -298,4 +298,42 @@ pub mod batch {
         check(unsafe { ffi::tecdsa_gg20_offline_records(e.raw(), ks.raw(), ptr::null_mut(), flat.as_ptr(), n, rnd.as_ptr(), rec.as_mut_ptr(), ffi::TECDSA_HOST) })?;
         Ok(rec)
     }
+
+    /// `party_two::PartialSig::compute` for a batch (two_party_ecdsa/lindell_2017/party_two.rs:390-424) with `rho` (< q^2) and the
+    /// randomness of `Paillier::encrypt` explicit: c3 per element, or `None` where the reference would panic (k2 = 0).
+    /// `n[key_idx[i]]` is the Paillier modulus of element i.
+    #[allow(clippy::too_many_arguments)]
+    pub fn l17_partial_sig(e: &Engine, n: &[BigInt], key_idx: &[u32], c_key: &[BigInt], x2: &[Scalar<Secp256k1>], k2: &[Scalar<Secp256k1>],
+                           eph_other_public: &[Point<Secp256k1>], message: &[BigInt], rho: &[BigInt], randomness: &[BigInt]) -> Result<Vec<Option<BigInt>>, EngineError> {
+        let cnt = c_key.len();
+        let pack = |v: &[BigInt], limbs: usize| -> Vec<u32> { v.iter().flat_map(|x| to_limbs(x, limbs)).collect() };
+        let q = Scalar::<Secp256k1>::group_order();
+        let msg: Vec<BigInt> = message.iter().map(|m| m.mod_floor(q)).collect();
+        let (nl, ck, ml, rl, rr) = (pack(n, 64), pack(c_key, 128), pack(&msg, 8), pack(rho, 16), pack(randomness, 64));
+        let x2l: Vec<u32> = x2.iter().flat_map(scalar_to_limbs).collect();
+        let k2l: Vec<u32> = k2.iter().flat_map(scalar_to_limbs).collect();
+        let pl: Vec<u32> = eph_other_public.iter().flat_map(point_to_limbs).collect();
+        let (mut c3, mut st) = (vec![0u32; cnt * 128], vec![255u8; cnt]);
+        check(unsafe {
+            ffi::tecdsa_l17_partial_sig_batch(e.raw(), nl.as_ptr(), key_idx.as_ptr(), n.len(), ck.as_ptr(), x2l.as_ptr(), k2l.as_ptr(), pl.as_ptr(), ml.as_ptr(),
+                                              rl.as_ptr(), rr.as_ptr(), c3.as_mut_ptr(), st.as_mut_ptr(), cnt, ffi::TECDSA_HOST)
+        })?;
+        Ok((0..cnt).map(|i| if st[i] == 0 { Some(from_limbs(&c3[i * 128..(i + 1) * 128])) } else { None }).collect())
+    }
+
+    /// `party_one::Signature::compute_with_recid` for a batch (party_one.rs:519-564) under Paillier key rows of an uploaded key set:
+    /// (r, s, recid) per element, or `None` where the reference would panic (k1 = 0).
+    pub fn l17_sign(e: &Engine, ks: &KeySets, key_row: &[u32], c3: &[BigInt], k1: &[Scalar<Secp256k1>], eph_other_public: &[Point<Secp256k1>])
+                    -> Result<Vec<Option<(BigInt, BigInt, u8)>>, EngineError> {
+        let cnt = c3.len();
+        let cl: Vec<u32> = c3.iter().flat_map(|x| to_limbs(x, 128)).collect();
+        let kl: Vec<u32> = k1.iter().flat_map(scalar_to_limbs).collect();
+        let pl: Vec<u32> = eph_other_public.iter().flat_map(point_to_limbs).collect();
+        let (mut r, mut s, mut rec, mut st) = (vec![0u32; cnt * 8], vec![0u32; cnt * 8], vec![0u8; cnt], vec![255u8; cnt]);
+        check(unsafe {
+            ffi::tecdsa_l17_sign_batch(e.raw(), ks.raw(), key_row.as_ptr(), cl.as_ptr(), kl.as_ptr(), pl.as_ptr(), r.as_mut_ptr(), s.as_mut_ptr(), rec.as_mut_ptr(),
+                                       st.as_mut_ptr(), cnt, ffi::TECDSA_HOST)
+        })?;
+        Ok((0..cnt).map(|i| if st[i] == 0 { Some((from_limbs(&r[i * 8..(i + 1) * 8]), from_limbs(&s[i * 8..(i + 1) * 8]), rec[i])) } else { None }).collect())
+    }
 }
