@@ -77,3 +77,13 @@ def test_gpu_reproduces_vectors(engine, pkg, keyset):
             assert pkg.limbs_to_ints(res.sigma[2 * i + p:2 * i + p + 1])[0] == X(s["sigma"][p])
         assert gg20.unpack_point(pkg.limbs_to_ints(res.R[2 * i:2 * i + 1])[0]) == PT(s["R"])
     ks.free()
+
+
+def test_other_protocol_oracles_match_frozen_vectors():
+    """tests/golden/vectors_other_protocols.json (make_other_vectors.py): the Lindell-2017 / zk_pdl / GG18 / size-generic GG20 oracles on
+    seeded inputs still produce the frozen outputs"""
+    import json, os
+    from tests.golden import make_other_vectors as mk
+    with open(mk.PATH) as f:
+        want = json.load(f)
+    assert mk.compute() == want

@@ -44,5 +44,40 @@ c = eng.paillier_encrypt([k0.dk.p * k0.dk.q], [0], [12345], [987654321])
 print("open", blame.paillier_open(eng, ks, [0], c), flush=True)
 pf = blame.ecddh_prove(eng, [9], [P[0]], eng.secp_mul([P[0]], [9]), [P[1]], eng.secp_mul([P[1]], [9]), [77])
 print("ecddh", blame.ecddh_verify(eng, pf, [P[0]], eng.secp_mul([P[0]], [9]), [P[1]], eng.secp_mul([P[1]], [9])).tolist(), flush=True)
+# ---- section 8(f) rank 4: Lindell-2017, zk_pdl, GG18 (whole signing), and the size-generic GG20 driver on three signers
+from mpecdsa_b200 import gg18, gg20_general, lindell17
+from oracle import gg20_oracle as o
+Q = o.Q
+n0 = k0.dk.p * k0.dk.q
+x1, x2, k1, k2 = 11, 13, 17, 19
+c_key = eng.paillier_encrypt([n0], [0], [x1], [5])
+e1 = lindell17.eph_create(eng, [k1], [23])
+e2 = lindell17.eph_create(eng, [k2], [29], [31], [37])
+print("l17 eph", lindell17.eph_verify(eng, e1["public_share"], e1["c"], e1["proof"]).tolist(),
+      lindell17.eph_verify(eng, e2["public_share"], e2["c"], e2["proof"], [31], [37], e2["pk_commitment"], e2["zk_pok_commitment"]).tolist(), flush=True)
+c3, st = lindell17.p2_partial_sig(eng, [n0], [0], c_key, [x2], [k2], e1["public_share"], [1234], [3 * Q + 1], [7])
+sr, ss, rec, st2 = lindell17.p1_sign(eng, ks, [0], c3, [k1], e2["public_share"])
+print("l17 sign", st.tolist(), st2.tolist(), lindell17.verify(eng, sr, ss, eng.secp_mul(None, [x1 * x2]), [1234]).tolist(), flush=True)
+ct, ctt, qt, st = lindell17.pdl_verifier_message1(eng, [n0], [0], c_key, eng.secp_mul(None, [x1]), [41], [43 * Q + 3], [9], [47])
+ch, qh, al, st2 = lindell17.pdl_prover_message1(eng, ks, [0], ct, [53])
+print("zk_pdl", st.tolist(), st2.tolist(), lindell17.pdl_prover_message2(eng, [x1], al, ctt, [41], [43 * Q + 3], [47]).tolist(),
+      lindell17.pdl_verifier_finalize(eng, ch, qh, [53], qt).tolist(), flush=True)
+rr = random.Random(3)
+parties, rows = 3, [0, 1, 2]
+U, P1 = 3, 2
+w = [o.lagrange_at_zero(p_, rows) * keysets[0][p_].x_i % Q for p_ in rows]
+sc = lambda m_: [rr.randrange(1, Q) for _ in range(m_)]
+nm = lambda elems: [rr.randrange(1, keysets[0][rows[u]].dk.p * keysets[0][rows[u]].dk.q >> 1) for u in elems]
+alice = [u for u in range(U) for _ in range(P1)]
+rnd18 = dict(k=sc(U), gamma=sc(U), blind=sc(U), r_a=nm(range(U)), l=sc(U), rho=sc(U), blind5=sc(U), blind5c=sc(U), heg_s1=sc(U), heg_s2=sc(U), dlog_nonce=sc(U),
+             r_b_gamma=nm(alice), r_b_w=nm(alice), nb_gamma=sc(U * P1), nbt_gamma=sc(U * P1), nb_w=sc(U * P1), nbt_w=sc(U * P1),
+             beta_tag_gamma=nm(alice), beta_tag_w=nm(alice))
+out = gg18.sign_batch(eng, ks, parties, rows, w, [keysets[0][0].y_sum_s] * U, [99] * U, rnd18)
+print("gg18 sign", out["status"].tolist(), flush=True)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import test_gg20_general as tg
+keys3, rnd3 = tg._session(rr, keysets[0], [1, 2, 3])
+args = tg._flatten([(keys3, [1, 2, 3], rnd3)], lambda lk, j: j)
+print("gg20 general", gg20_general.offline_batch(eng, ks, *args)["status"].tolist(), flush=True)
 ks.free(); eng.close()
 print("done", flush=True)
