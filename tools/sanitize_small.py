@@ -1,7 +1,8 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every kernel family of the library at sizes
 that finish under the tool — an offline batch over 8 key sets through the records call, a SPLIT batch (two host threads, two
 streams), the online step, modexp with both squaring paths, modinv, the Scalar/Point surface, keygen prove+verify, Paillier
-open + ECDDH (blame), fixed-base table build, N-adic setup.
+open + ECDDH (blame), Lindell-2017 signing, the interactive PDL proof, GG18 whole signing (three signers), the size-generic GG20 driver
+(three signers), fixed-base table build, N-adic setup.
     compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py [split]
 """
 import os, sys, random
