@@ -469,7 +469,7 @@ int tecdsa_gg20_debug_field(tecdsa_ctx* ctx, const char* name, uint32_t* out_hos
 /* Saturation micro-benchmarks of the integer multiply-add pipe, 32x32+64 MACs per second on this device — the roofline
  * denominators of every kernel of this library.  imad_peak: carry-free IMAD.WIDE.U32 on 16 independent
  * accumulators per thread, every product with its own operand pair; imad_peak_chained: IMAD.WIDE.U32.X in the carry chains of
- * the Montgomery rows (two accumulator sets per thread).  Both at full occupancy; SASS in profiles/r02_imad_peak_sass.md.      */
+ * the Montgomery rows (two accumulator sets per thread).  Both at full occupancy; SASS in profiles/r02_sass_mix.md.            */
 int tecdsa_imad_peak(tecdsa_ctx* ctx, double* mac32_per_s, float* ms);
 int tecdsa_imad_peak_chained(tecdsa_ctx* ctx, double* mac32_per_s, float* ms);
 

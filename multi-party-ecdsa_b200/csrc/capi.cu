@@ -305,7 +305,7 @@ extern "C" int tecdsa_modexp_batch(tecdsa_ctx* c, int mod_bits, int exp_limbs, c
 //    accumulators (the round-1 kernel reused operand pairs and ptxas turned half of its MACs into adds);
 //  * carry-chained: the instruction the Montgomery rows are made of, IMAD.WIDE.U32.X with carry in and out — the mad_even /
 //    mad_odd chains of bigint.cuh on two accumulator sets, exactly as mont_row issues them.
-// Both run at full occupancy with few registers; profiles/r02_imad_peak_sass.md holds the SASS of the two loops.
+// Both run at full occupancy with few registers; profiles/r02_sass_mix.md holds the SASS of the two loops.
 __global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* sink, uint32_t seed, int iters) {
     constexpr int NACC = 16;
     uint32_t acc[2 * NACC], a[NACC];                 // accumulator j = the register pair (acc[2j], acc[2j+1])
