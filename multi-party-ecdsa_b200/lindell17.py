@@ -12,7 +12,7 @@ import numpy as np
 
 from . import HOST, Engine, ints_to_limbs, limbs_to_ints, _ptr
 from . import gg20, keygen
-from .gg20 import KeySets, _pts, unpack_point
+from .gg20 import KeySets, _Screen, _pts, unpack_point
 
 Point = Tuple[int, int]
 
@@ -35,6 +35,18 @@ def _bind(lib):
 
 def _points(a: np.ndarray):
     return [unpack_point(v) for v in limbs_to_ints(a)]
+
+
+def _screen_pts(sc: _Screen, pts):
+    """Untrusted points: a coordinate that does not fit 256 bits (or a missing point) can never deserialise in the reference; it is
+    replaced by the identity encoding and that ONE element is marked rejected after the call (never an OverflowError for the batch)"""
+    out = []
+    for i, p in enumerate(pts):
+        if p is None or p[0] < 0 or p[1] < 0 or p[0] >> 256 or p[1] >> 256:
+            sc.bad[i] = True
+            p = None
+        out.append(p)
+    return _pts(out)
 
 
 # ----------------------------------------------------------------------------- key generation (composition of existing calls)
@@ -97,25 +109,28 @@ def eph_verify(eng: Engine, public_share, c, proof: np.ndarray, pk_blind=None, z
     `party_two::EphKeyGenSecondMsg::verify_and_decommit` (without) -> status"""
     _bind(eng.lib)
     n = len(public_share)
-    opt = [ints_to_limbs(v, 8) if v is not None else None for v in (pk_blind, zk_pok_blind, pk_commitment, zk_pok_commitment)]
-    ins = [_pts(public_share), _pts(c), np.ascontiguousarray(proof, dtype=np.uint32)]
+    sc = _Screen(n)
+    opt = [sc.limbs(v, 8) if v is not None else None for v in (pk_blind, zk_pok_blind, pk_commitment, zk_pok_commitment)]
+    ins = [_screen_pts(sc, public_share), _screen_pts(sc, c), np.ascontiguousarray(proof, dtype=np.uint32)]
     st = np.full(n, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_l17_eph_verify_batch(eng._ctx, *[_ptr(a) for a in ins], *[_ptr(a) for a in opt], _ptr(st), n, HOST), "l17_eph_verify")
-    return st
+    return sc.apply(st, 10)                  # TECDSA_ST_PROOF: the message would not deserialise
 
 
 # ----------------------------------------------------------------------------- signing
 def p2_partial_sig(eng: Engine, n_list, key_idx, c_key, x2, k2, eph_other_public, message, rho, randomness):
-    """`party_two::PartialSig::compute` (party_two.rs:390-424) -> (c3 list, status)"""
+    """`party_two::PartialSig::compute` (party_two.rs:390-424) -> (c3 list, status).  message = the hashed message as an integer below
+    2^256 (reduced mod q on the device); reduce anything wider with Engine.scalar_from_bigint first."""
     _bind(eng.lib)
     cnt = len(c_key)
     N, idx = ints_to_limbs(n_list, 64), np.asarray(key_idx, dtype=np.uint32)
-    ins = [ints_to_limbs(c_key, 128), ints_to_limbs(x2, 8), ints_to_limbs(k2, 8), _pts(eph_other_public), ints_to_limbs(message, 8),
+    sc = _Screen(cnt)
+    ins = [sc.limbs(c_key, 128), ints_to_limbs(x2, 8), ints_to_limbs(k2, 8), _screen_pts(sc, eph_other_public), ints_to_limbs(message, 8),
            ints_to_limbs(rho, 16), ints_to_limbs(randomness, 64)]
     c3, st = np.zeros((cnt, 128), np.uint32), np.full(cnt, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_l17_partial_sig_batch(eng._ctx, _ptr(N), _ptr(idx), len(n_list), *[_ptr(a) for a in ins], _ptr(c3), _ptr(st), cnt, HOST),
             "l17_partial_sig")
-    return limbs_to_ints(c3), st
+    return limbs_to_ints(c3), sc.apply(st, 2)                # TECDSA_ST_INVALID_KEY: party one's material is malformed
 
 
 def p1_sign(eng: Engine, keys: KeySets, key_row, c3, k1, eph_other_public):
@@ -123,21 +138,23 @@ def p1_sign(eng: Engine, keys: KeySets, key_row, c3, k1, eph_other_public):
     _bind(eng.lib)
     cnt = len(c3)
     rows = np.asarray(key_row, dtype=np.uint32)
-    ins = [ints_to_limbs(c3, 128), ints_to_limbs(k1, 8), _pts(eph_other_public)]
+    sc = _Screen(cnt)
+    ins = [sc.limbs(c3, 128), ints_to_limbs(k1, 8), _screen_pts(sc, eph_other_public)]
     r, s = np.zeros((cnt, 8), np.uint32), np.zeros((cnt, 8), np.uint32)
     rec, st = np.zeros(cnt, np.uint8), np.full(cnt, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_l17_sign_batch(eng._ctx, keys.handle, _ptr(rows), *[_ptr(a) for a in ins], _ptr(r), _ptr(s), _ptr(rec), _ptr(st), cnt, HOST), "l17_sign")
-    return limbs_to_ints(r), limbs_to_ints(s), rec, st
+    return limbs_to_ints(r), limbs_to_ints(s), rec, sc.apply(st, 2)
 
 
 def verify(eng: Engine, r, s, pubkey, message) -> np.ndarray:
     """`party_one::verify` (party_one.rs:567-592) -> status (0 accept, 9 InvalidSig)"""
     _bind(eng.lib)
     cnt = len(r)
-    ins = [ints_to_limbs(r, 8), ints_to_limbs(s, 8), _pts(pubkey), ints_to_limbs(message, 8)]
+    sc = _Screen(cnt)
+    ins = [sc.limbs(r, 8), sc.limbs(s, 8), _screen_pts(sc, pubkey), ints_to_limbs(message, 8)]
     st = np.full(cnt, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_l17_verify_batch(eng._ctx, *[_ptr(a) for a in ins], _ptr(st), cnt, HOST), "l17_verify")
-    return st
+    return sc.apply(st, 9)                   # TECDSA_ST_INVALID_SIG: an r or s wider than 256 bits matches no x coordinate / fails s < q - s
 
 
 # ----------------------------------------------------------------------------- interactive PDL proof
@@ -159,29 +176,32 @@ def pdl_prover_message1(eng: Engine, keys: KeySets, key_row, c_tag, blindness):
     _bind(eng.lib)
     cnt = len(c_tag)
     rows = np.asarray(key_row, dtype=np.uint32)
-    ins = [ints_to_limbs(c_tag, 128), ints_to_limbs(blindness, 8)]
+    sc = _Screen(cnt)
+    ins = [sc.limbs(c_tag, 128), ints_to_limbs(blindness, 8)]
     ch, qh, al = np.zeros((cnt, 8), np.uint32), np.zeros((cnt, 16), np.uint32), np.zeros((cnt, 64), np.uint32)
     st = np.full(cnt, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_zkpdl_prover_message1_batch(eng._ctx, keys.handle, _ptr(rows), *[_ptr(x) for x in ins], _ptr(ch), _ptr(qh), _ptr(al), _ptr(st), cnt, HOST),
             "zkpdl_prover_message1")
-    return limbs_to_ints(ch), _points(qh), limbs_to_ints(al), st
+    return limbs_to_ints(ch), _points(qh), limbs_to_ints(al), sc.apply(st, 2)
 
 
 def pdl_prover_message2(eng: Engine, x1, alpha, c_tag_tag, a, b, blindness) -> np.ndarray:
     """`zk_pdl::Prover::message2` (zk_pdl/mod.rs:217-243) -> status (0 = decommit, 6 = ZkPdlError::Message2)"""
     _bind(eng.lib)
     cnt = len(x1)
-    ins = [ints_to_limbs(x1, 8), ints_to_limbs(alpha, 64), ints_to_limbs(c_tag_tag, 8), ints_to_limbs(a, 8), ints_to_limbs(b, 16), ints_to_limbs(blindness, 8)]
+    sc = _Screen(cnt)
+    ins = [ints_to_limbs(x1, 8), ints_to_limbs(alpha, 64), sc.limbs(c_tag_tag, 8), sc.limbs(a, 8), sc.limbs(b, 16), sc.limbs(blindness, 8)]
     st = np.full(cnt, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_zkpdl_prover_message2_batch(eng._ctx, *[_ptr(x) for x in ins], _ptr(st), cnt, HOST), "zkpdl_prover_message2")
-    return st
+    return sc.apply(st, 6)                   # an over-wide decommitment can match neither alpha nor the commitment
 
 
 def pdl_verifier_finalize(eng: Engine, c_hat, q_hat, blindness, q_tag) -> np.ndarray:
     """`zk_pdl::Verifier::finalize` (zk_pdl/mod.rs:170-187) -> status (0 accept, 6 = ZkPdlError::Finalize)"""
     _bind(eng.lib)
     cnt = len(c_hat)
-    ins = [ints_to_limbs(c_hat, 8), _pts(q_hat), ints_to_limbs(blindness, 8), _pts(q_tag)]
+    sc = _Screen(cnt)
+    ins = [sc.limbs(c_hat, 8), _screen_pts(sc, q_hat), sc.limbs(blindness, 8), _pts(q_tag)]
     st = np.full(cnt, 255, np.uint8)
     eng._ck(eng.lib.tecdsa_zkpdl_verifier_finalize_batch(eng._ctx, *[_ptr(x) for x in ins], _ptr(st), cnt, HOST), "zkpdl_verifier_finalize")
-    return st
+    return sc.apply(st, 6)

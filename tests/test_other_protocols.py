@@ -577,3 +577,29 @@ def test_other_protocol_entry_points_reject_bad_arguments(engine, pkg):
     st2 = np.full(2, 255, np.uint8)
     assert lib.tecdsa_l17_verify_batch(ctx, P(np.ones((2, 8), np.uint32)), P(np.ones((2, 8), np.uint32)), P(bad), P(np.ones((2, 8), np.uint32)), P(st2), 2, pkg.HOST) == 0
     assert list(st2) == [pkg.ST_INVALID_SIG] * 2
+
+
+@pytest.mark.gpu
+def test_lindell17_wrappers_reject_malformed_peer_values_per_element(engine, pkg, keyset):
+    """Values a peer controls (ciphertexts, points, signature halves, decommitments) that do not fit their ABI slot reject that ONE
+    element with the status the reference's deserialisation / comparison would lead to; the batch goes through"""
+    from mpecdsa_b200 import gg20, lindell17 as L
+    rng = random.Random(0x5C12)
+    n = 4
+    c = _l17_case(keyset, rng, n)
+    ks = gg20.KeySets(engine, [keyset])
+    n_list = [keyset[r].dk.p * keyset[r].dk.q for r in range(3)]
+    e1 = L.eph_create(engine, c["k1"], c["n1"])
+    e2 = L.eph_create(engine, c["k2"], c["n2"], c["b1"], c["b2"])
+    wide_pt = (1 << 256, 5)
+    pubs = list(e1["public_share"]); pubs[1] = wide_pt
+    assert list(L.eph_verify(engine, pubs, e1["c"], e1["proof"])) == [0, pkg.ST_PROOF, 0, 0]
+    c_key = list(c["c_key"]); c_key[2] = 1 << 4096
+    c3, st = L.p2_partial_sig(engine, n_list, c["rows"], c_key, c["x2"], c["k2"], pubs, c["msg"], c["rho"], c["r_enc"])
+    assert list(st) == [0, pkg.ST_INVALID_KEY, pkg.ST_INVALID_KEY, 0]
+    c3[1] = c3[2] = -5
+    r, s, rec, st = L.p1_sign(engine, ks, c["rows"], c3, c["k1"], e2["public_share"])
+    assert list(st) == [0, pkg.ST_INVALID_KEY, pkg.ST_INVALID_KEY, 0]
+    r[3] = 1 << 300
+    assert list(L.verify(engine, r, s, c["pub"], c["msg"])) == [0, pkg.ST_INVALID_SIG, pkg.ST_INVALID_SIG, pkg.ST_INVALID_SIG]
+    ks.free()
