@@ -102,3 +102,31 @@ fn signature_of_a_gpu_offline_stage_verifies() {
     let d: SigDoc = load("signature");
     verify(&d.sig, &d.y, &d.message).expect("ECDSA signature rejected by the reference's verify"); // gg_2020/party_i.rs:913-936
 }
+
+// ---- Lindell-2017: the engine's ECDDHProof and a whole two-party signature -----------------------
+use multi_party_ecdsa::protocols::two_party_ecdsa::lindell_2017::{party_one, party_two};
+
+#[derive(Deserialize)]
+struct L17EphDoc { message: party_one::EphKeyGenFirstMsg }
+#[test]
+fn lindell17_ephemeral_message_from_the_gpu_verifies() {
+    let d: L17EphDoc = load("lindell17_eph_first_message");
+    // party_two::EphKeyGenSecondMsg::verify_and_decommit (party_two.rs:374-387) needs party two's own witness only to hand it back:
+    let (_first, witness, _pair) = party_two::EphKeyGenFirstMsg::create_commitments();
+    party_two::EphKeyGenSecondMsg::verify_and_decommit(witness, &d.message).expect("ECDDHProof of the engine rejected");
+}
+
+#[derive(Deserialize)]
+struct L17SigDoc { party_one_ec_key: party_one::EcKeyPair, party_one_paillier: party_one::PaillierKeyPair, party_one_eph: party_one::EphEcKeyPair,
+                   party_two_eph_public: Point<Secp256k1>, c3: BigInt, pubkey: Point<Secp256k1>, message: BigInt, signature: party_one::Signature, recid: u8 }
+#[test]
+fn lindell17_signature_is_what_the_reference_computes_from_the_gpu_partial_signature() {
+    let d: L17SigDoc = load("lindell17_signature");
+    let private = party_one::Party1Private::set_private_key(&d.party_one_ec_key, &d.party_one_paillier);
+    // party one's side on the CPU with the reference's own Paillier decrypt (party_one.rs:486-517) over party two's GPU-made c3 ...
+    let sig = party_one::Signature::compute(&private, &d.c3, &d.party_one_eph, &d.party_two_eph_public);
+    assert_eq!((&sig.r, &sig.s), (&d.signature.r, &d.signature.s)); // ... equals what tecdsa_l17_sign_batch produced on the device
+    let with_recid = party_one::Signature::compute_with_recid(&private, &d.c3, &d.party_one_eph, &d.party_two_eph_public);
+    assert_eq!(with_recid.recid, d.recid);
+    party_one::verify(&d.signature, &d.pubkey, &d.message).expect("signature rejected by party_one::verify"); // party_one.rs:567-592
+}

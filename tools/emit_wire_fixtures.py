@@ -25,6 +25,7 @@ def build_documents(eng, keyset, seed: int = 0xB2F2):
     import numpy as np
     from mpecdsa_b200 import gg20, keygen, wire
     from oracle.sampling import Drbg, sample_unit          # seeded sampling of the values the reference draws at random (test infrastructure)
+    from oracle.gg20_oracle import Q as o_Q
     E = wire.DEFAULT
     ks = gg20.KeySets(eng, [keyset])
     lk_a, lk_b = keyset[0], keyset[2]                       # Alice = party 1, Bob = party 3 (s_l = [1, 3])
@@ -88,9 +89,36 @@ def build_documents(eng, keyset, seed: int = 0xB2F2):
     kk = np.ascontiguousarray(rnd[:, 8:16])
     sg = gg20.sign_batch(eng, ks, np.array([[0, 0, 2]], dtype=np.uint32), msg, res.R, res.sigma, kk)
     assert list(sg["status"]) == [0]
-    I = lambda row: int.from_bytes(row.tobytes(), "little")
+    I = lambda row: int.from_bytes(np.ascontiguousarray(row).tobytes(), "little")
+    I2pt = lambda row: (I(row[:8]), I(row[8:16]))
     docs["signature"] = {"sig": wire.signature_recid(I(sg["r"][0]), I(sg["s"][0]), int(sg["recid"][0])), "y": E.point(lk_a.y_sum_s), "message": E.bigint(m),
                          "expect": "verify(&sig, &y, &message).is_ok() (gg_2020/party_i.rs:913); message = Sha256(b\"ZenGo\") as in sign.rs:693-696"}
+    # Lindell-2017 (two_party_ecdsa/lindell_2017): party one's ephemeral first message (ECDDHProof) and a whole signature; the
+    # reference recomputes the signature from party two's GPU-made c3 with ITS Paillier decrypt and must get the engine's (r, s)
+    from mpecdsa_b200 import lindell17
+    x1, x2, k1, k2 = rng.below(o_Q // 3), rng.below(o_Q), rng.below(o_Q - 1) + 1, rng.below(o_Q - 1) + 1
+    r_key, r_enc, rho = rng.below(n_a - 1) + 1, rng.below(n_a - 1) + 1, rng.below(o_Q * o_Q)
+    c_key = eng.paillier_encrypt([n_a], [0], [x1], [r_key])
+    e1 = lindell17.eph_create(eng, [k1], [rng.below(o_Q - 1) + 1])
+    e2 = lindell17.eph_create(eng, [k2], [rng.below(o_Q - 1) + 1], [rng.bits(256)], [rng.bits(256)])
+    assert list(lindell17.eph_verify(eng, e1["public_share"], e1["c"], e1["proof"])) == [0]
+    c3, st = lindell17.p2_partial_sig(eng, [n_a], [0], c_key, [x2], [k2], e1["public_share"], [m], [rho], [r_enc])
+    assert list(st) == [0]
+    sr, ss, rec, st = lindell17.p1_sign(eng, ks, [0], c3, [k1], e2["public_share"])
+    pub = eng.secp_mul(None, [x1 * x2 % o_Q])[0]
+    assert list(st) == [0] and list(lindell17.verify(eng, sr, ss, [pub], [m])) == [0]
+    pf = e1["proof"][0]
+    docs["lindell17_eph_first_message"] = {"message": {"d_log_proof": {"a1": E.point(I2pt(pf[:16])), "a2": E.point(I2pt(pf[16:32])), "z": E.scalar(I(pf[32:40]))},
+                                                       "public_share": E.point(e1["public_share"][0]), "c": E.point(e1["c"][0])},
+                                           "expect": "ECDDHProof::verify over (G, public_share, base_point2, c) is Ok (party_two.rs:374-387)"}
+    docs["lindell17_signature"] = {"party_one_ec_key": {"public_share": E.point(eng.secp_mul(None, [x1])[0]), "secret_share": E.scalar(x1)},
+                                   "party_one_paillier": {"ek": wire.encryption_key(n_a), "dk": {"p": E.bigint(lk_a.dk.p), "q": E.bigint(lk_a.dk.q)},
+                                                          "encrypted_share": E.bigint(c_key[0]), "randomness": E.bigint(r_key)},
+                                   "party_one_eph": {"public_share": E.point(e1["public_share"][0]), "secret_share": E.scalar(k1)},
+                                   "party_two_eph_public": E.point(e2["public_share"][0]), "c3": E.bigint(c3[0]), "pubkey": E.point(pub), "message": E.bigint(m),
+                                   "signature": {"s": E.bigint(ss[0]), "r": E.bigint(sr[0])}, "recid": int(rec[0]),
+                                   "expect": "party_one::Signature::compute(..) == signature and party_one::verify(&signature, &pubkey, &message).is_ok() "
+                                             "(party_one.rs:486-517, 567-592)"}
     ks.free()
     return docs
 
