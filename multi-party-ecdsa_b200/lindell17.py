@@ -72,18 +72,48 @@ def p2_keygen_verify(eng: Engine, pk_commitment, zk_pok_commitment, public_share
     return st
 
 
-def p1_paillier_and_proofs(eng: Engine, keys: KeySets, key_row, st_row, x1, randomness, pdl_rand, p_q):
+def generate_h1_h2_n_tilde(eng: Engine, setups):
+    """Lindell's `generate_h1_h2_n_tilde` (party_one.rs:594-607) with the samples explicit: setups[i] = (p~, q~, h1, xhi) ->
+    [(N~, h1, h2, xhi)] with h2 = (h1^-1)^xhi mod N~  (GG20's variant, gg_2020/party_i.rs:137-156, is keygen.h1_h2_n_tilde)"""
+    params, _ = keygen.h1_h2_n_tilde(eng, setups)                 # N~ = p~ q~ on the device
+    nt = [prm[0] for prm in params]
+    h1 = [s_[2] for s_ in setups]
+    h1_inv = eng.mod_inv(h1, nt)
+    h2, _ = eng.mod_pow([v or 0 for v in h1_inv], [s_[3] for s_ in setups], nt)
+    return [(nt[i], h1[i], h2[i], setups[i][3]) for i in range(len(setups))]
+
+
+def p1_paillier_and_proofs(eng: Engine, keys: KeySets, key_row, st_row, statements, xhi, x1, randomness, pdl_rand, cdlog_nonce, p_q):
     """`PaillierKeyPair::generate_encrypted_share_from_fixed_paillier_keypair`, `generate_ni_proof_correct_key` and `pdl_proof`
-    (party_one.rs:339-400) for Paillier key rows / (N~, h1, h2) rows of an uploaded key set: -> (encrypted_share,
-    NiCorrectKeyProof sigma vectors, PDLwSlackProof dict).  pdl_rand = (alpha, beta, rho, gamma) sequences; p_q the primes."""
+    (party_one.rs:339-400): Paillier key rows `key_row` and (N~, h1, h2) rows `st_row` of an uploaded key set, statements[i] =
+    (N~, h1, h2) of row st_row[i] with its secret xhi[i] -> dict(encrypted_share, correct_key_proof (11 sigmas), pdl (PDLwSlackProof
+    fields), composite_dlog_proof (x, y), Q).  pdl_rand = (alpha, beta, rho, gamma) sequences; p_q the primes of the Paillier keys."""
     n_list = [p * q for p, q in p_q]
     c_key = eng.paillier_encrypt(n_list, list(range(len(n_list))), list(x1), list(randomness))
     sigma, _ = keygen.correct_key_prove(eng, p_q)
+    cd = keygen.composite_dlog_prove(eng, list(statements), list(xhi), list(cdlog_nonce), secret_limbs=8)
     Q = eng.secp_mul(None, list(x1))
     G = eng.secp_mul(None, [1] * len(x1))
     alpha, beta, rho, gamma = pdl_rand
     pdl = gg20.pdl_prove(eng, keys, key_row, st_row, list(x1), list(randomness), c_key, Q, G, alpha, beta, rho, gamma)
-    return c_key, sigma, pdl
+    return {"encrypted_share": c_key, "correct_key_proof": sigma, "pdl": pdl, "composite_dlog_proof": cd, "Q": Q, "G": G}
+
+
+def p2_verify_paillier_and_proofs(eng: Engine, keys: KeySets, key_row, st_row, statements, n_list, msg, q1) -> np.ndarray:
+    """`PaillierPublic::verify_ni_proof_correct_key` (party_two.rs:302-311, incl. the bit-length floor of the modulus) and
+    `PaillierPublic::pdl_verify` (party_two.rs:275-300) over what p1_paillier_and_proofs produced -> status per element
+    (10 = IncorrectProof of the key, 6 = PartyTwoError::PdlVerify)"""
+    st = keygen.correct_key_verify(eng, n_list, msg["correct_key_proof"]).copy()
+    for i, n in enumerate(n_list):
+        if n.bit_length() < 2047 and not st[i]:                  # `ek.n.bit_length() < PAILLIER_KEY_SIZE - 1`
+            st[i] = 10
+    cd = keygen.composite_dlog_verify(eng, list(statements), msg["composite_dlog_proof"])
+    pd = msg["pdl"]
+    pv = gg20.pdl_verify(eng, keys, key_row, st_row, msg["encrypted_share"], msg["Q"], msg["G"], pd["z"], pd["u1"], pd["u2"], pd["u3"], pd["s1"], pd["s2"], pd["s3"])
+    for i in range(len(st)):
+        if not st[i] and (cd[i] or pv[i] or msg["Q"][i] != q1[i]):
+            st[i] = 6
+    return st
 
 
 # ----------------------------------------------------------------------------- ephemeral keys

@@ -603,3 +603,58 @@ def test_lindell17_wrappers_reject_malformed_peer_values_per_element(engine, pkg
     r[3] = 1 << 300
     assert list(L.verify(engine, r, s, c["pub"], c["msg"])) == [0, pkg.ST_INVALID_SIG, pkg.ST_INVALID_SIG, pkg.ST_INVALID_SIG]
     ks.free()
+
+
+@pytest.mark.gpu
+def test_lindell17_full_key_gen_on_gpu(engine, pkg, keyset):
+    """lindell_2017/test.rs `test_full_key_gen` as batch calls: commitments + DLog proof, Paillier-encrypted share, NiCorrectKeyProof,
+    PDL-with-slack proof against a freshly generated (N~, h1, h2) with its CompositeDLogProof — every proof checked by the engine's
+    verifier AND by the oracle's, and a wrong Q1 / foreign statement rejected"""
+    import dataclasses
+    from mpecdsa_b200 import gg20, lindell17 as L
+    from oracle import keygen_oracle as kg
+    from tests.test_keygen_oracle import _setup
+    rng = random.Random(0x17F6)
+    n = 2
+    setups = [_setup(rng, bits=1024) for _ in range(n)]
+    params = L.generate_h1_h2_n_tilde(engine, setups)
+    for (nt, h1, h2, xhi), (p_t, q_t, h1_in, xhi_in) in zip(params, setups):
+        assert nt == p_t * q_t and h2 == pow(pow(h1, -1, nt), xhi, nt) and (h1, xhi) == (h1_in, xhi_in)         # party_one.rs:594-607
+    # key rows 0 and 1 of a key set carry party one's Paillier keys and the fresh statements
+    parties = []
+    for i in range(3):
+        lk = keyset[i]
+        if i < n:
+            st = o.DLogStatement(params[i][0], params[i][1], params[i][2])
+            vec = list(lk.h1_h2_n_tilde_vec); vec[lk.i - 1] = st
+            lk = dataclasses.replace(lk, h1_h2_n_tilde_vec=vec)
+        parties.append(lk)
+    ks = gg20.KeySets(engine, [parties])
+    x1 = [rng.randrange(1, Q // 3) for _ in range(n)]
+    nonce, b1, b2 = [rng.randrange(1, Q) for _ in range(n)], [rng.getrandbits(256) for _ in range(n)], [rng.getrandbits(256) for _ in range(n)]
+    com1, com2, pk, proof = L.p1_keygen_first(engine, x1, nonce, b1, b2)
+    assert list(L.p2_keygen_verify(engine, com1, com2, pk, proof, b1, b2)) == [0] * n
+    p_q = [(keyset[i].dk.p, keyset[i].dk.q) for i in range(n)]
+    n_list = [p * q for p, q in p_q]
+    stm = [(prm[0], prm[1], prm[2]) for prm in params]
+    r_key = [rng.randrange(1, nn) for nn in n_list]
+    pdl_rand = ([rng.randrange(Q ** 3) for _ in range(n)], [rng.randrange(1, nn) for nn in n_list], [rng.randrange(Q * s[0]) for s in stm],
+                [rng.randrange(Q ** 3 * s[0]) for s in stm])
+    msg = L.p1_paillier_and_proofs(engine, ks, list(range(n)), list(range(n)), stm, [prm[3] for prm in params], x1, r_key, pdl_rand,
+                                   [rng.getrandbits(500) for _ in range(n)], p_q)
+    assert msg["Q"] == pk and msg["encrypted_share"] == [o.paillier_encrypt(o.EncryptionKey(nn, nn * nn), x, r) for nn, x, r in zip(n_list, x1, r_key)]
+    assert list(L.p2_verify_paillier_and_proofs(engine, ks, list(range(n)), list(range(n)), stm, n_list, msg, pk)) == [0] * n
+    # the oracle's verifiers accept the engine's proofs too
+    for i in range(n):
+        ek = o.EncryptionKey(n_list[i], n_list[i] ** 2)
+        st = o.DLogStatement(*stm[i])
+        assert kg.correct_key_verify(msg["correct_key_proof"][i], ek)
+        x_, y_ = msg["composite_dlog_proof"][i]
+        assert kg.composite_dlog_verify(kg.CompositeDLogProof(x_, y_), st)
+        pd = {k_: v[i] for k_, v in msg["pdl"].items()}
+        pf = o.PDLwSlackProof(pd["z"], pd["u1"], pd["u2"], pd["u3"], pd["s1"], pd["s2"], pd["s3"])
+        assert o.pdl_verify(pf, msg["encrypted_share"][i], ek, pk[i], G, st.g, st.ni, st.N)
+    # party two holds a different Q1 for element 0; element 1 is checked against the other element's statement
+    assert list(L.p2_verify_paillier_and_proofs(engine, ks, list(range(n)), list(range(n)), stm, n_list, msg, [pk[1], pk[1]])) == [pkg.ST_PDL_VERIFY, 0]
+    assert list(L.p2_verify_paillier_and_proofs(engine, ks, list(range(n)), [1, 1], [stm[1], stm[1]], n_list, msg, pk)) == [pkg.ST_PDL_VERIFY, 0]
+    ks.free()
