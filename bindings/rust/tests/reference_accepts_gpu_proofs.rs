@@ -130,3 +130,36 @@ fn lindell17_signature_is_what_the_reference_computes_from_the_gpu_partial_signa
     assert_eq!(with_recid.recid, d.recid);
     party_one::verify(&d.signature, &d.pubkey, &d.message).expect("signature rejected by party_one::verify"); // party_one.rs:567-592
 }
+
+// ---- the round messages of an offline stage produced by the engine (f2: state_machine/sign.rs:478-490) ---------------------------
+use curv::cryptographic_primitives::proofs::sigma_correct_homomorphic_elgamal_enc::{HomoELGamalProof, HomoElGamalStatement};
+use curv::cryptographic_primitives::proofs::sigma_valid_pedersen::PedersenProof;
+use multi_party_ecdsa::protocols::multi_party_ecdsa::gg_2020::state_machine::sign::OfflineProtocolMessage;
+use round_based::Msg;
+
+#[derive(Deserialize)]
+struct OfflineMsgDoc { messages: serde_json::Value, #[serde(rename = "R")] r: Point<Secp256k1>, #[serde(rename = "T_i")] t_i: Point<Secp256k1>,
+                       pdl_statement: PDLwSlackStatement }
+#[test]
+fn offline_round_messages_of_the_engine_are_reference_messages() {
+    let d: OfflineMsgDoc = load("offline_messages");
+    // shape: the whole array is what a `gg20_sm_manager` room would carry
+    let typed: Vec<Msg<OfflineProtocolMessage>> = serde_json::from_value(d.messages.clone()).expect("not Vec<Msg<OfflineProtocolMessage>>");
+    assert_eq!(serde_json::to_value(&typed).unwrap(), d.messages, "re-serialisation differs: a leaf encoding is not the reference's");
+    let body = |kind: &str| d.messages.as_array().unwrap().iter().find_map(|m| m["body"].get(kind).cloned()).unwrap_or_else(|| panic!("no {}", kind));
+    // M3 = (DeltaI, TI, TIProof): the Pedersen proof of T_i (sign/rounds.rs:371-378)
+    let m3 = body("M3");
+    let ped: PedersenProof<Secp256k1, Sha256> = serde_json::from_value(m3[2].clone()).unwrap();
+    assert_eq!(ped.com, d.t_i);
+    PedersenProof::verify(&ped).expect("PedersenProof of the engine rejected");
+    // M5 = (RDash, Vec<PDLwSlackProof>) (party_i.rs:719-766)
+    let m5 = body("M5");
+    let pdl: Vec<PDLwSlackProof> = serde_json::from_value(m5[1].clone()).unwrap();
+    pdl[0].verify(&d.pdl_statement).expect("PDLwSlackProof of the engine rejected");
+    // M6 = (SI, HEGProof) (party_i.rs:801-833)
+    let m6 = body("M6");
+    let s_i: Point<Secp256k1> = serde_json::from_value(m6[0].clone()).unwrap();
+    let heg: HomoELGamalProof<Secp256k1, Sha256> = serde_json::from_value(m6[1].clone()).unwrap();
+    let st = HomoElGamalStatement { G: d.r.clone(), H: Point::<Secp256k1>::base_point2().clone(), Y: Point::generator().to_point(), D: d.t_i.clone(), E: s_i };
+    heg.verify(&st).expect("HomoELGamalProof of the engine rejected");
+}

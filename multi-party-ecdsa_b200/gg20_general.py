@@ -22,7 +22,7 @@ def _pts_of(a: np.ndarray):
 
 
 def offline_batch(eng: Engine, keys: KeySets, ttag: int, key_rows: Sequence[int], all_rows: Sequence[Sequence[int]], w: Sequence[int],
-                  g_w: Sequence, y: Sequence, rnd: Dict[str, list]) -> Dict[str, list]:
+                  g_w: Sequence, y: Sequence, rnd: Dict[str, list], messages: bool = False) -> Dict[str, list]:
     """`OfflineStage` Round0..Round6 for sessions of `ttag` signers.
     key_rows[u]  key row (Paillier key + N~/h1/h2 setup) of element u in `keys`;
     all_rows[u]  the key rows of ALL keygen parties of its key, in keygen order (the statements `MessageA::a` proves against);
@@ -30,7 +30,9 @@ def offline_batch(eng: Engine, keys: KeySets, ttag: int, key_rows: Sequence[int]
     rnd          per element: gamma, k, blind, r_k, l, ped_s1, ped_s2, heg_s1, heg_s2 and alice[u] = n tuples (alpha, beta, gamma, ro);
                  per pair: beta_tag_gamma, r_gamma, nonce_gamma_b, nonce_gamma_beta, beta_tag_w, r_w, nonce_w_b, nonce_w_beta and
                  pdl[t] = (alpha, beta, rho, gamma).
-    -> dict(status, R, sigma, k, T): `CompletedOfflineStage` per element (T = its own T_i); status = the reference's first error."""
+    -> dict(status, R, sigma, k, T): `CompletedOfflineStage` per element (T = its own T_i); status = the reference's first error.
+    With messages=True also "messages": per element the list of `Msg<OfflineProtocolMessage>` documents it sends (serde-JSON shape of
+    state_machine/sign.rs:478-490 through wire.py; sender / receiver = 1-based signer positions), for sessions that completed."""
     U, P1 = len(key_rows), ttag - 1
     status = np.zeros(U, np.uint8)
     sess = lambda u: u // ttag * ttag
@@ -132,4 +134,29 @@ def offline_batch(eng: Engine, keys: KeySets, ttag: int, key_rows: Sequence[int]
             fail([u], ST_PHASE6)
     # a session stops in the round where its first party failed: the other parties of that session produce nothing either
     out_R = [R[u] if session_ok(u) else None for u in range(U)]
-    return {"status": status, "R": out_R, "sigma": sigma, "k": k, "T": _pts_of(T), "session_ok": [session_ok(u) for u in range(U)]}
+    out = {"status": status, "R": out_R, "sigma": sigma, "k": k, "T": _pts_of(T), "session_ok": [session_ok(u) for u in range(U)]}
+    if messages:
+        from . import wire
+        E = wire.DEFAULT
+        Tp = _pts_of(T)
+        docs = []
+        for u in range(U):
+            if not session_ok(u):
+                docs.append([])
+                continue
+            me_pos = u % ttag + 1
+            n_st = len(all_rows[u])
+            rp = [{f: proofs[f][u][x] for f in ("z", "e", "s", "s1", "s2")} for x in range(n_st)]
+            ped = wire.pedersen_proof(t_proof[u]); ped["com"] = E.point(Tp[u])
+            m = [wire.msg(me_pos, None, wire.offline_message("M1", [wire.message_a(c_a[u], rp), wire.sign_broadcast_phase1(com[u])]))]
+            for j in range(P1):
+                t = u * P1 + j
+                m.append(wire.msg(me_pos, peer[t] % ttag + 1, wire.offline_message("M2", [wire.message_b(cb_g[t], bp_g[t], btp_g[t]), wire.message_b(cb_w[t], bp_w[t], btp_w[t])])))
+            m.append(wire.msg(me_pos, None, wire.offline_message("M3", [E.scalar(delta[u]), E.point(Tp[u]), ped])))
+            m.append(wire.msg(me_pos, None, wire.offline_message("M4", wire.sign_decommit_phase1(rnd["blind"][u], g_gamma[u]))))
+            pl = [wire.pdl_proof({f: pdl[f][u * P1 + j] for f in ("z", "u1", "u2", "u3", "s1", "s2", "s3")}) for j in range(P1)]
+            m.append(wire.msg(me_pos, None, wire.offline_message("M5", [E.point(R_dash[u]), pl])))
+            m.append(wire.msg(me_pos, None, wire.offline_message("M6", [E.point(S[u]), wire.heg_proof(heg[u])])))
+            docs.append(m)
+        out["messages"] = docs
+    return out

@@ -91,7 +91,7 @@ def p1_paillier_and_proofs(eng: Engine, keys: KeySets, key_row, st_row, statemen
     n_list = [p * q for p, q in p_q]
     c_key = eng.paillier_encrypt(n_list, list(range(len(n_list))), list(x1), list(randomness))
     sigma, _ = keygen.correct_key_prove(eng, p_q)
-    cd = keygen.composite_dlog_prove(eng, list(statements), list(xhi), list(cdlog_nonce), secret_limbs=8)
+    cd = keygen.composite_dlog_prove(eng, list(statements), list(xhi), list(cdlog_nonce))
     Q = eng.secp_mul(None, list(x1))
     G = eng.secp_mul(None, [1] * len(x1))
     alpha, beta, rho, gamma = pdl_rand

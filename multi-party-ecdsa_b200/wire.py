@@ -132,6 +132,52 @@ def keygen_broadcast1(n: int, stmt: Tuple[int, int, int], com: int, sigma_vec: S
             "composite_dlog_proof_base_h2": {"x": enc.bigint(proof_h2[0]), "y": enc.bigint(proof_h2[1])}}
 
 
+# ------------------------------------------------------------------------------------------------- offline-stage round messages
+def _row_pt(limbs) -> Point:
+    v = int.from_bytes(limbs.tobytes(), "little")
+    return None if v == 0 else (v & ((1 << 256) - 1), v >> 256)
+
+
+def _row_int(limbs) -> int:
+    return int.from_bytes(limbs.tobytes(), "little")
+
+
+def pedersen_proof(row64, enc: Encoding = DEFAULT) -> Dict[str, Any]:
+    """curv `PedersenProof {e, a1, a2, com, z1, z2}` [R] from one row of gg20.pedersen_prove (e 8 | a1 16 | a2 16 | z1 8 | z2 8) and its
+    commitment; `com` is filled by the caller (it is T_i)"""
+    return {"e": enc.scalar(_row_int(row64[:8])), "a1": enc.point(_row_pt(row64[8:24])), "a2": enc.point(_row_pt(row64[24:40])), "com": None,
+            "z1": enc.scalar(_row_int(row64[40:48])), "z2": enc.scalar(_row_int(row64[48:56]))}
+
+
+def heg_proof(row48, enc: Encoding = DEFAULT) -> Dict[str, Any]:
+    """curv `HomoELGamalProof {T, A3, z1, z2}` [R] from one row of gg20.heg_prove (T 16 | A3 16 | z1 8 | z2 8)"""
+    return {"T": enc.point(_row_pt(row48[:16])), "A3": enc.point(_row_pt(row48[16:32])), "z1": enc.scalar(_row_int(row48[32:40])),
+            "z2": enc.scalar(_row_int(row48[40:48]))}
+
+
+def sign_broadcast_phase1(com: int, enc: Encoding = DEFAULT) -> Dict[str, Any]:
+    """`SignBroadcastPhase1 {com}` (gg_2020/party_i.rs:113-116)"""
+    return {"com": enc.bigint(com)}
+
+
+def sign_decommit_phase1(blind_factor: int, g_gamma_i: Point, enc: Encoding = DEFAULT) -> Dict[str, Any]:
+    """`SignDecommitPhase1 {blind_factor, g_gamma_i}` (gg_2020/party_i.rs:118-122)"""
+    return {"blind_factor": enc.bigint(blind_factor), "g_gamma_i": enc.point(g_gamma_i)}
+
+
+def offline_message(kind: str, body: Any) -> Dict[str, Any]:
+    """`OfflineProtocolMessage(OfflineM::<kind>(body))` (state_machine/sign.rs:478-490): a newtype around an externally tagged enum;
+    tuple bodies are JSON arrays, the newtype wrappers GammaI / WI / DeltaI / TI / TIProof / RDash / SI / HEGProof (sign/rounds.rs:33-49)
+    are transparent"""
+    assert kind in ("M1", "M2", "M3", "M4", "M5", "M6")
+    return {kind: body}
+
+
+def msg(sender: int, receiver: Optional[int], body: Any) -> Dict[str, Any]:
+    """round_based `Msg {sender, receiver, body}` [R] (1-based party indices; receiver = null for a broadcast)"""
+    return {"sender": int(sender), "receiver": None if receiver is None else int(receiver), "body": body}
+
+
 # ------------------------------------------------------------------------------------------------- LocalKey (local-share*.json)
 def local_key(lk, commitments: Sequence[Point], enc: Encoding = DEFAULT) -> Dict[str, Any]:
     """`LocalKey<Secp256k1>` from an object with the fields of oracle.LocalKey (i, t, n, x_i, dk.p, dk.q, pk_vec,

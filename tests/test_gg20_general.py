@@ -109,6 +109,33 @@ def _flatten(sessions, row_of):
     return ttag, key_rows, all_rows, w, g_w, y, {**per_elem, **per_pair}
 
 
+def _check_messages(out, sessions):
+    """the `Msg<OfflineProtocolMessage>` documents of every element: count, routing, and the fields the oracle can re-derive"""
+    from mpecdsa_b200 import wire
+    E = wire.DEFAULT
+    u = 0
+    for keys, s_l, rnd in sessions:
+        ttag = len(s_l)
+        for p, (lk, r) in enumerate(zip(keys, rnd)):
+            msgs = out["messages"][u]
+            assert [list(m["body"])[0] for m in msgs] == ["M1"] + ["M2"] * (ttag - 1) + ["M3", "M4", "M5", "M6"]
+            assert all(m["sender"] == p + 1 for m in msgs)
+            assert [m["receiver"] for m in msgs] == [None] + [gen._ind(p, j) + 1 for j in range(ttag - 1)] + [None] * 4
+            m_a = o.message_a(r.k_i % Q, lk.paillier_key_vec[lk.i - 1], r.r_k, lk.h1_h2_n_tilde_vec, r.alice)
+            want_a = wire.message_a(m_a.c, [{"z": x.z, "e": x.e, "s": x.s, "s1": x.s1, "s2": x.s2} for x in m_a.range_proofs])
+            m1 = msgs[0]["body"]["M1"]
+            assert m1[0] == want_a and m1[1] == wire.sign_broadcast_phase1(o.hash_commitment(o.bn_from_bytes(o.pt_compress(o.pt_mul(G, r.gamma_i % Q))), r.blind))
+            m4 = msgs[ttag + 1]["body"]["M4"]
+            assert m4 == wire.sign_decommit_phase1(r.blind, o.pt_mul(G, r.gamma_i % Q))
+            m3 = msgs[ttag]["body"]["M3"]
+            assert m3[1] == E.point(out["T"][u]) and m3[2]["com"] == m3[1] and set(m3[2]) == {"e", "a1", "a2", "com", "z1", "z2"}
+            m5 = msgs[ttag + 2]["body"]["M5"]
+            assert m5[0] == E.point(o.pt_mul(out["R"][u], out["k"][u])) and len(m5[1]) == ttag - 1 and set(m5[1][0]) == {"z", "u1", "u2", "u3", "s1", "s2", "s3"}
+            m6 = msgs[ttag + 3]["body"]["M6"]
+            assert m6[0] == E.point(o.pt_mul(out["R"][u], out["sigma"][u])) and set(m6[1]) == {"T", "A3", "z1", "z2"}
+            u += 1
+
+
 @pytest.mark.gpu
 def test_general_signing_sets_on_gpu_match_oracle(engine, pkg):
     from mpecdsa_b200 import gg20, gg20_general
@@ -126,7 +153,8 @@ def test_general_signing_sets_on_gpu_match_oracle(engine, pkg):
             owner.update({id(lk): kidx for lk in keys})
         cases.append((sessions, owner))
     for sessions, owner in cases:
-        out = gg20_general.offline_batch(engine, ks, *_flatten(sessions, lambda lk, j: 3 * owner[id(lk)] + j))
+        out = gg20_general.offline_batch(engine, ks, *_flatten(sessions, lambda lk, j: 3 * owner[id(lk)] + j), messages=True)
+        _check_messages(out, sessions)
         u = 0
         for keys, s_l, rnd in sessions:
             want = gen.offline_session(keys, s_l, rnd)

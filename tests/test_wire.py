@@ -83,3 +83,22 @@ def test_fixture_documents_from_engine_outputs(engine, pkg, keyset):
     assert back.pk_vec == lk_a.pk_vec and back.x_i == lk_a.x_i
     sig, _ = kg.correct_key_proof(lk_a.dk), None
     assert docs["keygen_broadcast1"]["message"]["correct_key_proof"]["sigma_vec"] == [wire.DEFAULT.bigint(x) for x in sig]
+
+
+def test_round_message_wrappers_follow_the_reference_definitions(pkg):
+    """state_machine/sign.rs:478-490 (`OfflineProtocolMessage(OfflineM)`, externally tagged, tuple bodies as arrays), sign/rounds.rs:33-49
+    (transparent newtypes), gg_2020/party_i.rs:113-122 (`SignBroadcastPhase1`, `SignDecommitPhase1`), round_based `Msg`"""
+    from mpecdsa_b200 import wire
+    E = wire.DEFAULT
+    ped = np.arange(64, dtype=np.uint32)
+    d = wire.pedersen_proof(ped)
+    assert list(d) == ["e", "a1", "a2", "com", "z1", "z2"] and d["e"] == E.scalar(int.from_bytes(ped[:8].tobytes(), "little"))
+    heg = wire.heg_proof(np.arange(48, dtype=np.uint32))
+    assert list(heg) == ["T", "A3", "z1", "z2"]
+    assert wire.sign_broadcast_phase1(255) == {"com": "ff"}
+    assert list(wire.sign_decommit_phase1(1, (o.G[0], o.G[1]))) == ["blind_factor", "g_gamma_i"]
+    m = wire.msg(2, None, wire.offline_message("M4", wire.sign_decommit_phase1(1, (o.G[0], o.G[1]))))
+    assert list(m) == ["sender", "receiver", "body"] and m["receiver"] is None and list(m["body"]) == ["M4"]
+    assert wire.msg(1, 2, wire.offline_message("M2", [{}, {}]))["receiver"] == 2
+    with pytest.raises(AssertionError):
+        wire.offline_message("M7", {})

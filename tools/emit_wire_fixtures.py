@@ -91,6 +91,7 @@ def build_documents(eng, keyset, seed: int = 0xB2F2):
     assert list(sg["status"]) == [0]
     I = lambda row: int.from_bytes(np.ascontiguousarray(row).tobytes(), "little")
     I2pt = lambda row: (I(row[:8]), I(row[8:16]))
+    unpack_res_point = lambda row: I2pt(row)
     docs["signature"] = {"sig": wire.signature_recid(I(sg["r"][0]), I(sg["s"][0]), int(sg["recid"][0])), "y": E.point(lk_a.y_sum_s), "message": E.bigint(m),
                          "expect": "verify(&sig, &y, &message).is_ok() (gg_2020/party_i.rs:913); message = Sha256(b\"ZenGo\") as in sign.rs:693-696"}
     # Lindell-2017 (two_party_ecdsa/lindell_2017): party one's ephemeral first message (ECDDHProof) and a whole signature; the
@@ -119,6 +120,28 @@ def build_documents(eng, keyset, seed: int = 0xB2F2):
                                    "signature": {"s": E.bigint(ss[0]), "r": E.bigint(sr[0])}, "recid": int(rec[0]),
                                    "expect": "party_one::Signature::compute(..) == signature and party_one::verify(&signature, &pubkey, &message).is_ok() "
                                              "(party_one.rs:486-517, 567-592)"}
+    # the six round messages of one signer of a two-signer offline stage, as `Msg<OfflineProtocolMessage>` (state_machine/sign.rs:478-490)
+    from mpecdsa_b200 import gg20_general
+    from oracle.gg20_oracle import lagrange_at_zero, pt_mul
+    s_l = [1, 3]
+    keys2 = [lk_a, lk_b]
+    g_rnd = {f: [] for f in ("gamma", "k", "blind", "r_k", "l", "ped_s1", "ped_s2", "heg_s1", "heg_s2", "alice", "beta_tag_gamma", "r_gamma", "nonce_gamma_b",
+                             "nonce_gamma_beta", "beta_tag_w", "r_w", "nonce_w_b", "nonce_w_beta", "pdl")}
+    for u_ in r:
+        for f, v in (("gamma", u_.gamma_i), ("k", u_.k_i), ("blind", u_.blind), ("r_k", u_.r_k), ("l", u_.l), ("ped_s1", u_.ped_s1), ("ped_s2", u_.ped_s2),
+                     ("heg_s1", u_.heg_s1), ("heg_s2", u_.heg_s2), ("alice", list(u_.alice)), ("beta_tag_gamma", u_.beta_tag_gamma), ("r_gamma", u_.r_gamma),
+                     ("nonce_gamma_b", u_.nonce_gamma_b), ("nonce_gamma_beta", u_.nonce_gamma_beta), ("beta_tag_w", u_.beta_tag_w), ("r_w", u_.r_w),
+                     ("nonce_w_b", u_.nonce_w_b), ("nonce_w_beta", u_.nonce_w_beta), ("pdl", u_.pdl)):
+            g_rnd[f].append(v)
+    lam = [lagrange_at_zero(i_ - 1, [0, 2]) for i_ in s_l]
+    gout = gg20_general.offline_batch(eng, ks, 2, [0, 2], [[0, 1, 2], [0, 1, 2]], [lam[p_] * keys2[p_].x_i % o_Q for p_ in range(2)],
+                                      [pt_mul(lk_a.pk_vec[s_l[p_] - 1], lam[p_]) for p_ in range(2)], [lk_a.y_sum_s] * 2, g_rnd, messages=True)
+    assert not gout["status"].any() and gout["R"][0] == unpack_res_point(res.R[0])
+    docs["offline_messages"] = {"messages": gout["messages"][0], "R": E.point(gout["R"][0]), "T_i": E.point(gout["T"][0]),
+                                "pdl_statement": wire.pdl_statement(c[0], n_a, eng.secp_mul([gout["R"][0]], [r[0].k_i])[0], gout["R"][0], stb.g, stb.ni, stb.N),
+                                "expect": "the array deserialises as Vec<Msg<OfflineProtocolMessage>> and re-serialises to the same JSON; M3's PedersenProof, M5's "
+                                          "PDLwSlackProof (against pdl_statement) and M6's HomoELGamalProof (statement G = R, H = base_point2, Y = generator, D = T_i, "
+                                          "E = M6[0]) verify; the same session through the fused driver gave the same R"}
     ks.free()
     return docs
 
