@@ -111,7 +111,7 @@ extern "C" int tecdsa_ctx_set_tpi(tecdsa_ctx* c, int mod_bits, int tpi) {
     if (!c) return fail(TECDSA_E_ARG, "null ctx");
     int slot = mod_bits == 1024 ? 0 : mod_bits == 2048 ? 1 : mod_bits == 4096 ? 2 : -1;
     if (slot < 0) return fail(TECDSA_E_ARG, "set_tpi: mod_bits must be 1024/2048/4096");
-    if (tpi != 0 && tpi != 2 && tpi != 4 && tpi != 8 && tpi != 16 && tpi != 32) return fail(TECDSA_E_ARG, "set_tpi: tpi must be 0/4/8/16/32");
+    if (tpi != 0 && tpi != 4 && tpi != 8 && tpi != 16 && tpi != 32) return fail(TECDSA_E_ARG, "set_tpi: tpi must be 0/4/8/16/32");
     c->tpi[slot] = tpi;
     return 0;
 }
@@ -217,7 +217,7 @@ static cudaError_t dispatch_modexp(bool sqr, int mod_bits, int tpi, cudaStream_t
 #define GO(K, T) return launch_modexp<K, T>(sqr, s, base, exp, mod, mod_idx, out, status, table, count, exp_limbs, work)
     switch (mod_bits) {
     case 1024: switch (tpi) { case 4: GO(32, 4); case 8: GO(32, 8); case 16: GO(32, 16); default: return cudaErrorInvalidValue; }
-    case 2048: switch (tpi) { case 2: GO(64, 2); case 4: GO(64, 4); case 8: GO(64, 8); case 16: GO(64, 16); case 32: GO(64, 32); default: return cudaErrorInvalidValue; }
+    case 2048: switch (tpi) { case 4: GO(64, 4); case 8: GO(64, 8); case 16: GO(64, 16); case 32: GO(64, 32); default: return cudaErrorInvalidValue; }
     case 4096: switch (tpi) { case 8: GO(128, 8); case 16: GO(128, 16); case 32: GO(128, 32); default: return cudaErrorInvalidValue; }
     }
 #undef GO
