@@ -5,11 +5,11 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-: > $O/r02_nadic32_shape.log
+: > $O/r02_nadic_shape2.log
 for rep in 1 2; do
-  for shape in "8,1,4,1" "8,1,2,1" "8,1,4,4"; do
-    echo "TECDSA_NADIC_SHAPE=$shape rep=$rep" >> $O/r02_nadic32_shape.log
-    TECDSA_NADIC_SHAPE=$shape python tools/offline_throughput.py 8192 2>&1 | tail -1 >> $O/r02_nadic32_shape.log
+  for shape in "8,1,4,4" "8,4,4,4" "8,4,4,1"; do
+    echo "TECDSA_NADIC_SHAPE=$shape rep=$rep" >> $O/r02_nadic_shape2.log
+    TECDSA_NADIC_SHAPE=$shape python tools/offline_throughput.py 8192 2>&1 | tail -1 >> $O/r02_nadic_shape2.log
   done
 done
-cat $O/r02_nadic32_shape.log
+cat $O/r02_nadic_shape2.log
