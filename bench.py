@@ -103,7 +103,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.first = device, [], None, 0
+
+    def mark(self):
+        """samples from here on are the ones reported (the poller itself is started before the warm-up: its NVML start-up takes the driver
+        lock for a few hundred ms, which would otherwise stall kernel launches inside the timed region)"""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -125,7 +130,7 @@ class ClockSampler:
             except Exception:
                 pass
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -339,12 +344,13 @@ def main():
             torch.cuda.synchronize()
 
     # ---- device-resident timing
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler.mark()
     eng.work(reset=True)
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
