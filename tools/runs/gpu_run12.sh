@@ -2,7 +2,7 @@
 # Round-2 run 12 on one B200: secp256k1 scalar-multiplication throughput (configs[2] shape, device buffers) and an ncu --set full capture
 # of the variable-base launch (one report per call: the merge-back limit of gpurun_out is 64 MiB).
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python tools/ec_throughput.py 20 2>&1 | tail -1 > $O/r02_ec_throughput.json

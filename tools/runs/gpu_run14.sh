@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 run 14 on TWO B200s of one box (gpurun --gpus 2): the library's NCCL gather against torch.distributed, then bench.py at N = 2.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests/test_nccl_gather_gpu.py -m gpu -q --tb=short -p no:cacheprovider 2>&1 | tail -15 > $O/r02_t14.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 run 15 on one B200: full GPU suite, smoke(), then the two bench arms exactly as the driver launches them.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider 2>&1 | tail -15 > $O/r02_t15.log

@@ -2,7 +2,7 @@
 # Round-2 run 16 on one B200: wire documents for the Rust pin test (incl. Lindell-2017), the tests that consume them, then compute-sanitizer
 # over every kernel family including the section 8(f) rank-4 kernels.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python tools/emit_wire_fixtures.py $O/wire 2>&1 | tail -2

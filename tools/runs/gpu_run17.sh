@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 run 17 on N GPUs of one box (gpurun --gpus N): the library's NCCL gather test and both bench arms as the driver launches them.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 N=$(nvidia-smi -L | wc -l)
 mkdir -p $O

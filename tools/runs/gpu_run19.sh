@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 run 19 on one B200: Lindell-2017 key generation test, round-message documents, the tests that consume them.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python tools/emit_wire_fixtures.py $O/wire 2>&1 | tail -3

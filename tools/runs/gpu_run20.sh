@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 run 20 on one B200: the 2-lanes-per-operand variant of the 2048-bit modexp kernel (254 registers, 8 warps per SM) against 4 lanes.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 : > $O/r02_tpi2.log

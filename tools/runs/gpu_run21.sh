@@ -2,7 +2,7 @@
 # Round-2 run 21 on one B200: lane-group shapes of the p-adic kernel (modulus p^2, q^2): 4 lanes x 8 limbs (default) against 2 lanes x 16 limbs
 # and against 4 lanes with 4 blocks per SM, through TECDSA_NADIC_SHAPE, on the 8192-session batch.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 : > $O/r02_nadic_shape2.log

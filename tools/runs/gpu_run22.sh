@@ -2,7 +2,7 @@
 # Round-2 run 22 on one B200: modexp kernel at 4 blocks per SM (128 registers, 8 B of spills) against 3 blocks (136 registers); the new
 # N-adic default shape in the bench loop.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 : > $O/r02_modexp_minb.log

@@ -2,7 +2,7 @@
 # Round-2 run 23 on one B200: final bench lines with the 4-blocks-per-SM defaults, launch list of the bench command, ncu --set full of the
 # dominant N-adic launch in its new shape.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python bench.py --impl reference > $O/r02_ref_n1.json 2> $O/r02_ref_n1.err

@@ -2,7 +2,7 @@
 # Round-2 evidence run on one B200 (through gpurun): parity suite, launch list of the bench command, ncu --set full captures of the
 # two headline kernels, lane-group sweep of the modexp kernel, compute-sanitizer over every kernel family.  Outputs: gpurun_out/.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -q --tb=short -x -p no:cacheprovider 2>&1 | tail -12 > $O/r02_t7.log

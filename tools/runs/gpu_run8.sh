@@ -2,7 +2,7 @@
 # Round-2 evidence run 8 on one B200: persistent modexp check, ncu --set full of the dominant N-adic launch and of the persistent
 # modexp kernel, then the bench lines (own arm with cpu_baseline, reference arm).  Outputs: gpurun_out/.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests/test_modexp_gpu.py -m gpu -q --tb=short -x -p no:cacheprovider 2>&1 | tail -5 > $O/r02_t8.log

@@ -2,7 +2,7 @@
 # Round-2 evidence run 9 on one B200: ncu --set full of the dominant N-adic launch (template-qualified kernel filter), modexp timing
 # after the persistent variant was reverted.  Outputs: gpurun_out/.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 TECDSA_SPLIT=0 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:nadic_jobs_kernel<.int.64' -s 8 -c 1 \
