@@ -52,7 +52,8 @@ enum {
     TECDSA_ST_PHASE6 = 8,         /* Error::Phase6Error          gg_2020/party_i.rs:846 */
     TECDSA_ST_INVALID_SIG = 9,    /* Error::InvalidSig           gg_2020/party_i.rs:908,934 */
     TECDSA_ST_PROOF = 10,         /* a curv sigma proof (DLog/Pedersen/HomoElGamal) failed to verify */
-    TECDSA_ST_COMMITMENT = 11     /* "bad gamma_i decommit"      gg_2020/party_i.rs:650-674 */
+    TECDSA_ST_COMMITMENT = 11,    /* "bad gamma_i decommit"      gg_2020/party_i.rs:650-674 */
+    TECDSA_ST_INVALID_SS = 12     /* Error::InvalidSS            gg_2018/party_i.rs:262-281 (reported by the host-composed key-generation drivers) */
 };
 
 /* ---- context ------------------------------------------------------------------------ */

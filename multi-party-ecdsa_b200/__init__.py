@@ -25,7 +25,7 @@ LIB_PATH = os.environ.get("TECDSA_B200_LIB") or os.path.join(_HERE, "libtecdsa_b
 
 HOST, DEVICE = 0, 1
 ST_OK, ST_EVEN_MODULUS, ST_INVALID_KEY, ST_RANGE, ST_NOT_INVERTIBLE, ST_HASH_MISMATCH = 0, 1, 2, 3, 4, 5
-ST_PDL_VERIFY, ST_PHASE5_BAD_SUM, ST_PHASE6, ST_INVALID_SIG, ST_PROOF, ST_COMMITMENT = 6, 7, 8, 9, 10, 11
+ST_PDL_VERIFY, ST_PHASE5_BAD_SUM, ST_PHASE6, ST_INVALID_SIG, ST_PROOF, ST_COMMITMENT, ST_INVALID_SS = 6, 7, 8, 9, 10, 11, 12
 
 # every symbol include/tecdsa_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [

@@ -184,3 +184,50 @@ def sign_batch(eng: Engine, keys, parties: int, key_rows, w, y, message, rnd):
     r, s, rec, st = output_signature(eng, parties, Rs, y, message, s_i)
     first_fail(st)
     return {"r": r, "s": s, "recid": rec, "status": status, "R": R, "s_i": s_i}
+
+
+# ----------------------------------------------------------------------------- key generation (gg_2018/party_i.rs:155-317)
+def keygen_batch(eng: Engine, t: int, n: int, u, p_q, blind, polynomials, dlog_nonce):
+    """GG18 key generation for `sessions` groups of n parties (element e = session * n + party) as batch calls:
+    `Keys::phase1_broadcast_phase3_proof_of_correct_key`, `phase1_verify_com_phase3_verify_correct_key_phase2_distribute`,
+    `phase2_verify_vss_construct_keypair_phase3_pok_dlog`, `verify_dlog_proofs`.  u[e] = the party's secret u_i, p_q[e] its Paillier
+    primes, blind[e] the commitment blinding factor, polynomials[e] = [u_i, a_1 .. a_t] (the coefficients `VerifiableSS::share`
+    samples), dlog_nonce[e] the nonce of the final DLogProof.
+    -> dict(status per element (0 / 2 = InvalidKey / 12 = InvalidSS), y per element (the group key), x_i (secret share), y_i, com,
+            correct_key_proof, vss commitments, shares, dlog proofs)"""
+    from . import gg20, keygen
+    E = len(u)
+    assert E % n == 0 and all(poly[0] == ui for poly, ui in zip(polynomials, u))
+    sess = lambda e: e // n * n
+    status = np.zeros(E, np.uint8)
+    # phase 1: y_i, commitment, NiCorrectKeyProof
+    y_i = eng.secp_mul(None, list(u))
+    com = gg20.hash_commitment(eng, y_i, blind)
+    n_list = [p * q for p, q in p_q]
+    sigma, st = keygen.correct_key_prove(eng, p_q)
+    # phase 1 verification by every receiver = one check per sender (the same for all receivers), then phase 2 distribution
+    reopen = gg20.hash_commitment(eng, y_i, blind)
+    ck = keygen.correct_key_verify(eng, n_list, sigma)
+    bad_sender = [reopen[e] != com[e] or ck[e] != 0 or st[e] != 0 for e in range(E)]
+    for e in range(E):
+        if any(bad_sender[sess(e):sess(e) + n]):
+            status[e] = 2                                         # Err(InvalidKey)
+    shares, commitments = keygen.vss_share(eng, t, n, polynomials)
+    # phase 2: receiver r validates the share of every sender s of its group: pairs (r, s)
+    recv = [r for r in range(E) for _ in range(n)]
+    send = [sess(r) + j for r in range(E) for j in range(n)]
+    ok = keygen.vss_validate_share(eng, [commitments[s] for s in send], [shares[s][r % n] for r, s in zip(recv, send)], [r % n + 1 for r in recv])
+    for i, (r, s) in enumerate(zip(recv, send)):
+        if (ok[i] != 0 or commitments[s][0] != y_i[s]) and not status[r]:
+            status[r] = 12                                        # Err(InvalidSS)
+    y = [y_i[sess(e)] for e in range(E)]
+    x_i = [shares[sess(e)][e % n] for e in range(E)]
+    for j in range(1, n):
+        y = eng.point_add(y, [y_i[sess(e) + j] for e in range(E)])
+        x_i = eng.scalar_op("add", x_i, [shares[sess(e) + j][e % n] for e in range(E)])
+    dlog = gg20.dlog_prove(eng, x_i, dlog_nonce)
+    dv = gg20.dlog_verify(eng, dlog)
+    for e in range(E):
+        if dv[sess(e):sess(e) + n].any() and not status[e]:
+            status[e] = 2                                         # verify_dlog_proofs -> Err(InvalidKey)
+    return {"status": status, "y": y, "x_i": x_i, "y_i": y_i, "com": com, "correct_key_proof": sigma, "commitments": commitments, "shares": shares, "dlog": dlog}

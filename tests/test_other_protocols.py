@@ -658,3 +658,64 @@ def test_lindell17_full_key_gen_on_gpu(engine, pkg, keyset):
     assert list(L.p2_verify_paillier_and_proofs(engine, ks, list(range(n)), list(range(n)), stm, n_list, msg, [pk[1], pk[1]])) == [pkg.ST_PDL_VERIFY, 0]
     assert list(L.p2_verify_paillier_and_proofs(engine, ks, list(range(n)), [1, 1], [stm[1], stm[1]], n_list, msg, pk)) == [pkg.ST_PDL_VERIFY, 0]
     ks.free()
+
+
+@pytest.mark.gpu
+def test_gg18_key_generation_then_signing_on_gpu(engine, pkg, keyset):
+    """gg_2018/test.rs `keygen_t_n_parties` + `sign` as batch calls: two groups of three parties generate (t = 1, n = 3) keys over the
+    fixture Paillier keys, the shares are Shamir-consistent with the group key, and two of the three sign with them; a tampered share
+    stops its receiver with InvalidSS"""
+    from mpecdsa_b200 import gg18, gg20
+    from oracle import keygen_oracle as kg
+    rng = random.Random(0x18C9)
+    t, n, groups = 1, 3, 2
+    E = n * groups
+    u = [rng.randrange(1, Q) for _ in range(E)]
+    polys = [[u[e]] + [rng.randrange(1, Q) for _ in range(t)] for e in range(E)]
+    p_q = [(keyset[e % n].dk.p, keyset[e % n].dk.q) for e in range(E)]
+    blind = [rng.getrandbits(256) for _ in range(E)]
+    nonce = [rng.randrange(1, Q) for _ in range(E)]
+    out = gg18.keygen_batch(engine, t, n, u, p_q, blind, polys, nonce)
+    assert list(out["status"]) == [0] * E
+    for g in range(groups):
+        ys = o.pt_mul(G, sum(u[g * n:(g + 1) * n]) % Q)
+        assert all(out["y"][e] == ys for e in range(g * n, (g + 1) * n))
+        for e in range(g * n, (g + 1) * n):
+            vss, sh = kg.vss_share(t, n, polys[e][0], polys[e][1:])
+            assert out["shares"][e] == sh and out["commitments"][e] == vss.commitments
+            assert out["x_i"][e] == sum(kg.vss_share(t, n, polys[s][0], polys[s][1:])[1][e % n] for s in range(g * n, (g + 1) * n)) % Q
+            assert kg.correct_key_verify(out["correct_key_proof"][e], o.EncryptionKey(p_q[e][0] * p_q[e][1], (p_q[e][0] * p_q[e][1]) ** 2))
+        for pair in ([0, 1], [0, 2], [1, 2]):                             # any two shares interpolate the group secret
+            lam = [o.lagrange_at_zero(i, pair) for i in pair]
+            assert o.pt_mul(G, sum(l * out["x_i"][g * n + i] for l, i in zip(lam, pair)) % Q) == ys
+    # sign with parties (0, 2) of group 0 and (1, 2) of group 1 using the freshly generated shares (the Paillier rows are the fixture's)
+    ks = gg20.KeySets(engine, [keyset])
+    signers = [[0, 2], [1, 2]]
+    rows = [p for s in signers for p in s]
+    w = [o.lagrange_at_zero(p, s) * out["x_i"][g * n + p] % Q for g, s in enumerate(signers) for p in s]
+    ysig = [out["y"][g * n] for g, s in enumerate(signers) for _ in s]
+    msg = [m for _ in signers for m in [rng.getrandbits(256)] * 2]
+    U, P1 = 4, 1
+    sc = lambda m_: [rng.randrange(1, Q) for _ in range(m_)]
+    nm = lambda elems: [rng.randrange(1, (keyset[rows[e]].dk.p * keyset[rows[e]].dk.q) >> 1) for e in elems]
+    alice = list(range(U))
+    rnd = dict(k=sc(U), gamma=sc(U), blind=sc(U), r_a=nm(range(U)), l=sc(U), rho=sc(U), blind5=sc(U), blind5c=sc(U), heg_s1=sc(U), heg_s2=sc(U), dlog_nonce=sc(U),
+               r_b_gamma=nm(alice), r_b_w=nm(alice), nb_gamma=sc(U), nbt_gamma=sc(U), nb_w=sc(U), nbt_w=sc(U), beta_tag_gamma=nm(alice), beta_tag_w=nm(alice))
+    sig = gg18.sign_batch(engine, ks, 2, rows, w, ysig, msg, rnd)
+    assert list(sig["status"]) == [0] * U
+    assert all(_ecdsa_ok(sig["r"][e], sig["s"][e], ysig[e], msg[e]) for e in range(U))
+    ks.free()
+    # failure: the share party 4 sends to party 5 is off by one -> InvalidSS for receiver 5 only
+    import mpecdsa_b200.keygen as kmod
+    orig = kmod.vss_share
+
+    def tampered(eng, t_, n_, polynomials):
+        sh, cm = orig(eng, t_, n_, polynomials)
+        sh[4][2] = (sh[4][2] + 1) % Q                                    # what party 4 sends to party 5 (index 3 of group 1)
+        return sh, cm
+    kmod.vss_share = tampered
+    try:
+        out3 = gg18.keygen_batch(engine, t, n, u, p_q, blind, polys, nonce)
+    finally:
+        kmod.vss_share = orig
+    assert list(out3["status"]) == [0, 0, 0, 0, 0, pkg.ST_INVALID_SS]
