@@ -242,6 +242,39 @@ def load_local_key(doc: Dict[str, Any], decompress, enc: Encoding = DEFAULT) -> 
         y_sum_s=pt(doc["y_sum_s"]), vss_commitments=[pt(p) for p in doc["vss_scheme"]["commitments"]])
 
 
+def parse_offline_message(m: Dict[str, Any], decompress, enc: Encoding = DEFAULT) -> Dict[str, Any]:
+    """Inverse of msg(...offline_message(...)): a `Msg<OfflineProtocolMessage>` document from a peer -> {"sender", "receiver", "kind"} plus
+    the decoded fields in the shapes the batch calls take (integers, (x, y) points, proof dicts / 40-limb DLogProof rows as integers):
+      M1: c, range_proofs [{z,e,s,s1,s2}], com          M2: gamma / w = {c, b_proof, beta_tag_proof} with proofs as {pk, pk_t_rand_commitment,
+      M3: delta, T, pedersen {e,a1,a2,com,z1,z2}              challenge_response}
+      M4: blind_factor, g_gamma                          M5: R_dash, pdl [{z,u1,u2,u3,s1,s2,s3}]          M6: S, heg {T,A3,z1,z2}
+    Field widths are NOT checked here: the verify-side wrappers (gg20._Screen) reject over-wide values per element."""
+    B, S = enc.bigint_from, enc.scalar_from
+    P = lambda d: enc.point_from(d, decompress)
+    (kind, body), = m["body"].items()
+    out = {"sender": int(m["sender"]), "receiver": None if m["receiver"] is None else int(m["receiver"]), "kind": kind}
+    dl = lambda d: {"pk": P(d["pk"]), "pk_t_rand_commitment": P(d["pk_t_rand_commitment"]), "challenge_response": S(d["challenge_response"])}
+    mb = lambda d: {"c": B(d["c"]), "b_proof": dl(d["b_proof"]), "beta_tag_proof": dl(d["beta_tag_proof"])}
+    if kind == "M1":
+        out.update(c=B(body[0]["c"]), range_proofs=[{k: B(pf[k]) for k in ("z", "e", "s", "s1", "s2")} for pf in body[0]["range_proofs"]], com=B(body[1]["com"]))
+    elif kind == "M2":
+        out.update(gamma=mb(body[0]), w=mb(body[1]))
+    elif kind == "M3":
+        pf = body[2]
+        out.update(delta=S(body[0]), T=P(body[1]), pedersen={"e": S(pf["e"]), "a1": P(pf["a1"]), "a2": P(pf["a2"]), "com": P(pf["com"]), "z1": S(pf["z1"]), "z2": S(pf["z2"])})
+    elif kind == "M4":
+        out.update(blind_factor=B(body["blind_factor"]), g_gamma=P(body["g_gamma_i"]))
+    elif kind == "M5":
+        out.update(R_dash=P(body[0]), pdl=[{"z": B(pf["z"]), "u1": P(pf["u1"]), "u2": B(pf["u2"]), "u3": B(pf["u3"]), "s1": B(pf["s1"]), "s2": B(pf["s2"]), "s3": B(pf["s3"])}
+                                            for pf in body[1]])
+    elif kind == "M6":
+        pf = body[1]
+        out.update(S=P(body[0]), heg={"T": P(pf["T"]), "A3": P(pf["A3"]), "z1": S(pf["z1"]), "z2": S(pf["z2"])})
+    else:
+        raise ValueError("unknown OfflineM variant " + kind)
+    return out
+
+
 def dumps(doc: Any) -> str:
     """serde_json's compact form"""
     return json.dumps(doc, separators=(",", ":"))

@@ -102,3 +102,78 @@ def test_round_message_wrappers_follow_the_reference_definitions(pkg):
     assert wire.msg(1, 2, wire.offline_message("M2", [{}, {}]))["receiver"] == 2
     with pytest.raises(AssertionError):
         wire.offline_message("M7", {})
+
+
+def test_offline_messages_parse_back(pkg):
+    """wire.parse_offline_message inverts the emitters on the engine-produced document committed for the Rust test
+    (bindings/rust/tests/data/offline_messages.json), with the oracle's decompression standing in for `Point::from_bytes`"""
+    import json, os
+    from mpecdsa_b200 import wire
+    E = wire.DEFAULT
+
+    def decompress(b):
+        x = int.from_bytes(b[1:], "big")
+        y = pow((x ** 3 + 7) % o.P, (o.P + 1) // 4, o.P)
+        return (x, y if (y & 1) == (b[0] & 1) else o.P - y)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bindings", "rust", "tests", "data", "offline_messages.json")
+    doc = json.load(open(path))
+    parsed = [wire.parse_offline_message(m, decompress) for m in doc["messages"]]
+    assert [p["kind"] for p in parsed] == ["M1", "M2", "M3", "M4", "M5", "M6"] and [p["receiver"] for p in parsed] == [None, 2, None, None, None, None]
+    m1, m2, m3, m4, m5, m6 = parsed
+    # re-emitting the parsed values gives the document back, byte for byte
+    assert wire.message_a(m1["c"], m1["range_proofs"]) == doc["messages"][0]["body"]["M1"][0] and wire.sign_broadcast_phase1(m1["com"]) == doc["messages"][0]["body"]["M1"][1]
+    assert wire.sign_decommit_phase1(m4["blind_factor"], m4["g_gamma"]) == doc["messages"][3]["body"]["M4"]
+    assert [wire.pdl_proof(p) for p in m5["pdl"]] == doc["messages"][4]["body"]["M5"][1] and E.point(m5["R_dash"]) == doc["messages"][4]["body"]["M5"][0]
+    # and the values are the protocol's: the commitment opens, T is the Pedersen commitment, the sigma proofs verify under the oracle
+    assert o.hash_commitment(o.bn_from_bytes(o.pt_compress(m4["g_gamma"])), m4["blind_factor"]) == m1["com"]
+    ped = m3["pedersen"]
+    assert ped["com"] == m3["T"] and o.pedersen_verify(o.PedersenProof(ped["e"], ped["a1"], ped["a2"], ped["com"], ped["z1"], ped["z2"]))
+    R = decompress(E.raw_from(doc["R"]["point"]))
+    heg = m6["heg"]
+    assert o.heg_verify(o.HomoElGamalProof(heg["T"], heg["A3"], heg["z1"], heg["z2"]), R, o.H2, o.G, m3["T"], m6["S"])
+    assert all(o.dlog_verify(o.DLogProof(d["pk"], d["pk_t_rand_commitment"], d["challenge_response"])) for mb in (m2["gamma"], m2["w"]) for d in (mb["b_proof"], mb["beta_tag_proof"]))
+
+
+def test_committed_engine_documents_verify_under_the_oracle(pkg):
+    """Every document under bindings/rust/tests/data/ was produced on a B200 (tools/emit_wire_fixtures.py); here, without a GPU, the
+    oracle's verifiers judge them — the same judgement the Rust test asks of the reference."""
+    import json, os
+    from oracle import lindell17_oracle as l17
+    from mpecdsa_b200 import wire
+    E = wire.DEFAULT
+    base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bindings", "rust", "tests", "data")
+    load = lambda name: json.load(open(os.path.join(base, name + ".json")))
+    B, S = E.bigint_from, E.scalar_from
+
+    def pt(d):
+        b = E.raw_from(d["point"])
+        x = int.from_bytes(b[1:], "big")
+        y = pow((x ** 3 + 7) % o.P, (o.P + 1) // 4, o.P)
+        return (x, y if (y & 1) == (b[0] & 1) else o.P - y)
+    ek = lambda d: o.EncryptionKey(B(d["n"]), B(d["n"]) ** 2)
+    st = lambda d: o.DLogStatement(B(d["N"]), B(d["g"]), B(d["ni"]))
+    ap = lambda d: o.AliceProof(*(B(d[k]) for k in ("z", "e", "s", "s1", "s2")))
+    d = load("alice_proof")
+    assert o.alice_proof_verify(ap(d["proof"]), B(d["cipher"]), ek(d["ek"]), st(d["dlog_statement"]))
+    d = load("message_a")
+    assert all(o.alice_proof_verify(ap(pf), B(d["message"]["c"]), ek(d["ek"]), st(s_)) for pf, s_ in zip(d["message"]["range_proofs"], d["dlog_statements"]))
+    d = load("dlog_proof")["proof"]
+    assert o.dlog_verify(o.DLogProof(pt(d["pk"]), pt(d["pk_t_rand_commitment"]), S(d["challenge_response"])))
+    d = load("pdl")
+    s_, p_ = d["statement"], d["proof"]
+    pf = o.PDLwSlackProof(B(p_["z"]), pt(p_["u1"]), B(p_["u2"]), B(p_["u3"]), B(p_["s1"]), B(p_["s2"]), B(p_["s3"]))
+    assert o.pdl_verify(pf, B(s_["ciphertext"]), ek(s_["ek"]), pt(s_["Q"]), pt(s_["G"]), B(s_["h1"]), B(s_["h2"]), B(s_["N_tilde"]))
+    d = load("signature")
+    assert o.ecdsa_verify(S(d["sig"]["r"]), S(d["sig"]["s"]), pt(d["y"]), B(d["message"]))
+    d = load("lindell17_eph_first_message")["message"]
+    proof = o.ECDDHProof(pt(d["d_log_proof"]["a1"]), pt(d["d_log_proof"]["a2"]), S(d["d_log_proof"]["z"]))
+    assert o.ecddh_verify(proof, o.G, pt(d["public_share"]), o.H2, pt(d["c"]))
+    d = load("lindell17_signature")
+    dk = o.DecryptionKey(B(d["party_one_paillier"]["dk"]["p"]), B(d["party_one_paillier"]["dk"]["q"]))
+    r, s, recid = l17.p1_sign(dk, B(d["c3"]), S(d["party_one_eph"]["secret_share"]), pt(d["party_two_eph_public"]))
+    assert (r, s, recid) == (B(d["signature"]["r"]), B(d["signature"]["s"]), d["recid"]) and l17.verify(r, s, pt(d["pubkey"]), B(d["message"]))
+    d = load("message_b")
+    mb = d["message"]
+    dl = lambda x: o.DLogProof(pt(x["pk"]), pt(x["pk_t_rand_commitment"]), S(x["challenge_response"]))
+    got = o.verify_proofs_get_alpha(o.MessageB(B(mb["c"]), dl(mb["b_proof"]), dl(mb["beta_tag_proof"])), o.DecryptionKey(B(d["dk"]["p"]), B(d["dk"]["q"])), S(d["a"]))
+    assert got is not None and got[0] == S(d["expected_alpha"]) and (got[0] + S(d["beta"])) % o.Q == S(d["expected_alpha_plus_beta"])
