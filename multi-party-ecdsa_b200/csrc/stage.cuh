@@ -15,7 +15,8 @@ namespace {
 struct Stage {
     tecdsa_ctx* c;
     int mem;
-    std::vector<void*> scratch;
+    struct Scratch { void* p; size_t bytes; };
+    std::vector<Scratch> scratch;
     struct Back { void* host; void* dev; size_t bytes; };
     std::vector<Back> back;
     int err = 0;
@@ -23,7 +24,7 @@ struct Stage {
     void* alloc(size_t bytes) {
         void* p = nullptr;
         if (cudaMallocAsync(&p, bytes ? bytes : 16, c->stream) != cudaSuccess) { err = tecdsa_fail(TECDSA_E_NOMEM, "cudaMallocAsync"); return nullptr; }
-        scratch.push_back(p);
+        scratch.push_back({p, bytes ? bytes : 16});
         return p;
     }
     template <typename T> const T* in(const T* p, size_t n) {
@@ -42,7 +43,9 @@ struct Stage {
     int finish() {
         for (auto& b : back)
             if (cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) err = tecdsa_fail(TECDSA_E_CUDA, "D2H copy");
-        for (void* p : scratch) cudaFreeAsync(p, c->stream);
+        // staged inputs, intermediates and results can all hold secrets (nonces, shares, plaintexts): wipe before the memory goes
+        // back to the stream-ordered pool, as the reference zeroizes its witnesses on drop (range_proofs.rs:26-27)
+        for (const Scratch& b : scratch) { cudaMemsetAsync(b.p, 0, b.bytes, c->stream); cudaFreeAsync(b.p, c->stream); }
         scratch.clear();
         if (mem == TECDSA_HOST) {
             cudaError_t e = cudaStreamSynchronize(c->stream);
