@@ -719,3 +719,32 @@ def test_gg18_key_generation_then_signing_on_gpu(engine, pkg, keyset):
     finally:
         kmod.vss_share = orig
     assert list(out3["status"]) == [0, 0, 0, 0, 0, pkg.ST_INVALID_SS]
+
+
+@pytest.mark.gpu
+def test_lindell17_bulk_parity_on_gpu(engine, pkg, keyset):
+    """384 two-party signatures (random + boundary inputs: k = 1, k = q - 1, message = 0 and 2^256 - 1, rho = 0 and q^2 - 1, x2 = q - 1) against the
+    oracle, bit for bit, every one verified by the reference's `verify` on the device and a sample under OpenSSL"""
+    from mpecdsa_b200 import gg20, lindell17 as L
+    rng = random.Random(0xB17C)
+    n = 384
+    c = _l17_case(keyset, rng, n)
+    edge = [dict(k1=1), dict(k2=1), dict(k1=Q - 1, k2=Q - 1), dict(msg=0), dict(msg=(1 << 256) - 1), dict(rho=0), dict(rho=Q * Q - 1), dict(x2=Q - 1)]
+    for i, e in enumerate(edge):
+        for f, v in e.items():
+            c[f][i] = v
+    c["pub"] = [o.pt_mul(G, a * b % Q) for a, b in zip(c["x1"], c["x2"])]
+    ks = gg20.KeySets(engine, [keyset])
+    n_list = [keyset[r].dk.p * keyset[r].dk.q for r in range(3)]
+    R1, R2 = engine.secp_mul(None, c["k1"]), engine.secp_mul(None, c["k2"])
+    c3, st = L.p2_partial_sig(engine, n_list, c["rows"], c["c_key"], c["x2"], c["k2"], R1, c["msg"], c["rho"], c["r_enc"])
+    assert not st.any()
+    r, s, rec, st = L.p1_sign(engine, ks, c["rows"], c3, c["k1"], R2)
+    assert not st.any()
+    assert not L.verify(engine, r, s, c["pub"], c["msg"]).any()
+    for i in list(range(len(edge))) + list(range(len(edge), n, 7)):
+        want_c3 = l17.p2_partial_sig(c["eks"][i], c["c_key"][i], c["x2"][i], c["k2"][i], R1[i], c["msg"][i], c["rho"][i], c["r_enc"][i])
+        assert c3[i] == want_c3, i
+        assert (r[i], s[i], int(rec[i])) == l17.p1_sign(c["dks"][i], want_c3, c["k1"][i], R2[i]), i
+    assert all(_ecdsa_ok(r[i], s[i], c["pub"][i], c["msg"][i]) for i in range(0, n, 16))
+    ks.free()
